@@ -1,0 +1,257 @@
+#!/usr/bin/env python
+"""bench.py -- steps/sec of the blub fluid step on B200 + PCG roofline + CPU baseline (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl blub|reference] [--workload dam_256]
+
+A "step" is one HybridFluid::step (P2G, PCG solve, G2P/advection, density rhs, PCG solve, particle correction) over the
+synthetic 256^3 / 16,387,064-particle dam break that BASELINE.json's metric is quoted on.  N > 1 (torchrun, one rank per
+GPU): every rank advances its own replica of the scene (the path has no cross-GPU exchange yet), `value` = ranks * steps/s.
+`--impl reference`: the reference (Rust + wgpu/Vulkan) cannot run on this image, so this arm times the CPU restatement of
+its algorithm (oracle/) on the host cores -- the only place besides cpu_baseline where bench.py executes oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "simulation steps/sec"
+SCENES = os.path.join(ROOT, "tests", "golden", "scenes")
+
+
+def scene_path(name):
+    return os.path.join(SCENES, name + ".json")
+
+
+def workload_desc(name):
+    sc = json.load(open(scene_path(name)))
+    d = sc["fluid"]["grid_dimension"]
+    return sc, f"{name}: {d['x']}x{d['y']}x{d['z']} grid"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def pcg_roofline(device, n=256, reps=5):
+    """SURVEY 8(d) microbench: n^3 grid, all interior cells FLUID, rhs ~ U[-1,1) (seed 1234) mean-removed, tolerance 0 so
+    all 33 iterations run; algorithmic bytes = (42 * 33 + 21) * N per solve."""
+    import numpy as np
+
+    import blub_b200
+    from blub_b200 import fluid as F
+
+    f = blub_b200.HybridFluid(n, n, n, 8, device=device)
+    m = np.zeros((n, n, n), dtype=np.int8)
+    m[1:-1, 1:-1, 1:-1] = 1
+    rng = np.random.default_rng(1234)
+    b = rng.uniform(-1.0, 1.0, (n, n, n)).astype(np.float32)
+    b -= b[m == 1].mean(dtype=np.float64).astype(np.float32)
+    b[m != 1] = 0
+    f.upload_grid(F.TAP_MARKER, m)
+    f.upload_grid(F.TAP_RESIDUAL, b)
+    f.set_solver_config(0, error_tolerance=0.0, max_num_iterations=32, error_check_frequency=4)
+    dt = F.DT_120HZ
+    f.time_solve(0, dt, 2)  # warm-up
+    ms = sorted(f.time_solve(0, dt, reps))
+    t = ms[len(ms) // 2] * 1e-3
+    cells = n ** 3
+    bytes_alg = (42 * 33 + 21) * cells
+    peaks = {}
+    src = "fallback 6650 GB/s (B200_PROFILING.md)"
+    peak = 6650.0
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+        peak = float(peaks.get("hbm_gbs", peak))
+        src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "pcg_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_solve")
+    ach = bytes_alg / t / 1e9
+    e, it = f.last_solve(0)
+    f.close()
+    return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
+            "kernel": "PCG solve (init + 33 x {dot, update, search})", "grid": f"{n}^3 all-fluid", "ms_per_solve": round(t * 1e3, 4),
+            "algorithmic_bytes_per_solve": bytes_alg, "peak_source": src, "iterations": it}
+
+
+def cpu_baseline_sample(workload, steps):
+    """Oracle (CPU port of the reference's algorithm) timed on this box's host cores on `steps` steps of the workload."""
+    from oracle import oracle as O
+
+    f = O.fluid_from_scene(O.load_scene(scene_path(workload)))
+    f.step(O.DT_120HZ)  # first step pays page faults / first-touch; not timed
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f.step(O.DT_120HZ)
+    t = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    return {"value": round(steps / t, 5), "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of {workload} after 1 untimed step, OpenMP over {cores} host threads (advection and list build serial)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    sc, desc = workload_desc(args.workload)
+    f = O.fluid_from_scene(O.load_scene(scene_path(args.workload)))
+    for _ in range(args.warmup):
+        f.step(O.DT_120HZ)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        f.step(O.DT_120HZ)
+    t = time.perf_counter() - t0
+    v = args.steps / t
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 5), "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(1e3 * t / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "particles": f.num_particles, "note": "reference wgpu path cannot run here; CPU restatement (oracle/) on host cores"},
+            "cpu_baseline": {"value": round(v, 5), "unit": "steps/s", "cores": cores, "kind": "port", "sample": f"{args.steps} step(s) of {args.workload}"},
+            "e2e": {"value": round(v, 5), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="blub", choices=["blub", "reference"])
+    ap.add_argument("--workload", default="dam_256")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 2
+        args.warmup = args.warmup if args.warmup is not None else 1
+        return run_reference(args)
+    args.steps = args.steps if args.steps is not None else 100
+    args.warmup = args.warmup if args.warmup is not None else 10
+
+    import torch
+    import torch.distributed as dist
+
+    import blub_b200
+    from blub_b200 import fluid as F
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sc, desc = workload_desc(args.workload)
+    dt = F.DT_120HZ
+    fluid = blub_b200.HybridFluid.from_scene(scene_path(args.workload), device=local)
+    npart = fluid.num_particles
+    for _ in range(max(args.warmup, 3)):
+        fluid.step(dt)
+    fluid.synchronize()
+
+    # ---- device-timed region: K steps between CUDA events on the fluid's stream, barrier + sync on both sides --------
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = blub_b200.kernel_launch_count()
+    ms = fluid.time_steps(dt, args.steps)
+    launches = blub_b200.kernel_launch_count() - launches0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+
+    # ---- end-to-end through the C ABI: per step one pinned H2D parameter block, one 16-byte D2H statistics read, host sync --
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fluid.step(dt)
+        fluid.synchronize()
+        fluid.update_statistics()
+    fluid.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e.item())
+    stats = fluid.pressure_solver_stats(0)[-1], fluid.pressure_solver_stats(1)[-1]
+    fluid.close()
+
+    roof = cpu = None
+    if rank == 0 and not args.no_roofline:
+        roof = pcg_roofline(local)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample(args.workload, 1)
+    if rank == 0:
+        steps_per_s = world * args.steps / (ms_max * 1e-3)
+        line = {
+            "metric": METRIC, "value": round(steps_per_s, 3), "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": desc, "particles": npart, "dt": dt, "solver": "tol 0.1 / max 32 / check 4 (reference defaults)", "rebin_every": 60,
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one scene per GPU, no exchange)",
+                       "l2": "inputs larger than L2 (>= 1 GB of particle state, 64 MiB per grid volume)",
+                       "last_solver_stats": {"velocity": stats[0], "density": stats[1]}},
+            "clocks": clocks,
+            "e2e": {"value": round(world * args.steps / e2e_s, 3), "unit": "steps/s", "h2d_bytes_per_step": 36, "d2h_bytes_per_step": 16,
+                    "note": "blub_fluid_step + blub_fluid_synchronize + blub_fluid_update_statistics per step (host-timed)"},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,201 @@
+// blub_core.hpp -- C++ host side of libblubcore: the B200-native counterparts of the reference's
+// `HybridFluid` (src/simulation/hybrid_fluid.rs), `PressureSolver` and `PressureField`
+// (src/simulation/pressure_solver.rs).  Same method names, argument meaning and defaults; wgpu objects are replaced by
+// device pointers and one CUDA stream.  The C ABI in include/blub_fluid.h is a thin shim over these classes.
+#pragma once
+#include <deque>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace blub {
+
+// pressure_solver.rs:57-62
+struct SolverConfig {
+    float error_tolerance = 0.1f;
+    int32_t max_num_iterations = 32;
+    int32_t error_check_frequency = 4;
+};
+// pressure_solver.rs:63-68
+struct SolverStatisticSample {
+    float error = 0.0f;
+    int32_t iteration_count = 0;
+};
+// hybrid_fluid.rs:19-22
+struct DynamicSettings {
+    uint32_t particle_rebinning_step_frequency = 60; // hybrid_fluid.rs:603-605
+};
+
+struct Quirks {
+    int precond_mode = 0; // 0: z = r/diag^2 ("LOD-1 fetch returns 0"), 1: as written with clamped LOD
+};
+
+// A padded device array of grid cells (see GridDim).
+template <class T> struct GridArray {
+    T *base = nullptr; // allocation
+    T *ptr = nullptr;  // cell 0
+    void alloc(const GridDim &g) {
+        size_t bytes = (size_t)(g.n + 2 * g.pad) * sizeof(T);
+        BLUB_CUDA_CHECK(cudaMalloc(&base, bytes));
+        BLUB_CUDA_CHECK(cudaMemset(base, 0, bytes));
+        ptr = base + g.pad;
+    }
+    void release() {
+        if (base) cudaFree(base);
+        base = ptr = nullptr;
+    }
+};
+
+class PressureSolver;
+
+// PressureField, pressure_solver.rs:84-210: one pressure volume (kept between steps = warm start), its solver
+// configuration, and the asynchronous {max error, iteration count} read-back ring.
+class PressureField {
+  public:
+    static constexpr size_t SOLVER_STATISTIC_HISTORY_LENGTH = 100; // pressure_solver.rs:101
+    static constexpr int NUM_PRESSURE_ERROR_BUFFER = 32;           // pressure_solver.rs:49
+
+    PressureField(const GridDim &grid, const SolverConfig &config);
+    ~PressureField();
+    PressureField(const PressureField &) = delete;
+
+    SolverConfig config;
+    std::deque<SolverStatisticSample> stats;
+    float *pressure() const { return pressure_.ptr; }
+
+    // PressureField::retrieve_new_error_samples, pressure_solver.rs:148-174 (never blocks)
+    void retrieve_new_error_samples();
+    // PressureField::enqueue_error_buffer_read, :176-191
+    void enqueue_error_buffer_read(cudaStream_t stream, float simulation_delta);
+    // blocking read of the device scalars (tests only)
+    void read_last_solve(cudaStream_t stream, float *max_error, int *iterations);
+
+    PcgScalars *scalars = nullptr; // device
+    bool touched = false;          // "timestamp_last_iteration == 0" of :601-603
+
+  private:
+    struct Pending {
+        cudaEvent_t event;
+        float *host; // pinned {max_error, float(num_iterations)}
+        float dt;
+        bool in_flight;
+    };
+    GridArray<float> pressure_;
+    std::vector<Pending> ring_;
+    std::deque<int> pending_;
+    std::vector<int> unused_;
+    float *pinned_ = nullptr;
+};
+
+// PressureSolver, pressure_solver.rs:22-47,228-729: scratch volumes shared by both solves and the PCG recording.
+class PressureSolver {
+  public:
+    PressureSolver(const GridDim &grid);
+    ~PressureSolver();
+    PressureSolver(const PressureSolver &) = delete;
+
+    float *residual() const { return residual_.ptr; } // the rhs is written straight into it (hybrid_fluid.rs:836-838)
+
+    // PressureSolver::solve, pressure_solver.rs:591-729.  Enqueue-only.
+    void solve(cudaStream_t stream, PressureField &field, int which, const int8_t *marker, const StepParams *dparams,
+               const Quirks &quirks);
+
+  private:
+    GridDim grid_;
+    GridArray<float> residual_, search_, aux_, aux_temp_;
+    float *partials_ = nullptr; // per-block partial sums / maxima, 2 * max_blocks
+    int num_blocks_ = 0;
+};
+
+// HybridFluid, hybrid_fluid.rs:24-72,92-977
+class HybridFluid {
+  public:
+    static constexpr uint32_t PARTICLES_PER_GRID_CELL = 8; // hybrid_fluid.rs:90
+
+    HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num_particles, int device, cudaStream_t stream);
+    ~HybridFluid();
+    HybridFluid(const HybridFluid &) = delete;
+
+    // returns true when the cube was truncated to max_num_particles (hybrid_fluid.rs:627-633)
+    bool add_fluid_cube(const float min_grid[3], const float max_grid[3]);
+    void set_gravity_grid(const float g[3]) { gravity_[0] = g[0]; gravity_[1] = g[1]; gravity_[2] = g[2]; }
+    uint32_t num_particles() const { return num_particles_; }
+    uint32_t num_active_particles() const { return num_particles_; }
+    const GridDim &grid_dimension() const { return grid_; }
+    SolverConfig &pressure_solver_config_velocity() { return field_velocity_->config; }
+    SolverConfig &pressure_solver_config_density() { return field_density_->config; }
+    DynamicSettings &dynamic_settings() { return dynamic_settings_; }
+    const std::deque<SolverStatisticSample> &pressure_solver_stats_velocity() const { return field_velocity_->stats; }
+    const std::deque<SolverStatisticSample> &pressure_solver_stats_density() const { return field_density_->stats; }
+    void update_statistics();
+    void set_solid_voxels(const void *rgba16f) { voxels_ = static_cast<const uint2 *>(rgba16f); }
+    void step(double simulation_delta_seconds);
+    void step_stages(double simulation_delta_seconds, int from, int to);
+    void solve_only(int which, double simulation_delta_seconds);
+    void synchronize();
+
+    Quirks quirks;
+
+    // raw views (renderer bind group, hybrid_fluid.rs:351-369) and test taps
+    float4 *particles_position() const { return pos_[cur_]; }
+    float4 *particles_row(int c) const { return row_[c]; }
+    float *grid_velocity(int c) const { return u_[c].ptr; }
+    int8_t *marker() const { return marker_.ptr; }
+    PressureField &field(int which) { return which == 0 ? *field_velocity_ : *field_density_; }
+    PressureSolver &solver() { return *solver_; }
+    cudaStream_t stream() const { return stream_; }
+    int device() const { return device_; }
+    uint32_t max_num_particles() const { return max_num_particles_; }
+    void set_particles(uint32_t count, const float *pos4, const float *vx4, const float *vy4, const float *vz4);
+
+  private:
+    void upload_step_params(float dt);
+    void run_stage(int stage, float dt);
+
+    GridDim grid_;
+    int device_;
+    cudaStream_t stream_;
+    bool owns_stream_;
+    uint32_t max_num_particles_, num_particles_ = 0;
+    float gravity_[3] = {0, 0, 0};
+    uint32_t step_counter_ = 0;
+    DynamicSettings dynamic_settings_;
+
+    float4 *pos_[2] = {nullptr, nullptr}; // ping-pong for the binning reorder
+    int cur_ = 0;
+    float4 *row_[3] = {nullptr, nullptr, nullptr};
+    GridArray<float> u_[3], weight_[3], density_;
+    GridArray<int8_t> marker_;
+    uint32_t *cell_count_ = nullptr; // binning: per-cell counters / offsets
+    uint32_t *block_sums_ = nullptr;
+    const uint2 *voxels_ = nullptr;
+
+    std::unique_ptr<PressureSolver> solver_;
+    std::unique_ptr<PressureField> field_velocity_, field_density_;
+
+    StepParams *params_dev_ = nullptr;
+    StepParams *params_host_ = nullptr; // pinned ring of 64
+    uint32_t step_param_slot_ = 0;
+    cudaEvent_t param_events_[64] = {};
+};
+
+// scene JSON (src/scene/mod.rs:19-43)
+struct SceneBox {
+    float min[3], max[3];
+};
+struct SceneConfig {
+    float gravity[3] = {0, 0, 0};
+    float world_position[3] = {0, 0, 0};
+    float grid_to_world_scale = 1.0f;
+    uint32_t grid_dimension[3] = {0, 0, 0};
+    uint32_t max_num_particles = 0;
+    std::vector<SceneBox> fluid_cubes;
+    uint32_t num_static_objects = 0;
+};
+SceneConfig parse_scene_file(const std::string &path);
+// Scene::create_fluid_from_config, src/scene/mod.rs:109-144
+std::unique_ptr<HybridFluid> create_fluid_from_config(const SceneConfig &cfg, int device, cudaStream_t stream);
+
+} // namespace blub

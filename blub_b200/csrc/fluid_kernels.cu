@@ -1,0 +1,663 @@
+// fluid_kernels.cu -- every kernel of the fluid step except the pressure solve (sm_100a).
+//
+// Reference counterparts (relative to /root/reference/shader/simulation): transfer_clear.comp,
+// transfer_build_linkedlist.comp, transfer_set_boundary_marker.comp, transfer_gather_velocity.comp,
+// divergence_compute.comp, divergence_remove.comp, extrapolate_velocity.comp, advect_particles.comp,
+// density_projection_{gather_error,position_change,correct_particles}.comp, particle_binning_*.comp.
+//
+// Not a port: the reference threads per-dual-cell linked lists through the particle buffer and gathers them with
+// 729-thread groups in lock-step rounds (capped at 12 / 32 entries).  Here particle->grid transfers are scatters
+// (RED.ADD.F32 into num/weight volumes, then one normalisation pass), which needs no lists, has no cap and touches each
+// particle once; binning is a counting sort with a work-efficient scan and ping-pong buffers (no copy-back).
+#include "fluid_kernels.hpp"
+
+namespace blub {
+namespace {
+
+constexpr int PT = 256; // threads per block for particle and cell kernels
+
+__device__ __forceinline__ int64_t lin(const GridDim &g, int x, int y, int z) { return ((int64_t)z * g.ny + y) * g.nx + x; }
+__device__ __forceinline__ void cell_of(const GridDim &g, int64_t i, int &x, int &y, int &z) {
+    x = (int)(i % g.nx);
+    int64_t t = i / g.nx;
+    y = (int)(t % g.ny);
+    z = (int)(t / g.ny);
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
+__device__ __forceinline__ float signf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+
+// ------------------------------------------------------------------------------------------------ P2G
+// One thread per particle.  For component c the particle lies in dual cell d = trunc(pos - off_c), off_c = 0.5 except
+// 1.0 on axis c (transfer_build_linkedlist.comp:21-23), and contributes to the eight faces d + {0,1}^3 -- exactly the
+// set of (face, particle) pairs the reference's gather visits (transfer_gather_velocity.comp:39-97) -- with
+//   weight = prod_k sat(1 - |q_k - pos_k|),  value = row_c . (q - pos, 1)          (:23-31)
+// MARK: also set marker[trunc(pos)] = FLUID (transfer_build_linkedlist.comp:17-19).
+template <bool MARK>
+__global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepParams *__restrict__ params,
+                                                         const float4 *__restrict__ pos, const float4 *__restrict__ rowx,
+                                                         const float4 *__restrict__ rowy, const float4 *__restrict__ rowz,
+                                                         float *__restrict__ ux, float *__restrict__ uy, float *__restrict__ uz,
+                                                         float *__restrict__ wx, float *__restrict__ wy, float *__restrict__ wz,
+                                                         int8_t *__restrict__ marker) {
+    const uint32_t i = blockIdx.x * PT + threadIdx.x;
+    if (i >= params->num_particles) return;
+    const float4 p = pos[i];
+    if (MARK) marker[lin(g, (int)p.x, (int)p.y, (int)p.z)] = (int8_t)CELL_FLUID;
+    const float4 rows[3] = {rowx[i], rowy[i], rowz[i]};
+    float *const num[3] = {ux, uy, uz};
+    float *const den[3] = {wx, wy, wz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float ox = c == 0 ? 1.0f : 0.5f, oy = c == 1 ? 1.0f : 0.5f, oz = c == 2 ? 1.0f : 0.5f;
+        const int dx = (int)(p.x - ox), dy = (int)(p.y - oy), dz = (int)(p.z - oz);
+        // sample point of face (dx,dy,dz): cell + 0.5 + 0.5 e_c
+        const float qx = (float)dx + ox, qy = (float)dy + oy, qz = (float)dz + oz;
+        const float4 r = rows[c];
+        float tx[2] = {qx - p.x, qx + 1.0f - p.x}, ty[2] = {qy - p.y, qy + 1.0f - p.y}, tz[2] = {qz - p.z, qz + 1.0f - p.z};
+        float wxs[2] = {saturatef(1.0f - fabsf(tx[0])), saturatef(1.0f - fabsf(tx[1]))};
+        float wys[2] = {saturatef(1.0f - fabsf(ty[0])), saturatef(1.0f - fabsf(ty[1]))};
+        float wzs[2] = {saturatef(1.0f - fabsf(tz[0])), saturatef(1.0f - fabsf(tz[1]))};
+        const int64_t base = lin(g, dx, dy, dz);
+#pragma unroll
+        for (int oz_ = 0; oz_ < 2; ++oz_)
+#pragma unroll
+            for (int oy_ = 0; oy_ < 2; ++oy_)
+#pragma unroll
+                for (int ox_ = 0; ox_ < 2; ++ox_) {
+                    const float w = wxs[ox_] * wys[oy_] * wzs[oz_];
+                    if (w <= 0.0f) continue;
+                    const float v = r.x * tx[ox_] + r.y * ty[oy_] + r.z * tz[oz_] + r.w;
+                    const int64_t f = base + ox_ + (int64_t)oy_ * g.sy + (int64_t)oz_ * g.sz;
+                    atomicAdd(num[c] + f, w * v);
+                    atomicAdd(den[c] + f, w);
+                }
+    }
+}
+
+// transfer_set_boundary_marker.comp:11-20
+__global__ void __launch_bounds__(PT) boundary_marker_kernel(GridDim g, int8_t *__restrict__ marker, const uint2 *__restrict__ vox) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (i >= g.n) return;
+    int x, y, z;
+    cell_of(g, i, x, y, z);
+    if (x == 0 || y == 0 || z == 0 || x == g.nx - 1 || y == g.ny - 1 || z == g.nz - 1) {
+        marker[i] = (int8_t)CELL_SOLID;
+    } else if (vox != nullptr) {
+        if (load_voxel(vox, i).w != 0.0f) marker[i] = (int8_t)CELL_SOLID;
+    }
+}
+
+// Normalisation + global forces + "don't flow into solid": transfer_gather_velocity.comp:116-127.
+// Faces that touch no FLUID cell are written 0 here (the reference leaves them stale; never observable).
+__global__ void __launch_bounds__(PT) p2g_normalize_kernel(GridDim g, const StepParams *__restrict__ params,
+                                                           const int8_t *__restrict__ marker, float *__restrict__ ux,
+                                                           float *__restrict__ uy, float *__restrict__ uz,
+                                                           const float *__restrict__ wx, const float *__restrict__ wy,
+                                                           const float *__restrict__ wz) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (i >= g.n) return;
+    const int ma = marker[i];
+    const int mb[3] = {marker[i + 1], marker[i + g.sy], marker[i + g.sz]};
+    float *const u[3] = {ux, uy, uz};
+    const float *const w[3] = {wx, wy, wz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float out = 0.0f;
+        if (ma == CELL_FLUID || mb[c] == CELL_FLUID) {
+            if (ma != CELL_SOLID && mb[c] != CELL_SOLID) {
+                float v = u[c][i];
+                const float wt = w[c][i];
+                if (wt > 0.0f) v /= wt;
+                out = v + params->gravity_dt[c];
+            }
+            u[c][i] = out;
+        } else {
+            u[c][i] = 0.0f;
+        }
+    }
+}
+
+// divergence_compute.comp:28-86
+__global__ void __launch_bounds__(PT) divergence_compute_kernel(GridDim g, const int8_t *__restrict__ marker,
+                                                                const float *__restrict__ ux, const float *__restrict__ uy,
+                                                                const float *__restrict__ uz, const uint2 *__restrict__ vox,
+                                                                float *__restrict__ rhs) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (i >= g.n) return;
+    if (marker[i] != CELL_FLUID) return;
+    const float px = ux[i], py = uy[i], pz = uz[i];
+    const float nx = ux[i - 1], ny = uy[i - g.sy], nz = uz[i - g.sz];
+    float d = px - nx;
+    d += py - ny;
+    d += pz - nz;
+    if (marker[i - 1] == CELL_SOLID) d += nx - load_voxel(vox, i - 1).x;
+    if (marker[i - g.sy] == CELL_SOLID) d += ny - load_voxel(vox, i - g.sy).y;
+    if (marker[i - g.sz] == CELL_SOLID) d += nz - load_voxel(vox, i - g.sz).z;
+    if (marker[i + 1] == CELL_SOLID) d -= px - load_voxel(vox, i + 1).x;
+    if (marker[i + g.sy] == CELL_SOLID) d -= py - load_voxel(vox, i + g.sy).y;
+    if (marker[i + g.sz] == CELL_SOLID) d -= pz - load_voxel(vox, i + g.sz).z;
+    rhs[i] = d;
+}
+
+// divergence_remove.comp:19-49
+__global__ void __launch_bounds__(PT) divergence_remove_kernel(GridDim g, const int8_t *__restrict__ marker,
+                                                               const float *__restrict__ p, const uint2 *__restrict__ vox,
+                                                               float *__restrict__ ux, float *__restrict__ uy, float *__restrict__ uz) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (i >= g.n) return;
+    int x, y, z;
+    cell_of(g, i, x, y, z);
+    const int mc = marker[i];
+    const float pc = mc == CELL_FLUID ? p[i] : 0.0f;
+    float *const u[3] = {ux, uy, uz};
+    const int64_t nb[3] = {i + 1, i + g.sy, i + g.sz};
+    const bool inb[3] = {x + 1 < g.nx, y + 1 < g.ny, z + 1 < g.nz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int mn = inb[c] ? marker[nb[c]] : CELL_SOLID;
+        float v = 0.0f;
+        if (mc == CELL_FLUID || mn == CELL_FLUID) {
+            if (mc == CELL_SOLID) {
+                const Voxel s = load_voxel(vox, i);
+                v = c == 0 ? s.x : (c == 1 ? s.y : s.z);
+            } else if (mn == CELL_SOLID) {
+                Voxel s = {0, 0, 0, 0};
+                if (inb[c]) s = load_voxel(vox, nb[c]);
+                v = c == 0 ? s.x : (c == 1 ? s.y : s.z);
+            } else {
+                const float pn = mn == CELL_FLUID ? p[nb[c]] : 0.0f;
+                v = u[c][i] - (pc - pn);
+            }
+        }
+        u[c][i] = v;
+    }
+}
+
+// density_projection_position_change.comp:18-51 (writes the displacement field INTO the velocity volumes)
+__global__ void __launch_bounds__(PT) position_change_kernel(GridDim g, const StepParams *__restrict__ params,
+                                                             const int8_t *__restrict__ marker, const float *__restrict__ p,
+                                                             float *__restrict__ ux, float *__restrict__ uy, float *__restrict__ uz) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (i >= g.n) return;
+    int x, y, z;
+    cell_of(g, i, x, y, z);
+    const float dt = params->dt;
+    const int mc = marker[i];
+    const float pc = mc == CELL_FLUID ? p[i] : 0.0f;
+    float *const u[3] = {ux, uy, uz};
+    const int64_t nb[3] = {i + 1, i + g.sy, i + g.sz};
+    const bool inb[3] = {x + 1 < g.nx, y + 1 < g.ny, z + 1 < g.nz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int mn = inb[c] ? marker[nb[c]] : CELL_SOLID;
+        const float pn = mn == CELL_FLUID ? p[nb[c]] : 0.0f;
+        float d = (pn - pc) * dt;
+        if (mc == CELL_SOLID || mn == CELL_SOLID) d = 0.0f;
+        u[c][i] = d;
+    }
+}
+
+// extrapolate_velocity.comp:26-90.  In place: only invalid faces are written, only valid faces are read.
+__device__ __forceinline__ bool valid_velocity(const GridDim &g, const int8_t *__restrict__ marker, int x, int y, int z, int c) {
+    if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz) return false;
+    const int64_t i = lin(g, x, y, z);
+    if (marker[i] == CELL_FLUID) return true;
+    const int64_t n = i + (c == 0 ? 1 : (c == 1 ? g.sy : g.sz));
+    const bool in = c == 0 ? x + 1 < g.nx : (c == 1 ? y + 1 < g.ny : z + 1 < g.nz);
+    return in && marker[n] == CELL_FLUID;
+}
+__global__ void __launch_bounds__(PT) extrapolate_kernel(GridDim g, const int8_t *__restrict__ marker, float *__restrict__ ux,
+                                                         float *__restrict__ uy, float *__restrict__ uz) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (i >= g.n) return;
+    if (marker[i] == CELL_FLUID) return;
+    int x, y, z;
+    cell_of(g, i, x, y, z);
+    float *const u[3] = {ux, uy, uz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const bool in = c == 0 ? x + 1 < g.nx : (c == 1 ? y + 1 < g.ny : z + 1 < g.nz);
+        const int64_t n = i + (c == 0 ? 1 : (c == 1 ? g.sy : g.sz));
+        if (in && marker[n] == CELL_FLUID) continue;
+        // in-plane axes, first one fastest (order of the velocityContribution lists in the shader)
+        const int a = c == 0 ? 1 : 0, b = c == 2 ? 1 : 2;
+        float numv = 0.0f, avg = 0.0f;
+        for (int ob = -1; ob <= 1; ++ob)
+            for (int oa = -1; oa <= 1; ++oa) {
+                if (oa == 0 && ob == 0) continue;
+                int h[3] = {x, y, z};
+                h[a] += oa;
+                h[b] += ob;
+                if (valid_velocity(g, marker, h[0], h[1], h[2], c)) {
+                    numv += 1.0f;
+                    avg += u[c][lin(g, h[0], h[1], h[2])];
+                }
+            }
+        if (numv > 0.0f) u[c][i] = avg / numv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ G2P + advection
+__device__ __forceinline__ Voxel voxel_point_clamp(const GridDim &g, const uint2 *__restrict__ vox, float px, float py, float pz) {
+    // texture(sampler3D(SceneVoxelization, SamplerPointClamp), pos / gridSize): nearest texel, clamp to edge
+    const int x = clampi((int)floorf(px), 0, g.nx - 1), y = clampi((int)floorf(py), 0, g.ny - 1), z = clampi((int)floorf(pz), 0, g.nz - 1);
+    return load_voxel(vox, lin(g, x, y, z));
+}
+__device__ __forceinline__ float voxel_w_trilinear(const GridDim &g, const uint2 *__restrict__ vox, float ux, float uy, float uz) {
+    const float cx = ux - 0.5f, cy = uy - 0.5f, cz = uz - 0.5f;
+    const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+    const float tx = cx - fx, ty = cy - fy, tz = cz - fz;
+    const int x0 = clampi((int)fx, 0, g.nx - 1), x1 = clampi((int)fx + 1, 0, g.nx - 1);
+    const int y0 = clampi((int)fy, 0, g.ny - 1), y1 = clampi((int)fy + 1, 0, g.ny - 1);
+    const int z0 = clampi((int)fz, 0, g.nz - 1), z1 = clampi((int)fz + 1, 0, g.nz - 1);
+    const float c00 = mixf(load_voxel(vox, lin(g, x0, y0, z0)).w, load_voxel(vox, lin(g, x1, y0, z0)).w, tx);
+    const float c10 = mixf(load_voxel(vox, lin(g, x0, y1, z0)).w, load_voxel(vox, lin(g, x1, y1, z0)).w, tx);
+    const float c01 = mixf(load_voxel(vox, lin(g, x0, y0, z1)).w, load_voxel(vox, lin(g, x1, y0, z1)).w, tx);
+    const float c11 = mixf(load_voxel(vox, lin(g, x0, y1, z1)).w, load_voxel(vox, lin(g, x1, y1, z1)).w, tx);
+    return mixf(mixf(c00, c10, ty), mixf(c01, c11, ty), tz);
+}
+__device__ __forceinline__ float grid_trilinear_clamp(const GridDim &g, const float *__restrict__ vol, float ux, float uy, float uz) {
+    const float cx = ux - 0.5f, cy = uy - 0.5f, cz = uz - 0.5f;
+    const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+    const float tx = cx - fx, ty = cy - fy, tz = cz - fz;
+    const int x0 = clampi((int)fx, 0, g.nx - 1), x1 = clampi((int)fx + 1, 0, g.nx - 1);
+    const int y0 = clampi((int)fy, 0, g.ny - 1), y1 = clampi((int)fy + 1, 0, g.ny - 1);
+    const int z0 = clampi((int)fz, 0, g.nz - 1), z1 = clampi((int)fz + 1, 0, g.nz - 1);
+    const float c00 = mixf(vol[lin(g, x0, y0, z0)], vol[lin(g, x1, y0, z0)], tx);
+    const float c10 = mixf(vol[lin(g, x0, y1, z0)], vol[lin(g, x1, y1, z0)], tx);
+    const float c01 = mixf(vol[lin(g, x0, y0, z1)], vol[lin(g, x1, y0, z1)], tx);
+    const float c11 = mixf(vol[lin(g, x0, y1, z1)], vol[lin(g, x1, y1, z1)], tx);
+    return mixf(mixf(c00, c10, ty), mixf(c01, c11, ty), tz);
+}
+
+struct Corners {
+    float v[8][3]; // corner order 000,100,010,110,001,101,011,111; [..][component]
+};
+__device__ __forceinline__ void trilerp3(const Corners &c, const float ix[3], const float iy[3], const float iz[3], float out[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { // InterpolateTrilinear, advect_particles.comp:19-23
+        const float a = mixf(mixf(c.v[0][k], c.v[1][k], ix[k]), mixf(c.v[2][k], c.v[3][k], ix[k]), iy[k]);
+        const float b = mixf(mixf(c.v[4][k], c.v[5][k], ix[k]), mixf(c.v[6][k], c.v[7][k], ix[k]), iy[k]);
+        out[k] = mixf(a, b, iz[k]);
+    }
+}
+
+// advect_particles.comp:35-194.  Writes position + the three APIC rows, marks the new cell FLUID (:175-178); the
+// linked-list rebuild of :179-181 has no counterpart (the density pass scatters).
+__global__ void __launch_bounds__(PT) advect_kernel(GridDim g, const StepParams *__restrict__ params, float4 *__restrict__ pos,
+                                                    float4 *__restrict__ rowx, float4 *__restrict__ rowy, float4 *__restrict__ rowz,
+                                                    const float *__restrict__ ux, const float *__restrict__ uy,
+                                                    const float *__restrict__ uz, const uint2 *__restrict__ vox,
+                                                    int8_t *__restrict__ marker) {
+    const uint32_t i = blockIdx.x * PT + threadIdx.x;
+    if (i >= params->num_particles) return;
+    const float dt = params->dt;
+    const float4 p4 = pos[i];
+    float x0[3] = {p4.x, p4.y, p4.z};
+    const int S[3] = {g.nx, g.ny, g.nz};
+    if (vox != nullptr) { // :45-64 particle "eaten" by a moving wall
+        const Voxel s = voxel_point_clamp(g, vox, x0[0], x0[1], x0[2]);
+        if (s.w > 0.0f) {
+            const float ax = fabsf(s.x), ay = fabsf(s.y), az = fabsf(s.z);
+            if (ax > ay) {
+                if (ax > az) x0[0] += signf(s.x); else x0[2] += signf(s.z);
+            } else {
+                if (ay > az) x0[1] += signf(s.y); else x0[2] += signf(s.z);
+            }
+        }
+    }
+    Corners cn;
+    float ix[3], iy[3], iz[3];
+    const float *const U[3] = {ux, uy, uz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { // :73-92
+        float op[3];
+        int lo[3], hi[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            op[k] = fmaxf(0.0f, x0[k] - (k == c ? 1.0f : 0.5f));
+            lo[k] = (int)op[k];
+            hi[k] = min(lo[k] + 1, S[k] - 1);
+            lo[k] = min(lo[k], S[k] - 1); // only reachable for particles outside the domain
+        }
+        const float *u = U[c];
+        cn.v[0][c] = u[lin(g, lo[0], lo[1], lo[2])]; cn.v[1][c] = u[lin(g, hi[0], lo[1], lo[2])];
+        cn.v[2][c] = u[lin(g, lo[0], hi[1], lo[2])]; cn.v[3][c] = u[lin(g, hi[0], hi[1], lo[2])];
+        cn.v[4][c] = u[lin(g, lo[0], lo[1], hi[2])]; cn.v[5][c] = u[lin(g, hi[0], lo[1], hi[2])];
+        cn.v[6][c] = u[lin(g, lo[0], hi[1], hi[2])]; cn.v[7][c] = u[lin(g, hi[0], hi[1], hi[2])];
+        ix[c] = fractf(op[0]); iy[c] = fractf(op[1]); iz[c] = fractf(op[2]);
+    }
+    float nv[3], cx[3], cy[3], cz[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { // :96-112
+        const float vx00 = mixf(cn.v[0][k], cn.v[1][k], ix[k]), vx01 = mixf(cn.v[4][k], cn.v[5][k], ix[k]);
+        const float vx10 = mixf(cn.v[2][k], cn.v[3][k], ix[k]), vx11 = mixf(cn.v[6][k], cn.v[7][k], ix[k]);
+        const float vxy0 = mixf(vx00, vx10, iy[k]), vxy1 = mixf(vx01, vx11, iy[k]);
+        nv[k] = mixf(vxy0, vxy1, iz[k]);
+        cx[k] = mixf(mixf(cn.v[1][k], cn.v[3][k], iy[k]), mixf(cn.v[5][k], cn.v[7][k], iy[k]), iz[k]) -
+                mixf(mixf(cn.v[0][k], cn.v[2][k], iy[k]), mixf(cn.v[4][k], cn.v[6][k], iy[k]), iz[k]);
+        cy[k] = mixf(vx10, vx11, iz[k]) - mixf(vx00, vx01, iz[k]);
+        cz[k] = vxy1 - vxy0;
+    }
+    // RK4 confined to the sampled cell, :116-126 (step.{x,y,z} is added to the {X,Y,Z} interpolants of every component)
+    float k2[3], k3[3], k4[3], ax[3], ay[3], az[3], st[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) st[k] = dt * 0.5f * nv[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ax[k] = saturatef(ix[k] + st[0]); ay[k] = saturatef(iy[k] + st[1]); az[k] = saturatef(iz[k] + st[2]); }
+    trilerp3(cn, ax, ay, az, k2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) st[k] = dt * 0.5f * k2[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ax[k] = saturatef(ix[k] + st[0]); ay[k] = saturatef(iy[k] + st[1]); az[k] = saturatef(iz[k] + st[2]); }
+    trilerp3(cn, ax, ay, az, k3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) st[k] = dt * k3[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ax[k] = saturatef(ix[k] + st[0]); ay[k] = saturatef(iy[k] + st[1]); az[k] = saturatef(iz[k] + st[2]); }
+    trilerp3(cn, ax, ay, az, k4);
+    float mv[3], x1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        mv[k] = dt * (1.0f / 6.0f) * (nv[k] + 2.0f * (k2[k] + k3[k]) + k4[k]);
+        x1[k] = x0[k] + mv[k];
+    }
+    const float hi[3] = {(float)g.nx - 1.001f, (float)g.ny - 1.001f, (float)g.nz - 1.001f};
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) hit = hit || (fminf(fmaxf(x1[k], 1.001f), hi[k]) != x1[k]);
+    if (!hit && vox != nullptr) hit = voxel_point_clamp(g, vox, x1[0], x1[1], x1[2]).w > 0.0f;
+    if (hit) { // :134-173
+        const float len = sqrtf(mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]) + 1e-10f;
+        const float dir[3] = {mv[0] / len, mv[1] / len, mv[2] / len};
+        float maxstep = len;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float pc = fractf(x0[k]);
+            maxstep = fminf(maxstep, (dir[k] > 0.0f ? pc : 1.0f - pc) / fabsf(dir[k]) - 0.001f);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mv[k] = dir[k] * maxstep;
+        if ((int)x0[0] == (int)x1[0] && (int)x0[1] == (int)x1[1] && (int)x0[2] == (int)x1[2] && vox != nullptr) {
+            float push[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float a[3] = {x1[0], x1[1], x1[2]}, b[3] = {x1[0], x1[1], x1[2]};
+                a[k] -= 1.0f;
+                b[k] += 1.0f;
+                push[k] = voxel_w_trilinear(g, vox, a[0], a[1], a[2]) - voxel_w_trilinear(g, vox, b[0], b[1], b[2]);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) mv[k] += push[k] * (dt * 50.0f);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            x1[k] = fminf(fmaxf(x0[k] + mv[k], 1.001f), hi[k]);
+            nv[k] = (dir[k] * maxstep) / dt;
+        }
+    }
+    marker[lin(g, clampi((int)x1[0], 0, g.nx - 1), clampi((int)x1[1], 0, g.ny - 1), clampi((int)x1[2], 0, g.nz - 1))] = (int8_t)CELL_FLUID;
+    pos[i] = make_float4(x1[0], x1[1], x1[2], p4.w);
+    rowx[i] = make_float4(cx[0], cx[1], cx[2], nv[0]); // :184-188 (B4: Jacobian columns stored as the rows)
+    rowy[i] = make_float4(cy[0], cy[1], cy[2], nv[1]);
+    rowz[i] = make_float4(cz[0], cz[1], cz[2], nv[2]);
+}
+
+// ------------------------------------------------------------------------------------------------ density projection
+// Scatter counterpart of density_projection_gather_error.comp:41-97: dual cell d = trunc(pos - 0.5), cell centres d + {0,1}^3.
+__global__ void __launch_bounds__(PT) density_scatter_kernel(GridDim g, const StepParams *__restrict__ params,
+                                                             const float4 *__restrict__ pos, float *__restrict__ density) {
+    const uint32_t i = blockIdx.x * PT + threadIdx.x;
+    if (i >= params->num_particles) return;
+    const float4 p = pos[i];
+    const int dx = (int)(p.x - 0.5f), dy = (int)(p.y - 0.5f), dz = (int)(p.z - 0.5f);
+    const float qx = (float)dx + 0.5f, qy = (float)dy + 0.5f, qz = (float)dz + 0.5f;
+    const float wx[2] = {saturatef(1.0f - fabsf(qx - p.x)), saturatef(1.0f - fabsf(qx + 1.0f - p.x))};
+    const float wy[2] = {saturatef(1.0f - fabsf(qy - p.y)), saturatef(1.0f - fabsf(qy + 1.0f - p.y))};
+    const float wz[2] = {saturatef(1.0f - fabsf(qz - p.z)), saturatef(1.0f - fabsf(qz + 1.0f - p.z))};
+    const int64_t base = lin(g, dx, dy, dz);
+#pragma unroll
+    for (int oz = 0; oz < 2; ++oz)
+#pragma unroll
+        for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+            for (int ox = 0; ox < 2; ++ox) {
+                const float w = wx[ox] * wy[oy] * wz[oz];
+                if (w > 0.0f) atomicAdd(density + base + ox + (int64_t)oy * g.sy + (int64_t)oz * g.sz, w);
+            }
+}
+
+// density_projection_gather_error.comp:99-199
+__global__ void __launch_bounds__(PT) density_rhs_kernel(GridDim g, const StepParams *__restrict__ params,
+                                                         const int8_t *__restrict__ marker, const float *__restrict__ density,
+                                                         float *__restrict__ rhs) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (i >= g.n) return;
+    if (marker[i] != CELL_FLUID) return;
+    float d = density[i];
+    const int m[6] = {marker[i + 1], marker[i + g.sy], marker[i + g.sz], marker[i - 1], marker[i - g.sy], marker[i - g.sz]};
+    bool any_air = false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        if (m[k] == CELL_SOLID) d += 0.5625f;
+        any_air = any_air || (m[k] == CELL_AIR);
+    }
+    if (any_air) d = fmaxf(8.0f, d);
+    d = 1.0f - d / 8.0f;
+    d = fminf(fmaxf(d, -0.5f), 0.5f);
+    d /= params->dt;
+    rhs[i] = d;
+}
+
+// density_projection_correct_particles.comp:25-73 (fp32 software trilinear instead of the 8-bit hardware filter)
+__global__ void __launch_bounds__(PT) correct_particles_kernel(GridDim g, const StepParams *__restrict__ params,
+                                                               float4 *__restrict__ pos, const int8_t *__restrict__ marker,
+                                                               const float *__restrict__ ux, const float *__restrict__ uy,
+                                                               const float *__restrict__ uz) {
+    const uint32_t i = blockIdx.x * PT + threadIdx.x;
+    if (i >= params->num_particles) return;
+    const float4 p4 = pos[i];
+    const float x0[3] = {p4.x, p4.y, p4.z};
+    float ch[3];
+    ch[0] = grid_trilinear_clamp(g, ux, fmaxf(0.0f, x0[0] - 0.5f), fmaxf(0.0f, x0[1]), fmaxf(0.0f, x0[2]));
+    ch[1] = grid_trilinear_clamp(g, uy, fmaxf(0.0f, x0[0]), fmaxf(0.0f, x0[1] - 0.5f), fmaxf(0.0f, x0[2]));
+    ch[2] = grid_trilinear_clamp(g, uz, fmaxf(0.0f, x0[0]), fmaxf(0.0f, x0[1]), fmaxf(0.0f, x0[2] - 0.5f));
+    float x1[3] = {x0[0] + ch[0], x0[1] + ch[1], x0[2] + ch[2]};
+    const float hi[3] = {(float)g.nx - 1.001f, (float)g.ny - 1.001f, (float)g.nz - 1.001f};
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) hit = hit || (fminf(fmaxf(x1[k], 1.001f), hi[k]) != x1[k]);
+    if (!hit) {
+        const int x = clampi((int)floorf(x1[0]), 0, g.nx - 1), y = clampi((int)floorf(x1[1]), 0, g.ny - 1), z = clampi((int)floorf(x1[2]), 0, g.nz - 1);
+        hit = marker[lin(g, x, y, z)] == CELL_SOLID;
+    }
+    if (hit) {
+        const float len = sqrtf(ch[0] * ch[0] + ch[1] * ch[1] + ch[2] * ch[2]) + 1e-10f;
+        const float dir[3] = {ch[0] / len, ch[1] / len, ch[2] / len};
+        float maxstep = len;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float pc = fractf(x0[k]);
+            maxstep = fminf(maxstep, (dir[k] > 0.0f ? pc : 1.0f - pc) / fabsf(dir[k]) - 0.001f);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) x1[k] = fminf(fmaxf(x0[k] + dir[k] * maxstep, 1.001f), hi[k]);
+    }
+    pos[i] = make_float4(x1[0], x1[1], x1[2], p4.w);
+}
+
+// ------------------------------------------------------------------------------------------------ binning
+// particle_binning_count.comp (guarded): rank inside the cell kept in pos.w
+__global__ void __launch_bounds__(PT) binning_count_kernel(GridDim g, const StepParams *__restrict__ params, float4 *__restrict__ pos,
+                                                           uint32_t *__restrict__ count) {
+    const uint32_t i = blockIdx.x * PT + threadIdx.x;
+    if (i >= params->num_particles) return;
+    float4 p = pos[i];
+    const int x = clampi((int)p.x, 0, g.nx - 1), y = clampi((int)p.y, 0, g.ny - 1), z = clampi((int)p.z, 0, g.nz - 1);
+    const uint32_t rank = atomicAdd(count + lin(g, x, y, z), 1u);
+    pos[i].w = __uint_as_float(rank);
+}
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8; // 2048 cells per block
+// phase 1: per-block totals
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint32_t *__restrict__ in, int64_t n, uint32_t *__restrict__ sums) {
+    __shared__ uint32_t sh[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_THREADS * SCAN_ITEMS + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) acc += in[base + k];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < SCAN_THREADS / 32; ++k) t += sh[k];
+        sums[blockIdx.x] = t;
+    }
+}
+// phase 2: exclusive scan of the block totals by one block (deterministic block order, unlike the reference's atomic
+// arrival order, particle_binning_prefixsum.comp:53-56)
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t *__restrict__ sums, int nblocks) {
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int idx = base + threadIdx.x;
+        const uint32_t v = idx < nblocks ? sums[idx] : 0u;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        const uint32_t incl = sh[threadIdx.x];
+        if (idx < nblocks) sums[idx] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+}
+// phase 3: exclusive scan inside each block + block base, written in place
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t *__restrict__ data, int64_t n, const uint32_t *__restrict__ sums) {
+    __shared__ uint32_t sh[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_THREADS * SCAN_ITEMS + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], acc = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < n ? data[base + k] : 0u;
+        acc += v[k];
+    }
+    uint32_t incl = acc;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sh[w] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int k = 0; k < w; ++k) wbase += sh[k];
+    uint32_t run = sums[blockIdx.x] + wbase + incl - acc;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) data[base + k] = run;
+        run += v[k];
+    }
+}
+// particle_binning_rewrite_particles.comp with exclusive offsets (the as-written inclusive - index is off by one, B2)
+__global__ void __launch_bounds__(PT) binning_scatter_kernel(GridDim g, const StepParams *__restrict__ params,
+                                                             const float4 *__restrict__ src, float4 *__restrict__ dst,
+                                                             const uint32_t *__restrict__ offsets) {
+    const uint32_t i = blockIdx.x * PT + threadIdx.x;
+    if (i >= params->num_particles) return;
+    const float4 p = src[i];
+    const int x = clampi((int)p.x, 0, g.nx - 1), y = clampi((int)p.y, 0, g.ny - 1), z = clampi((int)p.z, 0, g.nz - 1);
+    const uint32_t d = offsets[lin(g, x, y, z)] + __float_as_uint(p.w);
+    dst[d] = make_float4(p.x, p.y, p.z, 0.0f);
+}
+
+inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 1) / per_block); }
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------ launchers
+void launch_p2g(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float4 *const row[3],
+                float *const u[3], float *const w[3], int8_t *marker, const uint2 *vox) {
+    // transfer_clear.comp: marker <- AIR; the num / weight volumes replace the linked-list head volume
+    BLUB_CUDA_CHECK(cudaMemsetAsync(marker, 0xFF, (size_t)g.n, st));
+    for (int c = 0; c < 3; ++c) {
+        BLUB_CUDA_CHECK(cudaMemsetAsync(u[c], 0, (size_t)g.n * sizeof(float), st));
+        BLUB_CUDA_CHECK(cudaMemsetAsync(w[c], 0, (size_t)g.n * sizeof(float), st));
+    }
+    if (np_upper > 0)
+        BLUB_LAUNCH(p2g_scatter_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2],
+                    w[0], w[1], w[2], marker);
+    BLUB_LAUNCH(boundary_marker_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, vox);
+    BLUB_LAUNCH(p2g_normalize_kernel, blocks_for(g.n, PT), PT, 0, st, g, params, marker, u[0], u[1], u[2], w[0], w[1], w[2]);
+}
+
+void launch_divergence_compute(cudaStream_t st, const GridDim &g, const int8_t *marker, float *const u[3], const uint2 *vox, float *rhs) {
+    BLUB_LAUNCH(divergence_compute_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, u[0], u[1], u[2], vox, rhs);
+}
+
+void launch_divergence_remove(cudaStream_t st, const GridDim &g, const int8_t *marker, const float *p, const uint2 *vox, float *const u[3]) {
+    BLUB_LAUNCH(divergence_remove_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, p, vox, u[0], u[1], u[2]);
+}
+
+void launch_extrapolate(cudaStream_t st, const GridDim &g, const int8_t *marker, float *const u[3]) {
+    BLUB_LAUNCH(extrapolate_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, u[0], u[1], u[2]);
+}
+
+void launch_clear_marker(cudaStream_t st, const GridDim &g, int8_t *marker) {
+    BLUB_CUDA_CHECK(cudaMemsetAsync(marker, 0xFF, (size_t)g.n, st));
+}
+
+void launch_advect(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos, float4 *const row[3],
+                   float *const u[3], const uint2 *vox, int8_t *marker) {
+    if (np_upper == 0) return;
+    BLUB_LAUNCH(advect_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2], vox, marker);
+}
+
+void launch_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, const uint2 *vox) {
+    BLUB_LAUNCH(boundary_marker_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, vox);
+}
+
+void launch_density_rhs(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos,
+                        const int8_t *marker, float *density, float *rhs) {
+    BLUB_CUDA_CHECK(cudaMemsetAsync(density, 0, (size_t)g.n * sizeof(float), st));
+    if (np_upper > 0) BLUB_LAUNCH(density_scatter_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, density);
+    BLUB_LAUNCH(density_rhs_kernel, blocks_for(g.n, PT), PT, 0, st, g, params, marker, density, rhs);
+}
+
+void launch_position_change(cudaStream_t st, const GridDim &g, const StepParams *params, const int8_t *marker, const float *p, float *const u[3]) {
+    BLUB_LAUNCH(position_change_kernel, blocks_for(g.n, PT), PT, 0, st, g, params, marker, p, u[0], u[1], u[2]);
+}
+
+void launch_correct_particles(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos,
+                              const int8_t *marker, float *const u[3]) {
+    if (np_upper == 0) return;
+    BLUB_LAUNCH(correct_particles_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, marker, u[0], u[1], u[2]);
+}
+
+int binning_scan_blocks(const GridDim &g) { return blocks_for(g.n, SCAN_THREADS * SCAN_ITEMS); }
+
+void launch_binning(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *src, float4 *dst,
+                    uint32_t *cell_count, uint32_t *block_sums) {
+    if (np_upper == 0) return;
+    const int nb = binning_scan_blocks(g);
+    BLUB_CUDA_CHECK(cudaMemsetAsync(cell_count, 0, (size_t)g.n * sizeof(uint32_t), st));
+    BLUB_LAUNCH(binning_count_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, src, cell_count);
+    BLUB_LAUNCH(scan_block_sums_kernel, nb, SCAN_THREADS, 0, st, cell_count, g.n, block_sums);
+    BLUB_LAUNCH(scan_sums_kernel, 1, 1024, 0, st, block_sums, nb);
+    BLUB_LAUNCH(scan_apply_kernel, nb, SCAN_THREADS, 0, st, cell_count, g.n, block_sums);
+    BLUB_LAUNCH(binning_scatter_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, src, dst, cell_count);
+}
+
+} // namespace blub

@@ -1,0 +1,278 @@
+// hybrid_fluid.cu -- host side of the fluid: allocation, particle seeding and the recording of one step.
+// Counterpart of src/simulation/hybrid_fluid.rs (HybridFluid::{new, add_fluid_cube, step, ...}).
+#include <cmath>
+#include <cstring>
+
+#include "blub_core.hpp"
+#include "fluid_kernels.hpp"
+
+namespace blub {
+
+HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num_particles, int device, cudaStream_t stream)
+    : device_(device), stream_(stream), owns_stream_(false), max_num_particles_(max_num_particles) {
+    // the reference dispatches 8^3 groups without guards (hybrid_fluid.rs:735-741) and asserts N > 16384 (pressure_solver.rs:551)
+    if (nx == 0 || ny == 0 || nz == 0 || nx % 8 || ny % 8 || nz % 8) throw std::invalid_argument("grid dimensions must be positive multiples of 8");
+    if ((uint64_t)nx * ny * nz <= 16384) throw std::invalid_argument("grid must have more than 16384 cells");
+    if ((uint64_t)nx * ny * nz >= (1ull << 31)) throw std::invalid_argument("grid too large");
+    int count = 0;
+    BLUB_CUDA_CHECK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) throw CudaError("no such CUDA device");
+    BLUB_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BLUB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw CudaError(std::string("libblubcore is built for sm_100a only, found ") + prop.name);
+    if (stream_ == nullptr) {
+        BLUB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        owns_stream_ = true;
+    }
+    grid_ = make_grid((int)nx, (int)ny, (int)nz);
+    const size_t pbytes = ((size_t)max_num_particles + 64) * sizeof(float4);
+    for (int k = 0; k < 2; ++k) {
+        BLUB_CUDA_CHECK(cudaMalloc(&pos_[k], pbytes));
+        BLUB_CUDA_CHECK(cudaMemset(pos_[k], 0, pbytes));
+    }
+    for (int c = 0; c < 3; ++c) {
+        BLUB_CUDA_CHECK(cudaMalloc(&row_[c], pbytes));
+        BLUB_CUDA_CHECK(cudaMemset(row_[c], 0, pbytes));
+        u_[c].alloc(grid_);
+        weight_[c].alloc(grid_);
+    }
+    density_.alloc(grid_);
+    marker_.alloc(grid_);
+    BLUB_CUDA_CHECK(cudaMalloc(&cell_count_, (size_t)grid_.n * sizeof(uint32_t)));
+    BLUB_CUDA_CHECK(cudaMalloc(&block_sums_, (size_t)(binning_scan_blocks(grid_) + 1024) * sizeof(uint32_t)));
+    solver_.reset(new PressureSolver(grid_));
+    SolverConfig cfg; // defaults .1 / 32 / 4, hybrid_fluid.rs:253-257
+    field_velocity_.reset(new PressureField(grid_, cfg));
+    field_density_.reset(new PressureField(grid_, cfg));
+    BLUB_CUDA_CHECK(cudaMalloc(&params_dev_, sizeof(StepParams)));
+    BLUB_CUDA_CHECK(cudaMallocHost(&params_host_, sizeof(StepParams) * 64));
+    for (int k = 0; k < 64; ++k) BLUB_CUDA_CHECK(cudaEventCreateWithFlags(&param_events_[k], cudaEventDisableTiming));
+    BLUB_CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+HybridFluid::~HybridFluid() {
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    for (int k = 0; k < 2; ++k) cudaFree(pos_[k]);
+    for (int c = 0; c < 3; ++c) {
+        cudaFree(row_[c]);
+        u_[c].release();
+        weight_[c].release();
+    }
+    density_.release();
+    marker_.release();
+    cudaFree(cell_count_);
+    cudaFree(block_sums_);
+    solver_.reset();
+    field_velocity_.reset();
+    field_density_.reset();
+    cudaFree(params_dev_);
+    cudaFreeHost(params_host_);
+    for (int k = 0; k < 64; ++k) cudaEventDestroy(param_events_[k]);
+    if (owns_stream_) cudaStreamDestroy(stream_);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Particle seeding, hybrid_fluid.rs:609-678.  The jitter stream is rand 0.8.5 `SmallRng` (xoshiro256++ seeded from a
+// u64 through SplitMix64) drawing cgmath::Vector3<f32> as x, y, z with f32 = (next_u32 >> 8) * 2^-24 and next_u32 = high
+// half of next_u64 -- third-party crates that are not vendored in the reference checkout (Cargo.lock: rand 0.8.5,
+// rand_core 0.6.4, cgmath 0.18.0); restated from their published algorithms.
+namespace {
+struct Xoshiro256pp {
+    uint64_t s[4];
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    explicit Xoshiro256pp(uint64_t state) {
+        for (int i = 0; i < 4; ++i) {
+            state += 0x9e3779b97f4a7c15ull;
+            uint64_t z = state;
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+            s[i] = z ^ (z >> 31);
+        }
+    }
+    uint64_t next_u64() {
+        const uint64_t result = rotl(s[0] + s[3], 23) + s[0];
+        const uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return result;
+    }
+    float next_f32() { return (float)((uint32_t)(next_u64() >> 32) >> 8) * (1.0f / 16777216.0f); }
+};
+
+uint32_t clamp_to_grid(uint32_t dim, float v) { // hybrid_fluid.rs:609-617; Rust `as u32` saturates, NaN -> 0
+    uint32_t u = !(v > 0.0f) ? 0u : (v >= 4294967040.0f ? 0xFFFFFFFFu : (uint32_t)v);
+    uint32_t m = dim - 1 < u ? dim - 1 : u;
+    return m < 1 ? 1 : m;
+}
+} // namespace
+
+bool HybridFluid::add_fluid_cube(const float min_grid[3], const float max_grid[3]) {
+    BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    const uint32_t dim[3] = {(uint32_t)grid_.nx, (uint32_t)grid_.ny, (uint32_t)grid_.nz};
+    uint32_t mn[3], ext[3];
+    for (int k = 0; k < 3; ++k) {
+        mn[k] = clamp_to_grid(dim[k], min_grid[k]);
+        ext[k] = clamp_to_grid(dim[k], max_grid[k]) - mn[k]; // exclusive max corner; wraps like the reference if max < min
+    }
+    uint32_t num_new = ext[0] * ext[1] * ext[2] * PARTICLES_PER_GRID_CELL;
+    bool truncated = false;
+    if (max_num_particles_ < num_new + num_particles_) { // :627-633
+        num_new = max_num_particles_ - num_particles_;
+        truncated = true;
+    }
+    if (num_new == 0) return truncated;
+    Xoshiro256pp rng((uint64_t)(num_particles_ + num_new)); // :637
+    std::vector<float4> fresh(num_new);
+    for (uint32_t i = 0; i < num_new; ++i) {
+        const float cell[3] = {(float)(mn[0] + i / 8u % ext[0]), (float)(mn[1] + i / 8u / ext[0] % ext[1]), (float)(mn[2] + i / 8u / ext[0] / ext[1])};
+        const uint32_t s = i % 8u;
+        const float strat[3] = {(float)(s % 2u), (float)(s / 2u % 2u), (float)(s / 4u % 2u)};
+        float p[3];
+        for (int k = 0; k < 3; ++k) {
+            const float r = rng.next_f32();
+            p[k] = cell[k] + (strat[k] * 0.5f + r * 0.5f); // stratified jitter, :664-665
+        }
+        fresh[i] = make_float4(p[0], p[1], p[2], 0.0f);
+    }
+    BLUB_CUDA_CHECK(cudaMemcpyAsync(pos_[cur_] + num_particles_, fresh.data(), (size_t)num_new * sizeof(float4), cudaMemcpyHostToDevice, stream_));
+    BLUB_CUDA_CHECK(cudaStreamSynchronize(stream_)); // `fresh` is pageable: finish before it dies (queue.write_buffer semantics)
+    num_particles_ += num_new;
+    return truncated;
+}
+
+void HybridFluid::set_particles(uint32_t count, const float *pos4, const float *vx4, const float *vy4, const float *vz4) {
+    BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    if (count > max_num_particles_) throw std::invalid_argument("count exceeds max_num_particles");
+    const size_t bytes = (size_t)count * sizeof(float4);
+    BLUB_CUDA_CHECK(cudaMemcpyAsync(pos_[cur_], pos4, bytes, cudaMemcpyHostToDevice, stream_));
+    const float *rows[3] = {vx4, vy4, vz4};
+    for (int c = 0; c < 3; ++c) {
+        if (rows[c]) BLUB_CUDA_CHECK(cudaMemcpyAsync(row_[c], rows[c], bytes, cudaMemcpyHostToDevice, stream_));
+        else BLUB_CUDA_CHECK(cudaMemsetAsync(row_[c], 0, bytes, stream_));
+    }
+    BLUB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    num_particles_ = count;
+}
+
+void HybridFluid::update_statistics() {
+    // HybridFluid::update_statistics, :765-768 kicks map_async; retrieval happens at the next solve (:614).  Here both are
+    // the same non-blocking poll of the read-back ring.
+    BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    field_density_->retrieve_new_error_samples();
+    field_velocity_->retrieve_new_error_samples();
+}
+
+void HybridFluid::synchronize() {
+    BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    BLUB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+// "update uniforms", hybrid_fluid.rs:780-784: one small H2D copy from a pinned ring in front of every step.
+void HybridFluid::upload_step_params(float dt) {
+    static_assert(sizeof(StepParams) % 4 == 0, "");
+    const uint32_t slot = step_param_slot_++ % 64;
+    StepParams *h = params_host_ + slot;
+    // the copy reads the pinned slot when it EXECUTES: only block if the host is a full ring (64 steps) ahead of the GPU
+    BLUB_CUDA_CHECK(cudaEventSynchronize(param_events_[slot]));
+    h->dt = dt;
+    h->inv_dt = 1.0f / dt;
+    for (int c = 0; c < 3; ++c) h->gravity_dt[c] = gravity_[c] * dt;
+    h->tolerance[0] = field_velocity_->config.error_tolerance / dt; // pressure_solver.rs:193-201
+    h->tolerance[1] = field_density_->config.error_tolerance / dt;
+    h->num_particles = num_particles_;
+    BLUB_CUDA_CHECK(cudaMemcpyAsync(params_dev_, h, sizeof(StepParams), cudaMemcpyHostToDevice, stream_));
+    BLUB_CUDA_CHECK(cudaEventRecord(param_events_[slot], stream_));
+}
+
+// Stage numbering shared with oracle/blub_oracle.c:orc_step_stages (the order of hybrid_fluid.rs:798-974).
+void HybridFluid::run_stage(int stage, float dt) {
+    float *u[3] = {u_[0].ptr, u_[1].ptr, u_[2].ptr};
+    float *w[3] = {weight_[0].ptr, weight_[1].ptr, weight_[2].ptr};
+    const uint32_t np = num_particles_;
+    switch (stage) {
+    case 0: // transfer particle velocity to grid (:806-833)
+        launch_p2g(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, w, marker_.ptr, voxels_);
+        break;
+    case 1: // compute divergence -> PCG residual (:835-840)
+        launch_divergence_compute(stream_, grid_, marker_.ptr, u, voxels_, solver_->residual());
+        break;
+    case 2: // primary pressure solver (:843-852)
+        solver_->solve(stream_, *field_velocity_, 0, marker_.ptr, params_dev_, quirks);
+        field_velocity_->enqueue_error_buffer_read(stream_, dt);
+        break;
+    case 3: // particle binning every n-th step, including step 0 (:854-894)
+        if (dynamic_settings_.particle_rebinning_step_frequency != 0 && step_counter_ % dynamic_settings_.particle_rebinning_step_frequency == 0) {
+            launch_binning(stream_, grid_, params_dev_, np, pos_[cur_], pos_[1 - cur_], cell_count_, block_sums_);
+            if (np > 0) cur_ = 1 - cur_; // ping-pong instead of the reference's full-buffer copy-back (:884-892)
+        }
+        break;
+    case 4: // make velocity grid divergence free (:901-904)
+        launch_divergence_remove(stream_, grid_, marker_.ptr, field_velocity_->pressure(), voxels_, u);
+        break;
+    case 5: // extrapolate velocity grid (:906-909)
+        launch_extrapolate(stream_, grid_, marker_.ptr, u);
+        break;
+    case 6: // clear marker (& linked list) grids (:911-916)
+        launch_clear_marker(stream_, grid_, marker_.ptr);
+        break;
+    case 7: // advect particles (:917-921)
+        launch_advect(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, voxels_, marker_.ptr);
+        break;
+    case 8: // density projection: set boundary marker (:923-927)
+        launch_boundary_marker(stream_, grid_, marker_.ptr, voxels_);
+        break;
+    case 9: // density projection: compute density error (:928-932)
+        launch_density_rhs(stream_, grid_, params_dev_, np, pos_[cur_], marker_.ptr, density_.ptr, solver_->residual());
+        break;
+    case 10: // secondary pressure solver (:940-949)
+        solver_->solve(stream_, *field_density_, 1, marker_.ptr, params_dev_, quirks);
+        field_density_->enqueue_error_buffer_read(stream_, dt);
+        break;
+    case 11: // compute position change (:959-962)
+        launch_position_change(stream_, grid_, params_dev_, marker_.ptr, field_density_->pressure(), u);
+        break;
+    case 12: // extrapolate (:963-966)
+        launch_extrapolate(stream_, grid_, marker_.ptr, u);
+        break;
+    case 13: // correct particle density error (:968-972)
+        launch_correct_particles(stream_, grid_, params_dev_, np, pos_[cur_], marker_.ptr, u);
+        step_counter_ += 1;
+        break;
+    default: break;
+    }
+}
+
+void HybridFluid::step(double simulation_delta_seconds) { step_stages(simulation_delta_seconds, 0, 14); }
+
+void HybridFluid::step_stages(double simulation_delta_seconds, int from, int to) {
+    BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    const float dt = (float)simulation_delta_seconds; // Duration::as_secs_f32
+    if (!(dt > 0.0f)) throw std::invalid_argument("simulation delta must be positive");
+    upload_step_params(dt);
+    for (int s = from; s < to && s < 14; ++s) run_stage(s, dt);
+}
+
+void HybridFluid::solve_only(int which, double simulation_delta_seconds) {
+    BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    const float dt = (float)simulation_delta_seconds;
+    upload_step_params(dt);
+    solver_->solve(stream_, field(which), which, marker_.ptr, params_dev_, quirks);
+}
+
+std::unique_ptr<HybridFluid> create_fluid_from_config(const SceneConfig &cfg, int device, cudaStream_t stream) {
+    std::unique_ptr<HybridFluid> f(new HybridFluid(cfg.grid_dimension[0], cfg.grid_dimension[1], cfg.grid_dimension[2], cfg.max_num_particles, device, stream));
+    const float scale = cfg.grid_to_world_scale;
+    for (const SceneBox &b : cfg.fluid_cubes) { // src/scene/mod.rs:132-138
+        const float mn[3] = {b.min[0] / scale, b.min[1] / scale, b.min[2] / scale};
+        const float mx[3] = {b.max[0] / scale, b.max[1] / scale, b.max[2] / scale};
+        f->add_fluid_cube(mn, mx);
+    }
+    const float g[3] = {cfg.gravity[0] / scale, cfg.gravity[1] / scale, cfg.gravity[2] / scale}; // :139
+    f->set_gravity_grid(g);
+    return f;
+}
+
+} // namespace blub

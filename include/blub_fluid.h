@@ -1,0 +1,176 @@
+/*
+ * blub_fluid.h -- C ABI of libblubcore.so, the B200-native APIC/FLIP fluid-step core.
+ *
+ * Drop-in boundary for Wumpf/blub's `HybridFluid` (src/simulation/hybrid_fluid.rs) and its
+ * `PressureSolver`/`PressureField` (src/simulation/pressure_solver.rs).  The reference has no
+ * FFI/plugin layer: its narrowest seam is the Rust method set of `HybridFluid`, whose arguments are
+ * wgpu objects.  Every entry point below names the reference method it replaces (file:line relative
+ * to /root/reference); wgpu handles become plain device pointers, a CUDA stream and POD structs.
+ * INTEGRATION.md shows the Rust `extern "C"` block a maintainer would add.
+ *
+ * Conventions kept from the reference:
+ *   - positions in grid cells, velocities in cells/s, pressure pre-multiplied by dt/rho
+ *     (shader/simulation/divergence_compute.comp:4-5);
+ *   - the fluid owns all of its device memory; the solid-voxel volume is BORROWED and must outlive
+ *     the steps that use it (hybrid_fluid.rs:99,266);
+ *   - single host thread, one stream in submission order; `blub_fluid_step` only ENQUEUES work and
+ *     never blocks on the GPU (README.md:94-103); the only device->host traffic is the 8-byte solver
+ *     statistics read-back, which is asynchronous and may lag (pressure_solver.rs:148-209);
+ *   - the reference panics on set-up failure and only logs at run time; here every fallible call
+ *     returns an int code and nothing throws across the boundary.
+ * There is NO CPU fallback: every call fails with BLUB_ERR_CUDA if no usable sm_100 device exists.
+ */
+#ifndef BLUB_FLUID_H
+#define BLUB_FLUID_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLUB_OK 0
+#define BLUB_ERR_INVALID_ARGUMENT 1
+#define BLUB_ERR_CUDA 2
+#define BLUB_ERR_OUT_OF_MEMORY 3
+#define BLUB_ERR_IO 4
+#define BLUB_ERR_PARSE 5
+#define BLUB_WARN_TRUNCATED 100 /* add_cube hit max_num_particles: hybrid_fluid.rs:627-633 logs + truncates */
+
+/* HybridFluid::PARTICLES_PER_GRID_CELL, hybrid_fluid.rs:90 (read by the renderer for the particle radius) */
+#define BLUB_PARTICLES_PER_GRID_CELL 8
+
+/* marker values, shader/simulation/hybrid_fluid.glsl:20-23 (stored as int8 instead of R8Snorm) */
+#define BLUB_CELL_SOLID 0
+#define BLUB_CELL_FLUID 1
+#define BLUB_CELL_AIR (-1)
+
+typedef struct BlubFluid BlubFluid; /* opaque; owns its buffers like HybridFluid (hybrid_fluid.rs:24-72) */
+
+/* SolverConfig, pressure_solver.rs:57-62; defaults 0.1 / 32 / 4 (hybrid_fluid.rs:253-257) */
+typedef struct {
+    float error_tolerance;        /* on max|r| * dt */
+    int32_t max_num_iterations;
+    int32_t error_check_frequency;
+} BlubSolverConfig;
+
+/* SolverStatisticSample, pressure_solver.rs:63-68; error = max|r| * dt (pressure_solver.rs:162) */
+typedef struct {
+    float error;
+    int32_t iteration_count;
+} BlubSolverSample;
+
+/* Behaviour switches for the reference's driver-defined / buggy spots. */
+typedef struct {
+    int32_t precond_mode;   /* 0 = z = r/diag^2 (LOD-1 fetch returns 0, default), 1 = as written with clamped LOD */
+    int32_t reserved[7];
+} BlubQuirks;
+
+/* The ten read-only resources of HybridFluid::bind_group_renderer (hybrid_fluid.rs:351-369,700-713). */
+typedef struct {
+    const void *particles_position_ll;            /* num_particles x {float3 pos, uint32 unused}  */
+    const void *particles_velocity_x;             /* num_particles x float4 (C column xyz, v_x)   */
+    const void *particles_velocity_y;
+    const void *particles_velocity_z;
+    const float *grid_velocity_x;                 /* nx*ny*nz, x fastest, value on the +x face     */
+    const float *grid_velocity_y;
+    const float *grid_velocity_z;
+    const int8_t *marker;                         /* BLUB_CELL_*                                   */
+    const float *pressure_from_velocity;
+    const float *pressure_from_density;
+} BlubFluidView;
+
+/* HybridFluid::new, hybrid_fluid.rs:92-100.  Grid dimensions must be multiples of 8 (the reference dispatches
+ * 8^3 groups without guards) and nx*ny*nz > 16384 (pressure_solver.rs:551).  `cuda_stream` is a cudaStream_t
+ * (NULL = a private non-blocking stream owned by the fluid). */
+int blub_fluid_create(BlubFluid **out, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num_particles, int device,
+                      void *cuda_stream);
+void blub_fluid_destroy(BlubFluid *fluid);
+
+/* HybridFluid::add_fluid_cube, hybrid_fluid.rs:620-678: cell-aligned cube, corners clamped to [1, dim-1], 8
+ * stratified-jittered particles per cell (xoshiro256++ seeded with the new particle count, :637).
+ * Returns BLUB_WARN_TRUNCATED when max_num_particles was hit. */
+int blub_fluid_add_cube(BlubFluid *fluid, const float min_grid[3], const float max_grid[3]);
+/* HybridFluid::set_gravity_grid, :692 (world gravity / grid_to_world_scale, src/scene/mod.rs:139) */
+int blub_fluid_set_gravity_grid(BlubFluid *fluid, const float gravity_grid[3]);
+/* HybridFluid::num_particles / num_active_particles, :696,:731 */
+uint32_t blub_fluid_num_particles(const BlubFluid *fluid);
+/* HybridFluid::grid_dimension, :727 */
+void blub_fluid_grid_dimension(const BlubFluid *fluid, uint32_t out[3]);
+
+/* HybridFluid::pressure_solver_config_{velocity,density}, :743-749: mutable reference semantics.
+ * which: 0 = velocity (divergence) solve, 1 = density solve. */
+BlubSolverConfig *blub_fluid_solver_config(BlubFluid *fluid, int which);
+/* HybridFluid::dynamic_settings().particle_rebinning_step_frequency, :19-22,:751; 0 disables (:854) */
+uint32_t *blub_fluid_rebinning_frequency(BlubFluid *fluid);
+/* HybridFluid::pressure_solver_stats_{velocity,density}, :753-761: newest <= 100 samples, oldest first */
+size_t blub_fluid_solver_stats(const BlubFluid *fluid, int which, BlubSolverSample *out, size_t cap);
+/* HybridFluid::update_statistics, :765: collect finished asynchronous read-backs (never blocks) */
+void blub_fluid_update_statistics(BlubFluid *fluid);
+
+/* The SceneVoxelization view bound at set 1 / binding 1 (hybrid_fluid.rs:266, src/scene/voxelization.rs:17):
+ * nx*ny*nz RGBA16F texels in device memory, xyz = solid velocity in cells/s, w != 0 => solid.
+ * NULL = no solids.  Borrowed. */
+int blub_fluid_set_solid_voxels(BlubFluid *fluid, const void *rgba16f_device_ptr);
+
+/* HybridFluid::step, hybrid_fluid.rs:770-977.  Enqueues one simulation step on the fluid's stream. */
+int blub_fluid_step(BlubFluid *fluid, double simulation_delta_seconds);
+
+/* bind_group_renderer, :351-369,:723 */
+int blub_fluid_view(const BlubFluid *fluid, BlubFluidView *out);
+
+int blub_fluid_set_quirks(BlubFluid *fluid, const BlubQuirks *quirks);
+/* Wait for everything enqueued so far (the reference's device.poll(Maintain::Wait), simulation_controller.rs:140). */
+int blub_fluid_synchronize(BlubFluid *fluid);
+const char *blub_last_error(void);
+const char *blub_version(void);
+
+/* ---- scene JSON surface (src/scene/mod.rs:19-43,109-144; src/scene/models.rs:11-46) ------------------------- */
+/* Scene::new + create_fluid_from_config: parses an unchanged blub scene file, creates the fluid, seeds every
+ * fluid cube (world / grid_to_world_scale) and sets gravity.  static_objects are parsed and counted but their
+ * meshes (git-LFS stubs in the reference checkout) are not voxelized. */
+int blub_scene_load(BlubFluid **out, const char *scene_json_path, int device, void *cuda_stream);
+/* Scene description without creating a fluid: fills dims, max_num_particles, scale, gravity(world), #cubes, #static objects. */
+typedef struct {
+    uint32_t grid_dimension[3];
+    uint32_t max_num_particles;
+    float grid_to_world_scale;
+    float world_position[3];
+    float gravity[3];
+    uint32_t num_fluid_cubes;
+    uint32_t num_static_objects;
+} BlubSceneInfo;
+int blub_scene_info(const char *scene_json_path, BlubSceneInfo *out);
+
+/* ---- test / bench taps (not part of the reference surface) ---------------------------------------------------- */
+enum {
+    BLUB_TAP_PARTICLE_POS = 0, BLUB_TAP_PARTICLE_VX = 1, BLUB_TAP_PARTICLE_VY = 2, BLUB_TAP_PARTICLE_VZ = 3,
+    BLUB_TAP_GRID_VX = 4, BLUB_TAP_GRID_VY = 5, BLUB_TAP_GRID_VZ = 6, BLUB_TAP_MARKER = 7,
+    BLUB_TAP_PRESSURE_VELOCITY = 8, BLUB_TAP_PRESSURE_DENSITY = 9, BLUB_TAP_RESIDUAL = 10
+};
+/* synchronous copies between host memory and the tapped array (bytes must not exceed the array) */
+int blub_fluid_download(BlubFluid *fluid, int tap, void *host_dst, size_t bytes);
+int blub_fluid_upload(BlubFluid *fluid, int tap, const void *host_src, size_t bytes);
+/* replace the particle set (positions xyz_, three velocity rows); rows may be NULL (zero) */
+int blub_fluid_set_particles(BlubFluid *fluid, uint32_t count, const float *pos4, const float *vx4, const float *vy4,
+                             const float *vz4);
+/* run stages [from, to) of the 14-stage list of one step (same numbering as oracle/blub_oracle.c:orc_step_stages) */
+int blub_fluid_step_stages(BlubFluid *fluid, double simulation_delta_seconds, int from, int to);
+/* PCG only: solve for the rhs currently in the residual tap with the current markers; warm start from the field */
+int blub_fluid_solve_only(BlubFluid *fluid, int which, double simulation_delta_seconds);
+/* last finished solve of a field, synchronously: max|r| (not multiplied by dt) and iteration count */
+int blub_fluid_last_solve(BlubFluid *fluid, int which, float *max_error, int32_t *iterations);
+/* PCG micro-benchmark: `repetitions` times { restore the rhs that is in the residual tap now, zero the pressure field,
+ * solve } with CUDA events around each solve on the fluid's stream; ms_each[repetitions] receives device milliseconds.
+ * Synchronises. */
+int blub_fluid_time_solve(BlubFluid *fluid, int which, double simulation_delta_seconds, int repetitions, float *ms_each);
+/* device time of `steps` consecutive blub_fluid_step calls between two CUDA events on the fluid's stream (synchronises) */
+int blub_fluid_time_steps(BlubFluid *fluid, double simulation_delta_seconds, int steps, float *ms_total);
+/* number of kernels launched by this library since the last reset (bench.py's gpu_launches) */
+uint64_t blub_kernel_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLUB_FLUID_H */

@@ -1,0 +1,265 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances are the stated fp32 tolerances of SURVEY.md section 8c; order-dependent quantities (atomics, reductions)
+differ in the last bits, never structurally.  Everything here needs a B200: run with `-m gpu`.
+"""
+import numpy as np
+import pytest
+
+import blub_b200
+from blub_b200 import fluid as F
+from oracle import oracle as O
+from tests import util
+from tests.util import DT, grid_close
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(name, rebin=0, precond=0):
+    orc = util.oracle_from_scene(name)
+    gpu = blub_b200.HybridFluid.from_scene(util.scene_path(name))
+    orc.set_rebin_frequency(rebin)
+    gpu.set_rebin_frequency(rebin)
+    orc.set_quirks(precond_mode=precond)
+    gpu.set_quirks(precond_mode=precond)
+    return orc, gpu
+
+
+def test_scene_seeding_is_bit_exact():
+    orc, gpu = make_pair("dam_small")
+    assert gpu.num_particles == orc.num_particles > 0
+    assert np.array_equal(gpu.download_particles()[:, :3], orc.particles()[:, :3])
+
+
+def random_blob(n, seed, fill=0.7):
+    rng = np.random.default_rng(seed)
+    m = np.full((n, n, n), O.AIR, dtype=np.int8)
+    m[rng.random((n, n, n)) < fill] = O.FLUID
+    m[rng.random((n, n, n)) < 0.05] = O.SOLID
+    m[0], m[-1], m[:, 0], m[:, -1], m[:, :, 0], m[:, :, -1] = 0, 0, 0, 0, 0, 0
+    b = rng.uniform(-1, 1, (n, n, n)).astype(np.float32)
+    return m, b
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+@pytest.mark.parametrize("max_it,freq", [(32, 4), (7, 3), (2, 4)])
+def test_pcg_matches_oracle_on_random_blob(precond, max_it, freq):
+    n = 32
+    m, b = random_blob(n, 1234)
+    orc = O.OracleFluid(n, n, n, 8)
+    gpu = blub_b200.HybridFluid(n, n, n, 8)
+    for f in (orc, gpu):
+        f.set_quirks(precond_mode=precond)
+        f.set_solver_config(0, error_tolerance=0.0, max_num_iterations=max_it, error_check_frequency=freq)
+    orc.grid(O.ARR_MARKER)[:] = m
+    orc.grid(O.ARR_RESIDUAL)[:] = b
+    gpu.upload_grid(F.TAP_MARKER, m)
+    gpu.upload_grid(F.TAP_RESIDUAL, b)
+    orc.solve(0, DT)
+    gpu.solve_only(0, DT)
+    eo, io = orc.last_solve(0)
+    eg, ig = gpu.last_solve(0)
+    assert io == ig == max_it  # tolerance 0: never converges, statistics are written at i == max
+    fl = m == O.FLUID
+    p_o, p_g = orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL)
+    assert (p_g[~fl] == 0).all()
+    grid_close(p_o, p_g, "pressure", rel=2e-3, abs_=1e-5)
+    grid_close(orc.grid(O.ARR_RESIDUAL), gpu.download_grid(F.TAP_RESIDUAL), "residual", rel=5e-3, abs_=1e-5, mask=fl)
+    assert abs(eo - eg) <= 5e-3 * max(eo, eg) + 1e-6
+
+
+def test_pcg_convergence_schedule_and_warm_start():
+    n = 32
+    m, b = random_blob(n, 7, fill=0.9)
+    b[m != O.FLUID] = 0
+    orc = O.OracleFluid(n, n, n, 8)
+    gpu = blub_b200.HybridFluid(n, n, n, 8)
+    for f in (orc, gpu):
+        f.set_solver_config(0, error_tolerance=1e-3, max_num_iterations=128, error_check_frequency=4)
+    orc.grid(O.ARR_MARKER)[:] = m
+    gpu.upload_grid(F.TAP_MARKER, m)
+    for rep in range(2):  # the second solve warm-starts from the first solution
+        orc.grid(O.ARR_RESIDUAL)[:] = b
+        gpu.upload_grid(F.TAP_RESIDUAL, b)
+        orc.solve(0, DT)
+        gpu.solve_only(0, DT)
+        eo, io = orc.last_solve(0)
+        eg, ig = gpu.last_solve(0)
+        assert io % 4 == 0 and ig % 4 == 0 and abs(io - ig) <= 4, (rep, io, ig)
+        assert eg < 1e-3 / DT
+        grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), "pressure", rel=2e-3, abs_=2e-3)
+    assert ig <= 8  # warm start: already (nearly) converged
+
+
+def test_hydrostatic_known_answer_on_gpu():
+    n = 16 * 2
+    gpu = blub_b200.HybridFluid(n, n, n, 8 * n * n * n)
+    gpu.add_fluid_cube([1, 1, 1], [n - 1, 9, n - 1])
+    gpu.set_gravity_grid([0, -981.0, 0])
+    gpu.set_rebin_frequency(0)
+    gpu.set_solver_config(0, error_tolerance=1e-6, max_num_iterations=600, error_check_frequency=4)
+    gpu.step_stages(DT, 0, 3)
+    err, it = gpu.last_solve(0)
+    assert 0 < it < 600 and err < 1e-6 / DT
+    p = gpu.download_grid(F.TAP_P_VEL)
+    gdt = float(np.float32(-981.0) * np.float32(DT))
+    for y in range(1, 9):
+        assert np.allclose(p[1:n - 1, y, 1:n - 1], gdt * (9 - y), rtol=0, atol=3e-3), y
+    gpu.step_stages(DT, 4, 5)
+    uy = gpu.download_grid(F.TAP_UY)
+    assert np.abs(uy[1:n - 1, 1:8, 1:n - 1]).max() < 3e-3
+
+
+STAGE_TAPS = [(F.TAP_UX, O.ARR_UX), (F.TAP_UY, O.ARR_UY), (F.TAP_UZ, O.ARR_UZ)]
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_stagewise_parity_one_step(precond):
+    """Both implementations walk the 14 stages of one step from identical particles; taps are compared after each."""
+    orc, gpu = make_pair("dam_small", rebin=0, precond=precond)
+    # give the particles a non-trivial velocity / affine state
+    rng = np.random.default_rng(5)
+    npart = orc.num_particles
+    rows = [rng.normal(0, 3.0, (npart, 4)).astype(np.float32) for _ in range(3)]
+    pos = orc.particles().copy()
+    orc.set_particles(pos, *rows)
+    gpu.set_particles(pos, *rows)
+    grav = [0.0, -981.0, 0.0]
+    orc.set_gravity_grid(grav)
+    gpu.set_gravity_grid(grav)
+    for f in (orc, gpu):
+        f.set_solver_config(0, 0.1, 32, 4)
+        f.set_solver_config(1, 0.1, 32, 4)
+
+    def run(a, b):
+        orc.step_stages(DT, a, b)
+        gpu.step_stages(DT, a, b)
+
+    run(0, 1)  # P2G
+    m_o, m_g = orc.grid(O.ARR_MARKER), gpu.download_grid(F.TAP_MARKER)
+    assert np.array_equal(m_o, m_g)
+    for c, (tg, to) in enumerate(STAGE_TAPS):
+        grid_close(orc.grid(to), gpu.download_grid(tg), f"P2G u[{c}]", mask=util.fluid_adjacent_faces(m_o, c))
+    fl = m_o == O.FLUID
+    run(1, 2)  # rhs 1
+    grid_close(orc.grid(O.ARR_RESIDUAL), gpu.download_grid(F.TAP_RESIDUAL), "rhs1", mask=fl)
+    run(2, 3)  # solve 1
+    eo, io = orc.last_solve(0)
+    eg, ig = gpu.last_solve(0)
+    assert io == ig, (io, ig)
+    grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), "p1", rel=2e-3, abs_=1e-4)
+    # continue from the ORACLE's pressure so that solver round-off does not leak into the per-stage comparison
+    gpu.upload_grid(F.TAP_P_VEL, orc.grid(O.ARR_P_VEL))
+    run(3, 5)  # (binning off) + divergence_remove
+    for c, (tg, to) in enumerate(STAGE_TAPS):
+        grid_close(orc.grid(to), gpu.download_grid(tg), f"projected u[{c}]")
+    run(5, 6)  # extrapolate
+    for c, (tg, to) in enumerate(STAGE_TAPS):
+        grid_close(orc.grid(to), gpu.download_grid(tg), f"extrapolated u[{c}]")
+    for c, (tg, to) in enumerate(STAGE_TAPS):
+        gpu.upload_grid(tg, orc.grid(to))
+    run(6, 9)  # clear + advect + boundary marker
+    assert np.array_equal(orc.grid(O.ARR_MARKER), gpu.download_grid(F.TAP_MARKER))
+    p_o, p_g = orc.particles()[:, :3], gpu.download_particles()[:, :3]
+    assert np.abs(p_o - p_g).max() <= 2e-4
+    vmax = max(np.abs(orc.particles(O.ARR_ROWX)[:, 3]).max(), 1.0)
+    for k, (tg, to) in enumerate([(F.TAP_VX, O.ARR_ROWX), (F.TAP_VY, O.ARR_ROWY), (F.TAP_VZ, O.ARR_ROWZ)]):
+        d = np.abs(orc.particles(to) - gpu.download_particles(tg)).max()
+        assert d <= 1e-3 * vmax, (k, d, vmax)
+    gpu.set_particles(np.c_[p_o, np.zeros(npart, np.float32)], orc.particles(O.ARR_ROWX), orc.particles(O.ARR_ROWY), orc.particles(O.ARR_ROWZ))
+    run(9, 10)  # rhs 2
+    fl = orc.grid(O.ARR_MARKER) == O.FLUID
+    grid_close(orc.grid(O.ARR_RESIDUAL), gpu.download_grid(F.TAP_RESIDUAL), "rhs2", rel=1e-4, abs_=2e-3, mask=fl)
+    run(10, 11)  # solve 2
+    assert orc.last_solve(1)[1] == gpu.last_solve(1)[1]
+    grid_close(orc.grid(O.ARR_P_DEN), gpu.download_grid(F.TAP_P_DEN), "p2", rel=2e-3, abs_=1e-4)
+    gpu.upload_grid(F.TAP_P_DEN, orc.grid(O.ARR_P_DEN))
+    run(11, 13)  # position change + extrapolate
+    for c, (tg, to) in enumerate(STAGE_TAPS):
+        grid_close(orc.grid(to), gpu.download_grid(tg), f"displacement[{c}]")
+        gpu.upload_grid(tg, orc.grid(to))
+    run(13, 14)  # correct particles
+    assert np.abs(orc.particles()[:, :3] - gpu.download_particles()[:, :3]).max() <= 2e-4
+
+
+def test_binning_is_a_permutation_sorted_by_cell():
+    orc, gpu = make_pair("dam_small", rebin=1)
+    rng = np.random.default_rng(3)
+    pos = orc.particles().copy()
+    rng.shuffle(pos)
+    gpu.set_particles(pos)
+    gpu.step_stages(DT, 3, 4)
+    out = gpu.download_particles()[:, :3]
+    a, _ = util.sort_rows(pos[:, :3])
+    b, _ = util.sort_rows(out)
+    assert np.array_equal(a, b)  # same multiset, bit for bit
+    c = np.floor(out).astype(np.int64)
+    key = (c[:, 2] * gpu.ny + c[:, 1]) * gpu.nx + c[:, 0]
+    assert (np.diff(key) >= 0).all()  # x-fastest cell order (particle_binning_prefixsum.comp:18-24)
+
+
+def test_multi_step_scene_parity():
+    """5 steps of a dam break: same particle order (rebin off), tight solver so the iterate is well defined."""
+    orc, gpu = make_pair("dam_small", rebin=0)
+    for f in (orc, gpu):
+        f.set_solver_config(0, 1e-4, 128, 4)
+        f.set_solver_config(1, 1e-4, 128, 4)
+    for _ in range(5):
+        orc.step(DT)
+        gpu.step(DT)
+    p_o, p_g = orc.particles()[:, :3], gpu.download_particles()[:, :3]
+    d = np.abs(p_o - p_g).max(axis=1)
+    assert np.isfinite(p_g).all()
+    assert np.quantile(d, 0.999) <= 1e-2, (np.quantile(d, 0.999), d.max())
+    v_o = np.c_[orc.particles(O.ARR_ROWX)[:, 3], orc.particles(O.ARR_ROWY)[:, 3], orc.particles(O.ARR_ROWZ)[:, 3]].astype(np.float64)
+    v_g = np.c_[gpu.download_particles(F.TAP_VX)[:, 3], gpu.download_particles(F.TAP_VY)[:, 3], gpu.download_particles(F.TAP_VZ)[:, 3]].astype(np.float64)
+    mom_o, mom_g = v_o.sum(0), v_g.sum(0)
+    ke_o, ke_g = (v_o ** 2).sum(), (v_g ** 2).sum()
+    assert abs(ke_o - ke_g) <= 1e-3 * ke_o
+    assert np.abs(mom_o - mom_g).max() <= 1e-3 * np.abs(v_o).sum(0).max()
+
+
+def test_single_cell_debug_scene_one_step():
+    # configs[0] of BASELINE.json: the reference's own debug scene (8 particles), rebin off
+    orc, gpu = make_pair("single_cell_debug", rebin=0)
+    orc.step(DT)
+    gpu.step(DT)
+    assert gpu.num_particles == 8
+    assert np.abs(orc.particles()[:, :3] - gpu.download_particles()[:, :3]).max() <= 2e-4
+    for to, tg in [(O.ARR_ROWX, F.TAP_VX), (O.ARR_ROWY, F.TAP_VY), (O.ARR_ROWZ, F.TAP_VZ)]:
+        assert np.abs(orc.particles(to) - gpu.download_particles(tg)).max() <= 1e-3 * 10
+
+
+def test_statistics_are_asynchronous_and_scaled_by_dt():
+    _, gpu = make_pair("dam_small", rebin=0)
+    for _ in range(3):
+        gpu.step(DT)
+    gpu.synchronize()
+    gpu.update_statistics()
+    sv, sd = gpu.pressure_solver_stats(0), gpu.pressure_solver_stats(1)
+    assert len(sv) == 3 and len(sd) == 3
+    e, it = gpu.last_solve(1)
+    assert sd[-1][1] == it and abs(sd[-1][0] - e * DT) <= 1e-6 * max(1.0, e * DT)
+    assert all(i % 4 == 0 and 4 <= i <= 32 for _, i in sv + sd)
+
+
+def test_solid_voxels_block_flow():
+    """A static solid slab (synthetic analytic solid written straight into the RGBA16F volume) -- config C5's mechanism."""
+    import torch
+    orc, gpu = make_pair("dam_small", rebin=0)
+    vox = np.zeros((32, 32, 32, 4), dtype=np.float32)
+    vox[4:28, 1:12, 20:23, 3] = 1.0
+    vox[4:28, 1:12, 20:23, 0] = 5.0  # moving in +x at 5 cells/s
+    orc.set_voxels(vox)
+    tv = torch.from_numpy(vox).to("cuda").to(torch.float16).contiguous()
+    gpu.set_solid_voxels(tv.data_ptr())
+    for _ in range(2):
+        orc.step(DT)
+        gpu.step(DT)
+    gpu.synchronize()
+    assert np.array_equal(orc.grid(O.ARR_MARKER), gpu.download_grid(F.TAP_MARKER))
+    d = np.abs(orc.particles()[:, :3] - gpu.download_particles()[:, :3]).max(axis=1)
+    assert np.quantile(d, 0.999) <= 5e-3, (np.quantile(d, 0.999), d.max())
+    inside = vox[..., 3] > 0
+    c = np.floor(gpu.download_particles()[:, :3]).astype(int)
+    assert not inside[c[:, 2], c[:, 1], c[:, 0]].any()

@@ -1,0 +1,53 @@
+"""Helpers shared by the parity tests: build identical fluids on the oracle and on the CUDA library."""
+import json
+import os
+
+import numpy as np
+
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SCENES = os.path.join(HERE, "golden", "scenes")
+DT = O.DT_120HZ
+
+
+def scene_path(name):
+    return os.path.join(SCENES, name + ".json")
+
+
+def oracle_from_scene(name):
+    return O.fluid_from_scene(O.load_scene(scene_path(name)))
+
+
+def grid_close(a, b, what, rel=1e-4, abs_=1e-5, mask=None):
+    """max|d| <= rel * max|field| + abs."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if mask is not None:
+        a, b = a[mask], b[mask]
+    if a.size == 0:
+        return 0.0
+    scale = max(np.abs(a).max(), np.abs(b).max())
+    err = np.abs(a - b).max()
+    assert err <= rel * scale + abs_, f"{what}: max|d|={err:.3e} scale={scale:.3e} (tol {rel * scale + abs_:.3e})"
+    return err
+
+
+def fluid_adjacent_faces(marker, c):
+    """Faces a P2G pass writes: face between a cell and its +c neighbour, at least one of them FLUID."""
+    fl = marker == O.FLUID
+    nb = np.zeros_like(fl)
+    sl_src = [slice(None)] * 3
+    sl_dst = [slice(None)] * 3
+    ax = 2 - c  # arrays are [z, y, x]
+    sl_src[ax] = slice(1, None)
+    sl_dst[ax] = slice(0, -1)
+    nb[tuple(sl_dst)] = fl[tuple(sl_src)]
+    return fl | nb
+
+
+def sort_rows(p):
+    """Order-independent particle comparison: lexicographic sort by (cell key, x, y, z)."""
+    p = np.asarray(p)
+    key = np.lexsort((p[:, 2], p[:, 1], p[:, 0]))
+    return p[key], key
