@@ -1,0 +1,37 @@
+"""Short GPU workloads to run under ncu (never a source of bench numbers).
+
+    python tools/profile_targets.py step [scene] [steps]   # a few full steps
+    python tools/profile_targets.py pcg [n] [solves]       # the PCG roofline microbench (all-fluid n^3 box)
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import blub_b200  # noqa: E402
+from blub_b200 import fluid as F  # noqa: E402
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "step"
+if mode == "step":
+    scene = sys.argv[2] if len(sys.argv) > 2 else "dam_256"
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    f = blub_b200.HybridFluid.from_scene(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".json"))
+    for _ in range(steps):
+        f.step(F.DT_120HZ)
+    f.synchronize()
+    print("launches", blub_b200.kernel_launch_count())
+else:
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    solves = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    f = blub_b200.HybridFluid(n, n, n, 8)
+    m = np.zeros((n, n, n), dtype=np.int8)
+    m[1:-1, 1:-1, 1:-1] = 1
+    b = np.random.default_rng(1234).uniform(-1, 1, (n, n, n)).astype(np.float32)
+    b -= b[m == 1].mean(dtype=np.float64).astype(np.float32)
+    b[m != 1] = 0
+    f.upload_grid(F.TAP_MARKER, m)
+    f.upload_grid(F.TAP_RESIDUAL, b)
+    f.set_solver_config(0, 0.0, 32, 4)
+    print("ms per solve", f.time_solve(0, F.DT_120HZ, solves))
