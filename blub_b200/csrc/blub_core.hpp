@@ -105,7 +105,9 @@ class PressureSolver {
   private:
     GridDim grid_;
     GridArray<float> residual_, search_, aux_, aux_temp_;
-    float *partials_ = nullptr; // per-block partial sums / maxima, 2 * max_blocks
+    GridArray<uint8_t> codes_;       // per-cell code (diag | fluid << 3), rebuilt from the markers at the start of every solve
+    uint8_t *tile_active_ = nullptr; // per-tile "contains FLUID" flag
+    float *partials_ = nullptr;      // per-tile partial sums / maxima, 2 * tiles
     int num_blocks_ = 0;
 };
 
@@ -133,6 +135,9 @@ class HybridFluid {
     void set_solid_voxels(const void *rgba16f) { voxels_ = static_cast<const uint2 *>(rgba16f); }
     void step(double simulation_delta_seconds);
     void step_stages(double simulation_delta_seconds, int from, int to);
+    // one eager step with CUDA events between the 14 stages; ms[14] (synchronises; diagnostics only)
+    void step_timed(double simulation_delta_seconds, float ms[14]);
+    bool use_graph = true; // replay the step as a CUDA graph (BLUB_NO_GRAPH=1 disables)
     void solve_only(int which, double simulation_delta_seconds);
     void synchronize();
 
@@ -153,6 +158,24 @@ class HybridFluid {
   private:
     void upload_step_params(float dt);
     void run_stage(int stage, float dt);
+    void destroy_graphs();
+
+    // Cached executable graphs of one step, keyed by (position buffer in use, binning step?).  Everything a graph bakes
+    // in besides that key is in `GraphSignature`; a change drops the cache.
+    struct GraphSignature {
+        uint32_t num_particles = 0xFFFFFFFFu;
+        const void *voxels = nullptr;
+        int precond_mode = -1;
+        int max_it[2] = {-1, -1}, freq[2] = {-1, -1};
+        bool operator==(const GraphSignature &o) const {
+            return num_particles == o.num_particles && voxels == o.voxels && precond_mode == o.precond_mode && max_it[0] == o.max_it[0] &&
+                   max_it[1] == o.max_it[1] && freq[0] == o.freq[0] && freq[1] == o.freq[1];
+        }
+    };
+    GraphSignature graph_signature_;
+    cudaGraphExec_t graph_exec_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    uint64_t graph_kernel_nodes_[2][2] = {{0, 0}, {0, 0}}; // kernels inside each graph (for blub_kernel_launch_count)
+    bool capturing_ = false;
 
     GridDim grid_;
     int device_;

@@ -303,6 +303,17 @@ int blub_fluid_time_steps(BlubFluid *fluid, double dt, int steps, float *ms_tota
     });
 }
 
+int blub_fluid_step_timed(BlubFluid *fluid, double dt, float ms_per_stage[14]) {
+    if (!fluid || !ms_per_stage) return fail(BLUB_ERR_INVALID_ARGUMENT, "bad argument");
+    return guarded([&] { fluid->impl->step_timed(dt, ms_per_stage); return BLUB_OK; });
+}
+
+int blub_fluid_set_graph_replay(BlubFluid *fluid, int enabled) {
+    if (!fluid) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL fluid");
+    fluid->impl->use_graph = enabled != 0;
+    return BLUB_OK;
+}
+
 uint64_t blub_kernel_launch_count(int reset) {
     uint64_t v = blub::g_kernel_launches.load();
     if (reset) blub::g_kernel_launches.store(0);

@@ -1,6 +1,7 @@
 // hybrid_fluid.cu -- host side of the fluid: allocation, particle seeding and the recording of one step.
 // Counterpart of src/simulation/hybrid_fluid.rs (HybridFluid::{new, add_fluid_cube, step, ...}).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "blub_core.hpp"
@@ -49,11 +50,22 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
     BLUB_CUDA_CHECK(cudaMallocHost(&params_host_, sizeof(StepParams) * 64));
     for (int k = 0; k < 64; ++k) BLUB_CUDA_CHECK(cudaEventCreateWithFlags(&param_events_[k], cudaEventDisableTiming));
     BLUB_CUDA_CHECK(cudaDeviceSynchronize());
+    const char *ng = std::getenv("BLUB_NO_GRAPH");
+    if (ng && ng[0] == '1') use_graph = false;
+}
+
+void HybridFluid::destroy_graphs() {
+    for (auto &row : graph_exec_)
+        for (auto &e : row) {
+            if (e) cudaGraphExecDestroy(e);
+            e = nullptr;
+        }
 }
 
 HybridFluid::~HybridFluid() {
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
+    destroy_graphs();
     for (int k = 0; k < 2; ++k) cudaFree(pos_[k]);
     for (int c = 0; c < 3; ++c) {
         cudaFree(row_[c]);
@@ -201,7 +213,7 @@ void HybridFluid::run_stage(int stage, float dt) {
         break;
     case 2: // primary pressure solver (:843-852)
         solver_->solve(stream_, *field_velocity_, 0, marker_.ptr, params_dev_, quirks);
-        field_velocity_->enqueue_error_buffer_read(stream_, dt);
+        if (!capturing_) field_velocity_->enqueue_error_buffer_read(stream_, dt); // the scalars live until this field's next solve
         break;
     case 3: // particle binning every n-th step, including step 0 (:854-894)
         if (dynamic_settings_.particle_rebinning_step_frequency != 0 && step_counter_ % dynamic_settings_.particle_rebinning_step_frequency == 0) {
@@ -229,7 +241,7 @@ void HybridFluid::run_stage(int stage, float dt) {
         break;
     case 10: // secondary pressure solver (:940-949)
         solver_->solve(stream_, *field_density_, 1, marker_.ptr, params_dev_, quirks);
-        field_density_->enqueue_error_buffer_read(stream_, dt);
+        if (!capturing_) field_density_->enqueue_error_buffer_read(stream_, dt);
         break;
     case 11: // compute position change (:959-962)
         launch_position_change(stream_, grid_, params_dev_, marker_.ptr, field_density_->pressure(), u);
@@ -245,14 +257,91 @@ void HybridFluid::run_stage(int stage, float dt) {
     }
 }
 
-void HybridFluid::step(double simulation_delta_seconds) { step_stages(simulation_delta_seconds, 0, 14); }
-
-void HybridFluid::step_stages(double simulation_delta_seconds, int from, int to) {
+// HybridFluid::step, hybrid_fluid.rs:770-977.  The reference re-records ~650 dispatches into a command encoder every
+// step; here the 14 stages are captured ONCE into a CUDA graph (per position-buffer parity and binning/non-binning step)
+// and replayed with one launch -- dt, gravity*dt and the tolerances reach the kernels through the device StepParams block.
+void HybridFluid::step(double simulation_delta_seconds) {
     BLUB_CUDA_CHECK(cudaSetDevice(device_));
     const float dt = (float)simulation_delta_seconds; // Duration::as_secs_f32
     if (!(dt > 0.0f)) throw std::invalid_argument("simulation delta must be positive");
+    field_velocity_->retrieve_new_error_samples(); // pressure_solver.rs:614
+    field_density_->retrieve_new_error_samples();
+    upload_step_params(dt);
+    if (!use_graph) {
+        for (int s = 0; s < 14; ++s) run_stage(s, dt);
+        return;
+    }
+    GraphSignature sig;
+    sig.num_particles = num_particles_;
+    sig.voxels = voxels_;
+    sig.precond_mode = quirks.precond_mode;
+    sig.max_it[0] = field_velocity_->config.max_num_iterations; sig.freq[0] = field_velocity_->config.error_check_frequency;
+    sig.max_it[1] = field_density_->config.max_num_iterations; sig.freq[1] = field_density_->config.error_check_frequency;
+    if (!(sig == graph_signature_)) {
+        destroy_graphs();
+        graph_signature_ = sig;
+    }
+    const uint32_t rebin = dynamic_settings_.particle_rebinning_step_frequency;
+    const bool binning = rebin != 0 && step_counter_ % rebin == 0 && num_particles_ > 0;
+    const int cur0 = cur_;
+    cudaGraphExec_t &exec = graph_exec_[cur0][binning ? 1 : 0];
+    if (!exec) {
+        const uint32_t counter0 = step_counter_;
+        const uint64_t launches0 = g_kernel_launches.load();
+        cudaGraph_t graph = nullptr;
+        capturing_ = true;
+        BLUB_CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        try {
+            for (int s = 0; s < 14; ++s) run_stage(s, dt);
+        } catch (...) {
+            cudaStreamEndCapture(stream_, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            capturing_ = false;
+            cur_ = cur0;
+            step_counter_ = counter0;
+            throw;
+        }
+        capturing_ = false;
+        cur_ = cur0; // capture only recorded; replay below performs the step
+        step_counter_ = counter0;
+        const uint64_t nodes = g_kernel_launches.load() - launches0; // recorded, not launched
+        g_kernel_launches.fetch_sub(nodes);
+        graph_kernel_nodes_[cur0][binning ? 1 : 0] = nodes;
+        BLUB_CUDA_CHECK(cudaStreamEndCapture(stream_, &graph));
+        cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        BLUB_CUDA_CHECK(err);
+    }
+    BLUB_CUDA_CHECK(cudaGraphLaunch(exec, stream_));
+    g_kernel_launches.fetch_add(graph_kernel_nodes_[cur0][binning ? 1 : 0], std::memory_order_relaxed);
+    if (binning) cur_ = 1 - cur0;
+    step_counter_ += 1;
+    field_velocity_->enqueue_error_buffer_read(stream_, dt);
+    field_density_->enqueue_error_buffer_read(stream_, dt);
+}
+
+void HybridFluid::step_stages(double simulation_delta_seconds, int from, int to) {
+    BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    const float dt = (float)simulation_delta_seconds;
+    if (!(dt > 0.0f)) throw std::invalid_argument("simulation delta must be positive");
     upload_step_params(dt);
     for (int s = from; s < to && s < 14; ++s) run_stage(s, dt);
+}
+
+void HybridFluid::step_timed(double simulation_delta_seconds, float ms[14]) {
+    BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    const float dt = (float)simulation_delta_seconds;
+    upload_step_params(dt);
+    cudaEvent_t ev[15];
+    for (auto &e : ev) BLUB_CUDA_CHECK(cudaEventCreate(&e));
+    BLUB_CUDA_CHECK(cudaEventRecord(ev[0], stream_));
+    for (int s = 0; s < 14; ++s) {
+        run_stage(s, dt);
+        BLUB_CUDA_CHECK(cudaEventRecord(ev[s + 1], stream_));
+    }
+    BLUB_CUDA_CHECK(cudaEventSynchronize(ev[14]));
+    for (int s = 0; s < 14; ++s) BLUB_CUDA_CHECK(cudaEventElapsedTime(&ms[s], ev[s], ev[s + 1]));
+    for (auto &e : ev) cudaEventDestroy(e);
 }
 
 void HybridFluid::solve_only(int which, double simulation_delta_seconds) {

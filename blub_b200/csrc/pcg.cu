@@ -5,6 +5,7 @@
 // i == max, pressure_solver.rs:676-677), same epsilon guards (pressure_reduce.comp:73-80) -- but not the same pass
 // structure: the reference records 9 dispatches + 3 two-level reductions per iteration (313 dispatches per solve,
 // ~85 B/cell/iteration); here one iteration is three kernels
+//     prepare : marker -> 1-byte codes (diag, fluid) + tile activity; p, r, s <- 0 off-fluid   (once per solve)
 //     dot     : s.As                                       (pressure_apply_coeff.comp + reduce ALPHA)
 //     update  : p += a s, r -= a As, z.r and max|r| fused  (pressure_update_pressure_and_residual.comp + both
 //                                                           preconditioner passes + reduce BETA / MAX_ERROR)
@@ -13,7 +14,9 @@
 // the fly so that z is never stored.  Convergence is a device flag that turns the remaining launches into no-ops
 // (the reference zeroes its indirect-dispatch arguments instead, pressure_reduce.comp:89-92).
 //
-// Layout: four cells per thread along x (128-bit loads), marker as int8, fp32 vectors, padded arrays (common.cuh).
+// Layout: four cells per thread along x (128-bit loads) marching 4 z-planes with the z-neighbours kept in registers and
+// the x-neighbours exchanged by warp shuffles; fp32 vectors, 1-byte cell codes, padded arrays (common.cuh); tiles without
+// any FLUID cell exit at once.  Because p, r and s are kept at exactly 0 off-fluid the 7-point stencil needs no masks.
 #include "blub_core.hpp"
 
 namespace blub {
@@ -23,100 +26,92 @@ std::atomic<uint64_t> g_kernel_launches{0};
 namespace {
 
 constexpr int PCG_THREADS = 256;
+constexpr int PCG_TZ = 4;             // z planes marched by one block
 constexpr float PCG_EPSILON = 1e-10f; // pressure_reduce.comp:33
 
+// Per-cell code, built once per solve from the marker volume (pcg_prepare_kernel):
+//   bits 0..2  number of non-SOLID neighbours = diagonal of A (pressure.glsl:44-53)
+//   bit  3     cell is FLUID
+// INVARIANT kept by every kernel of a solve: p, r and s are exactly 0 on every non-FLUID cell (and in the padding).
+// Then "subtract the FLUID neighbours" (pressure.glsl:56-73) is "subtract all six neighbours", so the stencil needs no
+// neighbour masks:  (A x)_i = diag_i x_i - sum_6 x_nbr  on fluid cells.
+constexpr unsigned CODE_FLUID = 8u;
+
+// Block = (bx, by) threads, bx * by = 256; thread (lx, ly) owns the quad of 4 x-consecutive cells at
+// x = 4 * (blockIdx.x * bx + lx), y = blockIdx.y * by + ly and marches PCG_TZ planes in z from blockIdx.z * PCG_TZ.
 struct TileMap {
-    int bx, by, bz;                   // threads per tile edge (x in quads of 4 cells)
+    int bx, by;
     int tiles_x, tiles_y, tiles_z;
-    int qx;                           // quads per row
-    int nblocks;
+    int qx; // quads per row
+    int ntiles;
+    dim3 grid() const { return dim3(tiles_x, tiles_y, tiles_z); }
+    dim3 block() const { return dim3(bx, by, 1); }
 };
 
 TileMap make_tilemap(const GridDim &g) {
     TileMap t;
     t.qx = g.nx / 4;
-    t.bx = t.qx >= 32 ? 32 : (t.qx >= 16 ? 16 : 8);
-    if (t.qx < 8) t.bx = t.qx; // nx = 8, 16, 24
-    t.by = 4;
-    t.bz = PCG_THREADS / (t.bx * t.by);
-    if (t.bz > 8) t.bz = 8;
+    t.bx = t.qx > 16 ? 32 : (t.qx > 8 ? 16 : 8);
+    t.by = PCG_THREADS / t.bx;
     t.tiles_x = (t.qx + t.bx - 1) / t.bx;
-    t.tiles_y = g.ny / t.by;
-    t.tiles_z = (g.nz + t.bz - 1) / t.bz;
-    t.nblocks = t.tiles_x * t.tiles_y * t.tiles_z;
+    t.tiles_y = (g.ny + t.by - 1) / t.by;
+    t.tiles_z = g.nz / PCG_TZ;
+    t.ntiles = t.tiles_x * t.tiles_y * t.tiles_z;
     return t;
 }
 
-__device__ __forceinline__ bool tile_cell(const GridDim &g, const TileMap &t, int64_t &i) {
-    int tid = threadIdx.x;
-    int lx = tid % t.bx, ly = (tid / t.bx) % t.by, lz = tid / (t.bx * t.by);
-    int b = blockIdx.x;
-    int tx = b % t.tiles_x, ty = (b / t.tiles_x) % t.tiles_y, tz = b / (t.tiles_x * t.tiles_y);
-    int q = tx * t.bx + lx, y = ty * t.by + ly, z = tz * t.bz + lz;
-    if (q >= t.qx || lz >= t.bz || z >= g.nz) return false;
-    i = ((int64_t)z * g.ny + y) * g.nx + 4 * q;
-    return true;
-}
-
-// Markers of a quad of four x-consecutive cells and of their six neighbours.
-struct QuadStencil {
-    bool fluid[4];
-    float diag[4];       // number of non-SOLID neighbours (pressure.glsl:44-50)
-    unsigned nbr[4];     // FLUID flags: bit 0 -x, 1 +x, 2 -y, 3 +y, 4 -z, 5 +z
+struct TileCtx {
+    int tile;
+    bool valid, first, last; // first/last quad of the block's row segment (x neighbours come from memory there)
+    int i;                   // linear index of the quad in the block's first plane (fits: n < 2^31)
 };
-
-__device__ __forceinline__ bool load_quad_stencil(const int8_t *__restrict__ m, int64_t i, int sy, int sz, QuadStencil &q) {
-    const char4 c = *reinterpret_cast<const char4 *>(m + i);
-    if (c.x != CELL_FLUID && c.y != CELL_FLUID && c.z != CELL_FLUID && c.w != CELL_FLUID) return false;
-    const char4 ym = *reinterpret_cast<const char4 *>(m + i - sy), yp = *reinterpret_cast<const char4 *>(m + i + sy);
-    const char4 zm = *reinterpret_cast<const char4 *>(m + i - sz), zp = *reinterpret_cast<const char4 *>(m + i + sz);
-    const int cx[6] = {m[i - 1], c.x, c.y, c.z, c.w, m[i + 4]};
-    const int cym[4] = {ym.x, ym.y, ym.z, ym.w}, cyp[4] = {yp.x, yp.y, yp.z, yp.w};
-    const int czm[4] = {zm.x, zm.y, zm.z, zm.w}, czp[4] = {zp.x, zp.y, zp.z, zp.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        q.fluid[k] = cx[k + 1] == CELL_FLUID;
-        int d = (cx[k] != CELL_SOLID) + (cx[k + 2] != CELL_SOLID) + (cym[k] != CELL_SOLID) + (cyp[k] != CELL_SOLID) +
-                (czm[k] != CELL_SOLID) + (czp[k] != CELL_SOLID);
-        q.diag[k] = (float)d;
-        q.nbr[k] = (cx[k] == CELL_FLUID ? 1u : 0u) | (cx[k + 2] == CELL_FLUID ? 2u : 0u) | (cym[k] == CELL_FLUID ? 4u : 0u) |
-                   (cyp[k] == CELL_FLUID ? 8u : 0u) | (czm[k] == CELL_FLUID ? 16u : 0u) | (czp[k] == CELL_FLUID ? 32u : 0u);
-    }
-    return true;
+__device__ __forceinline__ TileCtx tile_ctx(const GridDim &g, const TileMap &t) {
+    TileCtx c;
+    const int q = blockIdx.x * t.bx + threadIdx.x;
+    const int y = blockIdx.y * t.by + threadIdx.y;
+    c.tile = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    c.valid = q < t.qx && y < g.ny;
+    c.first = threadIdx.x == 0;
+    c.last = threadIdx.x == t.bx - 1 || q == t.qx - 1;
+    c.i = c.valid ? (blockIdx.z * PCG_TZ * g.ny + y) * g.nx + 4 * q : 0;
+    return c;
 }
 
-// (A x) for the four cells of a quad: MultiplyWithCoefficientMatrix, pressure.glsl:34-75
-__device__ __forceinline__ void apply_coeff(const float *__restrict__ x, int64_t i, int sy, int sz, const QuadStencil &q,
-                                            const float xc[4], float out[4]) {
-    const float4 ym = *reinterpret_cast<const float4 *>(x + i - sy), yp = *reinterpret_cast<const float4 *>(x + i + sy);
-    const float4 zm = *reinterpret_cast<const float4 *>(x + i - sz), zp = *reinterpret_cast<const float4 *>(x + i + sz);
-    const float xr[6] = {x[i - 1], xc[0], xc[1], xc[2], xc[3], x[i + 4]};
-    const float vym[4] = {ym.x, ym.y, ym.z, ym.w}, vyp[4] = {yp.x, yp.y, yp.z, yp.w};
-    const float vzm[4] = {zm.x, zm.y, zm.z, zm.w}, vzp[4] = {zp.x, zp.y, zp.z, zp.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float r = q.diag[k] * xc[k];
-        const unsigned n = q.nbr[k];
-        if (n & 1u) r -= xr[k];
-        if (n & 2u) r -= xr[k + 2];
-        if (n & 4u) r -= vym[k];
-        if (n & 8u) r -= vyp[k];
-        if (n & 16u) r -= vzm[k];
-        if (n & 32u) r -= vzp[k];
-        out[k] = r;
-    }
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, const float4 &v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ uchar4 ldcode(const uint8_t *p) { return *reinterpret_cast<const uchar4 *>(p); }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// x-neighbours of a quad: from the adjacent lanes, or from memory at the ends of the block's row segment.
+// Must be called by all 32 lanes of a warp.
+__device__ __forceinline__ void x_neighbours(const float *__restrict__ x, int i, const float4 &c, const TileCtx &t, float &left, float &right) {
+    left = __shfl_up_sync(0xffffffffu, c.w, 1);
+    right = __shfl_down_sync(0xffffffffu, c.x, 1);
+    if (t.valid && t.first) left = x[i - 1];
+    if (t.valid && t.last) right = x[i + 4];
+}
+
+// A x for a quad under the zero invariant (MultiplyWithCoefficientMatrix, pressure.glsl:34-75)
+__device__ __forceinline__ float4 stencil_quad(const uchar4 &code, const float4 &c, float left, float right, const float4 &ym, const float4 &yp,
+                                               const float4 &zm, const float4 &zp) {
+    float4 o;
+    o.x = (float)(code.x & 7u) * c.x - (((left + c.y) + (ym.x + yp.x)) + (zm.x + zp.x));
+    o.y = (float)(code.y & 7u) * c.y - (((c.x + c.z) + (ym.y + yp.y)) + (zm.y + zp.y));
+    o.z = (float)(code.z & 7u) * c.z - (((c.y + c.w) + (ym.z + yp.z)) + (zm.z + zp.z));
+    o.w = (float)(code.w & 7u) * c.w - (((c.z + right) + (ym.w + yp.w)) + (zm.w + zp.w));
+    return o;
 }
 
 // z = P(P(r)) with the LOD-1 neighbour fetches reading 0: z = (r / d) / d, d = max(diag, 1)
 // (pressure_apply_preconditioner.comp:48-77).  1/d^2 by table: <= 1.5 ulp from the two divisions.
-__device__ __forceinline__ float precond_diag2(float r, float diag) {
-    const float inv[7] = {1.0f, 1.0f, 0.25f, 1.0f / 9.0f, 0.0625f, 0.04f, 1.0f / 36.0f};
-    return r * inv[(int)diag];
-}
+__constant__ float c_inv_diag2[8] = {1.0f, 1.0f, 0.25f, 1.0f / 9.0f, 0.0625f, 0.04f, 1.0f / 36.0f, 1.0f};
+__device__ __forceinline__ float precond_diag2(float r, unsigned code) { return r * c_inv_diag2[code & 7u]; }
+
+__device__ __forceinline__ int linear_tid() { return threadIdx.y * blockDim.x + threadIdx.x; }
 
 __device__ __forceinline__ float block_sum(float v, float *sh) {
     v = warp_sum(v);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tid = linear_tid(), lane = tid & 31, w = tid >> 5;
     if (lane == 0) sh[w] = v;
     __syncthreads();
     float r = 0.0f;
@@ -129,7 +124,7 @@ __device__ __forceinline__ float block_sum(float v, float *sh) {
 }
 __device__ __forceinline__ float block_max(float v, float *sh) {
     v = warp_max(v);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tid = linear_tid(), lane = tid & 31, w = tid >> 5;
     if (lane == 0) sh[w] = v;
     __syncthreads();
     float r = 0.0f;
@@ -144,7 +139,7 @@ __device__ __forceinline__ float block_max(float v, float *sh) {
 // Publishes this block's partial(s) and returns true in exactly one block: the last one to arrive.
 __device__ __forceinline__ bool publish_and_elect(PcgScalars *scal, unsigned nblocks) {
     __shared__ bool last;
-    if (threadIdx.x == 0) {
+    if (linear_tid() == 0) {
         __threadfence();
         unsigned t = atomicAdd(&scal->ticket, 1u);
         last = (t == nblocks - 1);
@@ -155,12 +150,20 @@ __device__ __forceinline__ bool publish_and_elect(PcgScalars *scal, unsigned nbl
 }
 
 // Final reduction by the elected block, in fixed order and double precision => bit-reproducible run to run.
-__device__ __forceinline__ double final_sum(const float *partials, int n, float *sh_unused) {
+__device__ __forceinline__ double final_sum(const float *partials, int n) {
     __shared__ double shd[PCG_THREADS / 32];
-    double acc = 0.0;
-    for (int k = threadIdx.x; k < n; k += PCG_THREADS) acc += (double)__ldcg(partials + k);
-    acc = warp_sum(acc);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tid = linear_tid();
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = tid;
+    for (; k + 3 * PCG_THREADS < n; k += 4 * PCG_THREADS) { // four independent loads in flight
+        a0 += (double)__ldcg(partials + k);
+        a1 += (double)__ldcg(partials + k + PCG_THREADS);
+        a2 += (double)__ldcg(partials + k + 2 * PCG_THREADS);
+        a3 += (double)__ldcg(partials + k + 3 * PCG_THREADS);
+    }
+    for (; k < n; k += PCG_THREADS) a0 += (double)__ldcg(partials + k);
+    double acc = warp_sum((a0 + a1) + (a2 + a3));
+    const int lane = tid & 31, w = tid >> 5;
     if (lane == 0) shd[w] = acc;
     __syncthreads();
     double r = 0.0;
@@ -173,7 +176,7 @@ __device__ __forceinline__ double final_sum(const float *partials, int n, float 
 }
 __device__ __forceinline__ float final_max(const float *partials, int n, float *sh) {
     float acc = 0.0f;
-    for (int k = threadIdx.x; k < n; k += PCG_THREADS) acc = fmaxf(acc, __ldcg(partials + k));
+    for (int k = linear_tid(); k < n; k += PCG_THREADS) acc = fmaxf(acc, __ldcg(partials + k));
     return block_max(acc, sh);
 }
 
@@ -182,49 +185,99 @@ __device__ __forceinline__ float guarded_div(float num, float den) { // pressure
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// init: p <- 0 off-fluid, r <- b - A p (warm start), and for the diag2 preconditioner s <- z, sigma <- z.r
-// (pressure_init.comp:19-84 + the init block of pressure_solver.rs:625-649)
-template <int MODE>
-__global__ void __launch_bounds__(PCG_THREADS) pcg_init_kernel(GridDim g, TileMap t, const int8_t *__restrict__ marker,
-                                                               float *__restrict__ p, float *__restrict__ r,
-                                                               float *__restrict__ s, PcgScalars *scal, float *partials) {
-    __shared__ float sh[PCG_THREADS / 32];
-    float acc = 0.0f;
-    int64_t i;
-    if (tile_cell(g, t, i)) {
-        QuadStencil q;
-        if (!load_quad_stencil(marker, i, g.sy, g.sz, q)) {
-            *reinterpret_cast<float4 *>(p + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            const float4 p4 = *reinterpret_cast<const float4 *>(p + i);
-            const float4 b4 = *reinterpret_cast<const float4 *>(r + i);
-            float pc[4] = {p4.x, p4.y, p4.z, p4.w}, rc[4] = {b4.x, b4.y, b4.z, b4.w}, Ap[4], sc[4];
-            apply_coeff(p, i, g.sy, g.sz, q, pc, Ap);
+// prepare (once per solve, every tile): marker -> codes + per-tile activity; establish the zero invariant:
+// p <- 0 and rhs <- 0 off-fluid (pressure_init.comp:37-43 zeroes p there), s <- 0 everywhere.
+__global__ void __launch_bounds__(PCG_THREADS) pcg_prepare_kernel(GridDim g, TileMap t, const int8_t *__restrict__ m, uint8_t *__restrict__ codes,
+                                                                  uint8_t *__restrict__ tile_active, float *__restrict__ p, float *__restrict__ r,
+                                                                  float *__restrict__ s) {
+    const TileCtx c = tile_ctx(g, t);
+    int any = 0;
+    if (c.valid) {
+        int i = c.i;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (q.fluid[k]) {
-                    rc[k] -= Ap[k];
-                    if (MODE == 0) {
-                        float z = precond_diag2(rc[k], q.diag[k]);
-                        sc[k] = z;
-                        acc += z * rc[k];
-                    }
-                } else {
-                    pc[k] = 0.0f;
-                    sc[k] = 0.0f;
+        for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+            const char4 cc = *reinterpret_cast<const char4 *>(m + i);
+            uchar4 out = make_uchar4(0, 0, 0, 0);
+            if (cc.x == CELL_FLUID || cc.y == CELL_FLUID || cc.z == CELL_FLUID || cc.w == CELL_FLUID) {
+                any = 1;
+                const char4 ym = *reinterpret_cast<const char4 *>(m + i - g.sy), yp = *reinterpret_cast<const char4 *>(m + i + g.sy);
+                const char4 zm = *reinterpret_cast<const char4 *>(m + i - g.sz), zp = *reinterpret_cast<const char4 *>(m + i + g.sz);
+                const int cx[6] = {m[i - 1], cc.x, cc.y, cc.z, cc.w, m[i + 4]};
+                const int cym[4] = {ym.x, ym.y, ym.z, ym.w}, cyp[4] = {yp.x, yp.y, yp.z, yp.w};
+                const int czm[4] = {zm.x, zm.y, zm.z, zm.w}, czp[4] = {zp.x, zp.y, zp.z, zp.w};
+                unsigned code[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const unsigned d = (cx[e] != CELL_SOLID) + (cx[e + 2] != CELL_SOLID) + (cym[e] != CELL_SOLID) + (cyp[e] != CELL_SOLID) +
+                                       (czm[e] != CELL_SOLID) + (czp[e] != CELL_SOLID);
+                    code[e] = cx[e + 1] == CELL_FLUID ? (CODE_FLUID | d) : 0u;
+                }
+                out = make_uchar4((unsigned char)code[0], (unsigned char)code[1], (unsigned char)code[2], (unsigned char)code[3]);
+                float4 p4 = ld4(p + i), r4 = ld4(r + i);
+                if (!code[0]) { p4.x = 0.f; r4.x = 0.f; }
+                if (!code[1]) { p4.y = 0.f; r4.y = 0.f; }
+                if (!code[2]) { p4.z = 0.f; r4.z = 0.f; }
+                if (!code[3]) { p4.w = 0.f; r4.w = 0.f; }
+                st4(p + i, p4);
+                st4(r + i, r4);
+            } else {
+                st4(p + i, zero4());
+                st4(r + i, zero4());
+            }
+            *reinterpret_cast<uchar4 *>(codes + i) = out;
+            st4(s + i, zero4());
+        }
+    }
+    any = __syncthreads_or(any);
+    if (linear_tid() == 0) tile_active[c.tile] = (uint8_t)(any ? 1 : 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// init: r <- b - A p (warm start) and, for the diag2 preconditioner, s <- z, sigma <- z.r
+// (pressure_init.comp:45-83 + the init block of pressure_solver.rs:625-649)
+template <int MODE>
+__global__ void __launch_bounds__(PCG_THREADS) pcg_init_kernel(GridDim g, TileMap t, const uint8_t *__restrict__ codes,
+                                                               const uint8_t *__restrict__ tile_active, const float *__restrict__ p,
+                                                               float *__restrict__ r, float *__restrict__ s, PcgScalars *scal, float *partials) {
+    __shared__ float sh[PCG_THREADS / 32];
+    const TileCtx c = tile_ctx(g, t);
+    float acc = 0.0f;
+    if (tile_active[c.tile]) {
+        int i = c.i;
+        float4 pm = zero4(), p0 = zero4(), pp = zero4();
+        if (c.valid) { pm = ld4(p + i - g.sz); p0 = ld4(p + i); }
+#pragma unroll
+        for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+            float left, right;
+            x_neighbours(p, i, p0, c, left, right);
+            if (c.valid) {
+                pp = ld4(p + i + g.sz);
+                const uchar4 code = ldcode(codes + i);
+                const float4 ym = ld4(p + i - g.sy), yp = ld4(p + i + g.sy);
+                float4 r4 = ld4(r + i);
+                const float4 Ap = stencil_quad(code, p0, left, right, ym, yp, pm, pp);
+                r4.x -= code.x ? Ap.x : 0.0f;
+                r4.y -= code.y ? Ap.y : 0.0f;
+                r4.z -= code.z ? Ap.z : 0.0f;
+                r4.w -= code.w ? Ap.w : 0.0f;
+                st4(r + i, r4);
+                if (MODE == 0) {
+                    const float4 z = make_float4(precond_diag2(r4.x, code.x), precond_diag2(r4.y, code.y), precond_diag2(r4.z, code.z),
+                                                 precond_diag2(r4.w, code.w));
+                    st4(s + i, z);
+                    acc += (z.x * r4.x + z.y * r4.y) + (z.z * r4.z + z.w * r4.w);
                 }
             }
-            *reinterpret_cast<float4 *>(p + i) = make_float4(pc[0], pc[1], pc[2], pc[3]);
-            *reinterpret_cast<float4 *>(r + i) = make_float4(rc[0], rc[1], rc[2], rc[3]);
-            if (MODE == 0) *reinterpret_cast<float4 *>(s + i) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+            pm = p0;
+            p0 = pp;
         }
     }
     if (MODE != 0) return;
-    float bs = block_sum(acc, sh);
-    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
-    if (publish_and_elect(scal, t.nblocks)) {
-        double tot = final_sum(partials, t.nblocks, sh);
-        if (threadIdx.x == 0) {
+    const float bs = block_sum(acc, sh);
+    if (linear_tid() == 0) partials[c.tile] = bs;
+    if (publish_and_elect(scal, t.ntiles)) {
+        const double tot = final_sum(partials, t.ntiles);
+        if (linear_tid() == 0) {
             scal->alpha = 0.0f; // RESULTMODE_INIT, pressure_reduce.comp:68-71
             scal->beta = 0.0f;
             scal->sigma = (float)tot;
@@ -235,48 +288,44 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_init_kernel(GridDim g, TileMa
 
 // One half-pass of the preconditioner as literally written with the LOD clamped to 0 (MODE 1 only):
 // out = (in - sum over FLUID -x,-y,-z neighbours of in) / diag;  pass 1 also reduces out . r
-// (pressure_apply_preconditioner.comp:36-82).  result_mode: 1 = INIT (sigma), 3 = BETA.
-__global__ void __launch_bounds__(PCG_THREADS) pcg_precond_pass_kernel(GridDim g, TileMap t, const int8_t *__restrict__ marker,
-                                                                       const float *__restrict__ in, float *__restrict__ out,
-                                                                       const float *__restrict__ r, int pass1, int result_mode,
-                                                                       PcgScalars *scal, float *partials) {
+// (pressure_apply_preconditioner.comp:36-82).  `in` obeys the zero invariant.  result_mode: 1 = INIT (sigma), 3 = BETA.
+__global__ void __launch_bounds__(PCG_THREADS) pcg_precond_pass_kernel(GridDim g, TileMap t, const uint8_t *__restrict__ codes,
+                                                                       const uint8_t *__restrict__ tile_active, const float *__restrict__ in,
+                                                                       float *__restrict__ out, const float *__restrict__ r, int pass1,
+                                                                       int result_mode, PcgScalars *scal, float *partials) {
     __shared__ float sh[PCG_THREADS / 32];
     if (scal->done) return;
+    const TileCtx c = tile_ctx(g, t);
     float acc = 0.0f;
-    int64_t i;
-    if (tile_cell(g, t, i)) {
-        QuadStencil q;
-        if (load_quad_stencil(marker, i, g.sy, g.sz, q)) {
-            const float4 c4 = *reinterpret_cast<const float4 *>(in + i);
-            const float4 ym = *reinterpret_cast<const float4 *>(in + i - g.sy), zm = *reinterpret_cast<const float4 *>(in + i - g.sz);
-            const float xr[5] = {in[i - 1], c4.x, c4.y, c4.z, c4.w};
-            const float vym[4] = {ym.x, ym.y, ym.z, ym.w}, vzm[4] = {zm.x, zm.y, zm.z, zm.w};
-            float4 o4 = *reinterpret_cast<const float4 *>(out + i);
-            float oc[4] = {o4.x, o4.y, o4.z, o4.w};
-            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pass1) r4 = *reinterpret_cast<const float4 *>(r + i);
-            const float rc[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!q.fluid[k]) continue;
-                float v = xr[k + 1];
-                if (q.nbr[k] & 1u) v -= xr[k];
-                if (q.nbr[k] & 4u) v -= vym[k];
-                if (q.nbr[k] & 16u) v -= vzm[k];
-                if (q.diag[k] > 0.0f) v /= q.diag[k];
-                oc[k] = v;
-                acc += v * rc[k];
+    if (tile_active[c.tile] && c.valid) {
+        int i = c.i;
+        for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+            const uchar4 code = ldcode(codes + i);
+            const float4 c4 = ld4(in + i), ym = ld4(in + i - g.sy), zm = ld4(in + i - g.sz);
+            const float xl = in[i - 1];
+            float4 o;
+            o.x = code.x ? (c4.x - ((xl + ym.x) + zm.x)) : 0.0f;
+            o.y = code.y ? (c4.y - ((c4.x + ym.y) + zm.y)) : 0.0f;
+            o.z = code.z ? (c4.z - ((c4.y + ym.z) + zm.z)) : 0.0f;
+            o.w = code.w ? (c4.w - ((c4.z + ym.w) + zm.w)) : 0.0f;
+            if (code.x & 7u) o.x /= (float)(code.x & 7u);
+            if (code.y & 7u) o.y /= (float)(code.y & 7u);
+            if (code.z & 7u) o.z /= (float)(code.z & 7u);
+            if (code.w & 7u) o.w /= (float)(code.w & 7u);
+            st4(out + i, o);
+            if (pass1) {
+                const float4 r4 = ld4(r + i);
+                acc += (o.x * r4.x + o.y * r4.y) + (o.z * r4.z + o.w * r4.w);
             }
-            *reinterpret_cast<float4 *>(out + i) = make_float4(oc[0], oc[1], oc[2], oc[3]);
         }
     }
     if (!pass1) return;
-    float bs = block_sum(acc, sh);
-    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
-    if (publish_and_elect(scal, t.nblocks)) {
-        double tot = final_sum(partials, t.nblocks, sh);
-        if (threadIdx.x == 0) {
-            float zr = (float)tot;
+    const float bs = block_sum(acc, sh);
+    if (linear_tid() == 0) partials[c.tile] = bs;
+    if (publish_and_elect(scal, t.ntiles)) {
+        const double tot = final_sum(partials, t.ntiles);
+        if (linear_tid() == 0) {
+            const float zr = (float)tot;
             if (result_mode == 1) {
                 scal->alpha = 0.0f;
                 scal->beta = 0.0f;
@@ -291,29 +340,37 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_precond_pass_kernel(GridDim g
 }
 
 // dot: alpha <- sigma / (s . A s)   (pressure_apply_coeff.comp:19-30 + RESULTMODE_ALPHA)
-__global__ void __launch_bounds__(PCG_THREADS) pcg_dot_kernel(GridDim g, TileMap t, const int8_t *__restrict__ marker,
-                                                              const float *__restrict__ s, PcgScalars *scal, float *partials) {
+__global__ void __launch_bounds__(PCG_THREADS) pcg_dot_kernel(GridDim g, TileMap t, const uint8_t *__restrict__ codes,
+                                                              const uint8_t *__restrict__ tile_active, const float *__restrict__ s,
+                                                              PcgScalars *scal, float *partials) {
     __shared__ float sh[PCG_THREADS / 32];
     if (scal->done) return;
+    const TileCtx c = tile_ctx(g, t);
     float acc = 0.0f;
-    int64_t i;
-    if (tile_cell(g, t, i)) {
-        QuadStencil q;
-        if (load_quad_stencil(marker, i, g.sy, g.sz, q)) {
-            const float4 s4 = *reinterpret_cast<const float4 *>(s + i);
-            const float sc[4] = {s4.x, s4.y, s4.z, s4.w};
-            float As[4];
-            apply_coeff(s, i, g.sy, g.sz, q, sc, As);
+    if (tile_active[c.tile]) {
+        int i = c.i;
+        float4 sm = zero4(), s0 = zero4(), sp = zero4();
+        if (c.valid) { sm = ld4(s + i - g.sz); s0 = ld4(s + i); }
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (q.fluid[k]) acc += sc[k] * As[k];
+        for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+            float left, right;
+            x_neighbours(s, i, s0, c, left, right);
+            if (c.valid) {
+                sp = ld4(s + i + g.sz);
+                const uchar4 code = ldcode(codes + i);
+                const float4 ym = ld4(s + i - g.sy), yp = ld4(s + i + g.sy);
+                const float4 As = stencil_quad(code, s0, left, right, ym, yp, sm, sp);
+                acc += (s0.x * As.x + s0.y * As.y) + (s0.z * As.z + s0.w * As.w); // s == 0 off-fluid: no mask needed
+            }
+            sm = s0;
+            s0 = sp;
         }
     }
-    float bs = block_sum(acc, sh);
-    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
-    if (publish_and_elect(scal, t.nblocks)) {
-        double tot = final_sum(partials, t.nblocks, sh);
-        if (threadIdx.x == 0) {
+    const float bs = block_sum(acc, sh);
+    if (linear_tid() == 0) partials[c.tile] = bs;
+    if (publish_and_elect(scal, t.ntiles)) {
+        const double tot = final_sum(partials, t.ntiles);
+        if (linear_tid() == 0) {
             scal->alpha = guarded_div(scal->sigma, (float)tot);
             scal->ticket = 0u;
         }
@@ -324,53 +381,62 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_dot_kernel(GridDim g, TileMap
 // (pressure_update_pressure_and_residual.comp:23-59, reduce MAX_ERROR pressure_reduce.comp:82-94, and for MODE 0
 //  both preconditioner passes + reduce BETA)
 template <int MODE, bool WITH_ERR>
-__global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(GridDim g, TileMap t, const int8_t *__restrict__ marker,
-                                                                 float *__restrict__ p, float *__restrict__ r,
-                                                                 const float *__restrict__ s, PcgScalars *scal, float *partials,
-                                                                 const StepParams *__restrict__ params, int which, int iteration,
-                                                                 int max_iterations) {
+__global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(GridDim g, TileMap t, const uint8_t *__restrict__ codes,
+                                                                 const uint8_t *__restrict__ tile_active, float *__restrict__ p,
+                                                                 float *__restrict__ r, const float *__restrict__ s, PcgScalars *scal,
+                                                                 float *partials, const StepParams *__restrict__ params, int which,
+                                                                 int iteration, int max_iterations) {
     __shared__ float sh[PCG_THREADS / 32];
     if (scal->done) return;
     const float alpha = scal->alpha;
+    const TileCtx c = tile_ctx(g, t);
     float acc = 0.0f, err = 0.0f;
-    int64_t i;
-    if (tile_cell(g, t, i)) {
-        QuadStencil q;
-        if (load_quad_stencil(marker, i, g.sy, g.sz, q)) {
-            const float4 s4 = *reinterpret_cast<const float4 *>(s + i);
-            const float4 p4 = *reinterpret_cast<const float4 *>(p + i);
-            const float4 r4 = *reinterpret_cast<const float4 *>(r + i);
-            const float sc[4] = {s4.x, s4.y, s4.z, s4.w};
-            float pc[4] = {p4.x, p4.y, p4.z, p4.w}, rc[4] = {r4.x, r4.y, r4.z, r4.w}, As[4];
-            apply_coeff(s, i, g.sy, g.sz, q, sc, As);
+    if (tile_active[c.tile]) {
+        int i = c.i;
+        float4 sm = zero4(), s0 = zero4(), sp = zero4();
+        if (c.valid) { sm = ld4(s + i - g.sz); s0 = ld4(s + i); }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!q.fluid[k]) continue;
-                pc[k] = pc[k] + alpha * sc[k];
-                rc[k] -= alpha * As[k];
-                if (MODE == 0) acc += precond_diag2(rc[k], q.diag[k]) * rc[k];
-                if (WITH_ERR) err = fmaxf(err, fabsf(rc[k]));
+        for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+            float left, right;
+            x_neighbours(s, i, s0, c, left, right);
+            if (c.valid) {
+                sp = ld4(s + i + g.sz);
+                const uchar4 code = ldcode(codes + i);
+                const float4 ym = ld4(s + i - g.sy), yp = ld4(s + i + g.sy);
+                float4 p4 = ld4(p + i), r4 = ld4(r + i);
+                const float4 As = stencil_quad(code, s0, left, right, ym, yp, sm, sp);
+                p4.x += alpha * s0.x; p4.y += alpha * s0.y; p4.z += alpha * s0.z; p4.w += alpha * s0.w; // s == 0 off-fluid
+                r4.x -= alpha * (code.x ? As.x : 0.0f);
+                r4.y -= alpha * (code.y ? As.y : 0.0f);
+                r4.z -= alpha * (code.z ? As.z : 0.0f);
+                r4.w -= alpha * (code.w ? As.w : 0.0f);
+                st4(p + i, p4);
+                st4(r + i, r4);
+                if (MODE == 0) // r == 0 off-fluid: no mask needed
+                    acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
+                           (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
+                if (WITH_ERR) err = fmaxf(fmaxf(err, fmaxf(fabsf(r4.x), fabsf(r4.y))), fmaxf(fabsf(r4.z), fabsf(r4.w)));
             }
-            *reinterpret_cast<float4 *>(p + i) = make_float4(pc[0], pc[1], pc[2], pc[3]);
-            *reinterpret_cast<float4 *>(r + i) = make_float4(rc[0], rc[1], rc[2], rc[3]);
+            sm = s0;
+            s0 = sp;
         }
     }
     if (MODE != 0 && !WITH_ERR) return;
-    float *pmax = partials + t.nblocks;
+    float *pmax = partials + t.ntiles;
     if (MODE == 0) {
-        float bs = block_sum(acc, sh);
-        if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+        const float bs = block_sum(acc, sh);
+        if (linear_tid() == 0) partials[c.tile] = bs;
     }
     if (WITH_ERR) {
-        float bm = block_max(err, sh);
-        if (threadIdx.x == 0) pmax[blockIdx.x] = bm;
+        const float bm = block_max(err, sh);
+        if (linear_tid() == 0) pmax[c.tile] = bm;
     }
-    if (publish_and_elect(scal, t.nblocks)) {
+    if (publish_and_elect(scal, t.ntiles)) {
         double tot = 0.0;
         float e = 0.0f;
-        if (MODE == 0) tot = final_sum(partials, t.nblocks, sh);
-        if (WITH_ERR) e = final_max(pmax, t.nblocks, sh);
-        if (threadIdx.x == 0) {
+        if (MODE == 0) tot = final_sum(partials, t.ntiles);
+        if (WITH_ERR) e = final_max(pmax, t.ntiles, sh);
+        if (linear_tid() == 0) {
             if (WITH_ERR) {
                 const float tol = params->tolerance[which];
                 if (scal->num_iterations == 0 && (iteration == max_iterations || e < tol)) {
@@ -380,7 +446,7 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(GridDim g, Tile
                 }
             }
             if (MODE == 0) {
-                float zr = (float)tot;
+                const float zr = (float)tot;
                 scal->beta = guarded_div(zr, scal->sigma);
                 scal->sigma = zr;
             }
@@ -389,37 +455,40 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(GridDim g, Tile
     }
 }
 
-// search: s <- z + beta s on fluid cells (pressure_update_search.comp:13-24); MODE 0 recomputes z = r / diag^2
+// search: s <- z + beta s (pressure_update_search.comp:13-24); MODE 0 recomputes z = r / diag^2.  r, z, s are 0
+// off-fluid, so the update needs no mask.
 template <int MODE>
-__global__ void __launch_bounds__(PCG_THREADS) pcg_search_kernel(GridDim g, TileMap t, const int8_t *__restrict__ marker,
-                                                                 float *__restrict__ s, const float *__restrict__ r_or_z,
-                                                                 const PcgScalars *scal) {
+__global__ void __launch_bounds__(PCG_THREADS) pcg_search_kernel(GridDim g, TileMap t, const uint8_t *__restrict__ codes,
+                                                                 const uint8_t *__restrict__ tile_active, float *__restrict__ s,
+                                                                 const float *__restrict__ r_or_z, const PcgScalars *scal) {
     if (scal->done) return;
     const float beta = scal->beta;
-    int64_t i;
-    if (!tile_cell(g, t, i)) return;
-    if (MODE == 0) {
-        QuadStencil q;
-        if (!load_quad_stencil(marker, i, g.sy, g.sz, q)) return;
-        const float4 s4 = *reinterpret_cast<const float4 *>(s + i);
-        const float4 r4 = *reinterpret_cast<const float4 *>(r_or_z + i);
-        float sc[4] = {s4.x, s4.y, s4.z, s4.w};
-        const float rc[4] = {r4.x, r4.y, r4.z, r4.w};
+    const TileCtx c = tile_ctx(g, t);
+    if (!tile_active[c.tile] || !c.valid) return;
+    int i = c.i;
+    float4 s4[PCG_TZ], r4[PCG_TZ];
+    uchar4 code[PCG_TZ];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (q.fluid[k]) sc[k] = precond_diag2(rc[k], q.diag[k]) + beta * sc[k];
-        *reinterpret_cast<float4 *>(s + i) = make_float4(sc[0], sc[1], sc[2], sc[3]);
-    } else {
-        const char4 c = *reinterpret_cast<const char4 *>(marker + i);
-        if (c.x != CELL_FLUID && c.y != CELL_FLUID && c.z != CELL_FLUID && c.w != CELL_FLUID) return;
-        const float4 s4 = *reinterpret_cast<const float4 *>(s + i);
-        const float4 z4 = *reinterpret_cast<const float4 *>(r_or_z + i);
-        float4 o = s4;
-        if (c.x == CELL_FLUID) o.x = z4.x + beta * s4.x;
-        if (c.y == CELL_FLUID) o.y = z4.y + beta * s4.y;
-        if (c.z == CELL_FLUID) o.z = z4.z + beta * s4.z;
-        if (c.w == CELL_FLUID) o.w = z4.w + beta * s4.w;
-        *reinterpret_cast<float4 *>(s + i) = o;
+    for (int k = 0; k < PCG_TZ; ++k) {
+        s4[k] = ld4(s + i + k * g.sz);
+        r4[k] = ld4(r_or_z + i + k * g.sz);
+        if (MODE == 0) code[k] = ldcode(codes + i + k * g.sz);
+    }
+#pragma unroll
+    for (int k = 0; k < PCG_TZ; ++k) {
+        float4 o;
+        if (MODE == 0) {
+            o.x = precond_diag2(r4[k].x, code[k].x) + beta * s4[k].x;
+            o.y = precond_diag2(r4[k].y, code[k].y) + beta * s4[k].y;
+            o.z = precond_diag2(r4[k].z, code[k].z) + beta * s4[k].z;
+            o.w = precond_diag2(r4[k].w, code[k].w) + beta * s4[k].w;
+        } else {
+            o.x = r4[k].x + beta * s4[k].x;
+            o.y = r4[k].y + beta * s4[k].y;
+            o.z = r4[k].z + beta * s4[k].z;
+            o.w = r4[k].w + beta * s4[k].w;
+        }
+        st4(s + i + k * g.sz, o);
     }
 }
 
@@ -501,58 +570,69 @@ PressureSolver::PressureSolver(const GridDim &grid) : grid_(grid) {
     search_.alloc(grid);
     aux_.alloc(grid);
     aux_temp_.alloc(grid);
+    codes_.alloc(grid);
     TileMap t = make_tilemap(grid);
-    num_blocks_ = t.nblocks;
+    num_blocks_ = t.ntiles;
     BLUB_CUDA_CHECK(cudaMalloc(&partials_, sizeof(float) * 2 * (size_t)num_blocks_));
+    BLUB_CUDA_CHECK(cudaMalloc(&tile_active_, (size_t)num_blocks_));
+    BLUB_CUDA_CHECK(cudaMemset(tile_active_, 0, (size_t)num_blocks_));
 }
 
 PressureSolver::~PressureSolver() {
-    residual_.release(); search_.release(); aux_.release(); aux_temp_.release();
+    residual_.release(); search_.release(); aux_.release(); aux_temp_.release(); codes_.release();
     if (partials_) cudaFree(partials_);
+    if (tile_active_) cudaFree(tile_active_);
 }
 
 void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which, const int8_t *marker, const StepParams *dparams,
                            const Quirks &quirks) {
     const GridDim g = grid_;
     const TileMap t = make_tilemap(g);
+    const dim3 grid = t.grid(), block = t.block();
     float *p = field.pressure(), *r = residual_.ptr, *s = search_.ptr;
+    const uint8_t *st = codes_.ptr;
+    const uint8_t *ta = tile_active_;
     PcgScalars *scal = field.scalars;
     const int mode = quirks.precond_mode;
     const int max_it = field.config.max_num_iterations;
     const int freq = field.config.error_check_frequency > 0 ? field.config.error_check_frequency : 1;
 
-    field.retrieve_new_error_samples(); // pressure_solver.rs:614
-    field.touched = true;               // the volume is zero-initialised at allocation (:601-603)
+    field.touched = true; // the volume is zero-initialised at allocation (pressure_solver.rs:601-603)
 
     BLUB_LAUNCH(pcg_reset_scalars_kernel, 1, 1, 0, stream, scal);
+    BLUB_LAUNCH(pcg_prepare_kernel, grid, block, 0, stream, g, t, marker, codes_.ptr, tile_active_, p, r, s);
+    if (mode != 0) { // the stored preconditioner vectors must obey the zero invariant as well
+        BLUB_CUDA_CHECK(cudaMemsetAsync(aux_.ptr, 0, (size_t)g.n * sizeof(float), stream));
+        BLUB_CUDA_CHECK(cudaMemsetAsync(aux_temp_.ptr, 0, (size_t)g.n * sizeof(float), stream));
+    }
     if (mode == 0) {
-        BLUB_LAUNCH(pcg_init_kernel<0>, t.nblocks, PCG_THREADS, 0, stream, g, t, marker, p, r, s, scal, partials_);
+        BLUB_LAUNCH(pcg_init_kernel<0>, grid, block, 0, stream, g, t, st, ta, p, r, s, scal, partials_);
     } else {
-        BLUB_LAUNCH(pcg_init_kernel<1>, t.nblocks, PCG_THREADS, 0, stream, g, t, marker, p, r, s, scal, partials_);
-        BLUB_LAUNCH(pcg_precond_pass_kernel, t.nblocks, PCG_THREADS, 0, stream, g, t, marker, r, aux_temp_.ptr, r, 0, 0, scal, partials_);
-        BLUB_LAUNCH(pcg_precond_pass_kernel, t.nblocks, PCG_THREADS, 0, stream, g, t, marker, aux_temp_.ptr, s, r, 1, 1, scal, partials_);
+        BLUB_LAUNCH(pcg_init_kernel<1>, grid, block, 0, stream, g, t, st, ta, p, r, s, scal, partials_);
+        BLUB_LAUNCH(pcg_precond_pass_kernel, grid, block, 0, stream, g, t, st, ta, r, aux_temp_.ptr, r, 0, 0, scal, partials_);
+        BLUB_LAUNCH(pcg_precond_pass_kernel, grid, block, 0, stream, g, t, st, ta, aux_temp_.ptr, s, r, 1, 1, scal, partials_);
     }
     for (int i = 0;; ++i) {
-        BLUB_LAUNCH(pcg_dot_kernel, t.nblocks, PCG_THREADS, 0, stream, g, t, marker, s, scal, partials_);
+        BLUB_LAUNCH(pcg_dot_kernel, grid, block, 0, stream, g, t, st, ta, s, scal, partials_);
         const bool with_err = (max_it == i) || (i > 0 && i % freq == 0); // pressure_solver.rs:676-677
         if (mode == 0) {
             if (with_err)
-                BLUB_LAUNCH((pcg_update_kernel<0, true>), t.nblocks, PCG_THREADS, 0, stream, g, t, marker, p, r, s, scal, partials_, dparams, which, i, max_it);
+                BLUB_LAUNCH((pcg_update_kernel<0, true>), grid, block, 0, stream, g, t, st, ta, p, r, s, scal, partials_, dparams, which, i, max_it);
             else
-                BLUB_LAUNCH((pcg_update_kernel<0, false>), t.nblocks, PCG_THREADS, 0, stream, g, t, marker, p, r, s, scal, partials_, dparams, which, i, max_it);
+                BLUB_LAUNCH((pcg_update_kernel<0, false>), grid, block, 0, stream, g, t, st, ta, p, r, s, scal, partials_, dparams, which, i, max_it);
         } else {
             if (with_err)
-                BLUB_LAUNCH((pcg_update_kernel<1, true>), t.nblocks, PCG_THREADS, 0, stream, g, t, marker, p, r, s, scal, partials_, dparams, which, i, max_it);
+                BLUB_LAUNCH((pcg_update_kernel<1, true>), grid, block, 0, stream, g, t, st, ta, p, r, s, scal, partials_, dparams, which, i, max_it);
             else
-                BLUB_LAUNCH((pcg_update_kernel<1, false>), t.nblocks, PCG_THREADS, 0, stream, g, t, marker, p, r, s, scal, partials_, dparams, which, i, max_it);
+                BLUB_LAUNCH((pcg_update_kernel<1, false>), grid, block, 0, stream, g, t, st, ta, p, r, s, scal, partials_, dparams, which, i, max_it);
         }
         if (i >= max_it) break; // :699-701
         if (mode == 0) {
-            BLUB_LAUNCH(pcg_search_kernel<0>, t.nblocks, PCG_THREADS, 0, stream, g, t, marker, s, r, scal);
+            BLUB_LAUNCH(pcg_search_kernel<0>, grid, block, 0, stream, g, t, st, ta, s, r, scal);
         } else {
-            BLUB_LAUNCH(pcg_precond_pass_kernel, t.nblocks, PCG_THREADS, 0, stream, g, t, marker, r, aux_temp_.ptr, r, 0, 0, scal, partials_);
-            BLUB_LAUNCH(pcg_precond_pass_kernel, t.nblocks, PCG_THREADS, 0, stream, g, t, marker, aux_temp_.ptr, aux_.ptr, r, 1, 3, scal, partials_);
-            BLUB_LAUNCH(pcg_search_kernel<1>, t.nblocks, PCG_THREADS, 0, stream, g, t, marker, s, aux_.ptr, scal);
+            BLUB_LAUNCH(pcg_precond_pass_kernel, grid, block, 0, stream, g, t, st, ta, r, aux_temp_.ptr, r, 0, 0, scal, partials_);
+            BLUB_LAUNCH(pcg_precond_pass_kernel, grid, block, 0, stream, g, t, st, ta, aux_temp_.ptr, aux_.ptr, r, 1, 3, scal, partials_);
+            BLUB_LAUNCH(pcg_search_kernel<1>, grid, block, 0, stream, g, t, st, ta, s, aux_.ptr, scal);
         }
     }
 }

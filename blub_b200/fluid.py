@@ -97,6 +97,8 @@ def lib():
         "blub_fluid_last_solve": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
         "blub_fluid_time_solve": (C.c_int, [vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_float)]),
         "blub_fluid_time_steps": (C.c_int, [vp, C.c_double, C.c_int, C.POINTER(C.c_float)]),
+        "blub_fluid_step_timed": (C.c_int, [vp, C.c_double, C.POINTER(C.c_float)]),
+        "blub_fluid_set_graph_replay": (C.c_int, [vp, C.c_int]),
         "blub_kernel_launch_count": (C.c_uint64, [C.c_int]),
     }
     for name, (res, args) in sig.items():
@@ -258,6 +260,14 @@ class HybridFluid:
         ms = (C.c_float * repetitions)()
         _check(self.L.blub_fluid_time_solve(self.h, which, dt, repetitions, ms))
         return [float(x) for x in ms]
+
+    def step_timed(self, dt=DT_120HZ):
+        ms = (C.c_float * 14)()
+        _check(self.L.blub_fluid_step_timed(self.h, dt, ms))
+        return [float(x) for x in ms]
+
+    def set_graph_replay(self, enabled):
+        _check(self.L.blub_fluid_set_graph_replay(self.h, 1 if enabled else 0))
 
     def time_steps(self, dt, steps):
         ms = C.c_float(0)

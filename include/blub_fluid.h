@@ -167,6 +167,10 @@ int blub_fluid_last_solve(BlubFluid *fluid, int which, float *max_error, int32_t
 int blub_fluid_time_solve(BlubFluid *fluid, int which, double simulation_delta_seconds, int repetitions, float *ms_each);
 /* device time of `steps` consecutive blub_fluid_step calls between two CUDA events on the fluid's stream (synchronises) */
 int blub_fluid_time_steps(BlubFluid *fluid, double simulation_delta_seconds, int steps, float *ms_total);
+/* one eagerly launched step with CUDA events between the 14 stages (same numbering as blub_fluid_step_stages); synchronises */
+int blub_fluid_step_timed(BlubFluid *fluid, double simulation_delta_seconds, float ms_per_stage[14]);
+/* blub_fluid_step replays a captured CUDA graph of the step by default; 0 = launch every kernel eagerly instead */
+int blub_fluid_set_graph_replay(BlubFluid *fluid, int enabled);
 /* number of kernels launched by this library since the last reset (bench.py's gpu_launches) */
 uint64_t blub_kernel_launch_count(int reset);
 

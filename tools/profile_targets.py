@@ -22,6 +22,19 @@ if mode == "step":
         f.step(F.DT_120HZ)
     f.synchronize()
     print("launches", blub_b200.kernel_launch_count())
+elif mode == "stages":
+    scene = sys.argv[2] if len(sys.argv) > 2 else "dam_256"
+    f = blub_b200.HybridFluid.from_scene(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".json"))
+    from oracle.oracle import STAGES
+    for _ in range(3):
+        f.step(F.DT_120HZ)
+    acc = np.zeros(14)
+    reps = 5
+    for _ in range(reps):
+        acc += np.array(f.step_timed(F.DT_120HZ))
+    for name, ms in zip(STAGES, acc / reps):
+        print(f"{name:24s} {ms:8.3f} ms")
+    print(f"{'total':24s} {acc.sum() / reps:8.3f} ms (eager launches, events between stages)")
 else:
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     solves = int(sys.argv[3]) if len(sys.argv) > 3 else 2
