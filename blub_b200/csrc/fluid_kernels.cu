@@ -33,21 +33,20 @@ __device__ __forceinline__ float signf(float x) { return x > 0.0f ? 1.0f : (x < 
 // 1.0 on axis c (transfer_build_linkedlist.comp:21-23), and contributes to the eight faces d + {0,1}^3 -- exactly the
 // set of (face, particle) pairs the reference's gather visits (transfer_gather_velocity.comp:39-97) -- with
 //   weight = prod_k sat(1 - |q_k - pos_k|),  value = row_c . (q - pos, 1)          (:23-31)
-// MARK: also set marker[trunc(pos)] = FLUID (transfer_build_linkedlist.comp:17-19).
+// (sum w*value, sum w) of a face are interleaved as one float2 so that each contribution is a single 8-byte vector
+// reduction.  MARK: also set marker[trunc(pos)] = FLUID (transfer_build_linkedlist.comp:17-19).
 template <bool MARK>
 __global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepParams *__restrict__ params,
                                                          const float4 *__restrict__ pos, const float4 *__restrict__ rowx,
                                                          const float4 *__restrict__ rowy, const float4 *__restrict__ rowz,
-                                                         float *__restrict__ ux, float *__restrict__ uy, float *__restrict__ uz,
-                                                         float *__restrict__ wx, float *__restrict__ wy, float *__restrict__ wz,
+                                                         float2 *__restrict__ nwx, float2 *__restrict__ nwy, float2 *__restrict__ nwz,
                                                          int8_t *__restrict__ marker) {
     const uint32_t i = blockIdx.x * PT + threadIdx.x;
     if (i >= params->num_particles) return;
     const float4 p = pos[i];
     if (MARK) marker[lin(g, (int)p.x, (int)p.y, (int)p.z)] = (int8_t)CELL_FLUID;
     const float4 rows[3] = {rowx[i], rowy[i], rowz[i]};
-    float *const num[3] = {ux, uy, uz};
-    float *const den[3] = {wx, wy, wz};
+    float2 *const nw[3] = {nwx, nwy, nwz};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float ox = c == 0 ? 1.0f : 0.5f, oy = c == 1 ? 1.0f : 0.5f, oz = c == 2 ? 1.0f : 0.5f;
@@ -70,22 +69,42 @@ __global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepPa
                     if (w <= 0.0f) continue;
                     const float v = r.x * tx[ox_] + r.y * ty[oy_] + r.z * tz[oz_] + r.w;
                     const int64_t f = base + ox_ + (int64_t)oy_ * g.sy + (int64_t)oz_ * g.sz;
-                    atomicAdd(num[c] + f, w * v);
-                    atomicAdd(den[c] + f, w);
+                    // one 8-byte vector reduction (RED.E.ADD.F32x2) per face instead of two scalar ones
+                    atomicAdd(nw[c] + f, make_float2(w * v, w));
                 }
     }
 }
 
-// transfer_set_boundary_marker.comp:11-20
-__global__ void __launch_bounds__(PT) boundary_marker_kernel(GridDim g, int8_t *__restrict__ marker, const uint2 *__restrict__ vox) {
-    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
-    if (i >= g.n) return;
+// transfer_set_boundary_marker.comp:11-20.  Also publishes two coarse occupancy maps of the finished marker volume,
+// used by the extrapolation pass to reject cells that have no FLUID cell anywhere near them:
+//   seg_fluid[cell / seg_w]  any FLUID cell in the seg_w x-consecutive cells (seg_w = 32, or 8 when nx % 32 != 0)
+//   row_fluid[z * ny + y]    any FLUID cell in the row (must be zeroed before the launch)
+__global__ void __launch_bounds__(PT) boundary_marker_kernel(GridDim g, int8_t *__restrict__ marker, const uint2 *__restrict__ vox,
+                                                             uint8_t *__restrict__ seg_fluid, uint8_t *__restrict__ row_fluid, int seg_w) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x; // g.n is a multiple of 512: no partial warps
     int x, y, z;
     cell_of(g, i, x, y, z);
+    int m = marker[i];
     if (x == 0 || y == 0 || z == 0 || x == g.nx - 1 || y == g.ny - 1 || z == g.nz - 1) {
-        marker[i] = (int8_t)CELL_SOLID;
+        m = CELL_SOLID;
+        marker[i] = (int8_t)m;
     } else if (vox != nullptr) {
-        if (load_voxel(vox, i).w != 0.0f) marker[i] = (int8_t)CELL_SOLID;
+        if (load_voxel(vox, i).w != 0.0f) {
+            m = CELL_SOLID;
+            marker[i] = (int8_t)m;
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, m == CELL_FLUID);
+    const int lane = threadIdx.x & 31;
+    if (seg_w == 32) {
+        if (lane == 0) {
+            seg_fluid[i >> 5] = ballot ? 1 : 0;
+            if (ballot) row_fluid[z * g.ny + y] = 1;
+        }
+    } else if ((lane & 7) == 0) {
+        const unsigned b = (ballot >> lane) & 0xffu;
+        seg_fluid[i >> 3] = b ? 1 : 0;
+        if (b) row_fluid[z * g.ny + y] = 1;
     }
 }
 
@@ -94,28 +113,26 @@ __global__ void __launch_bounds__(PT) boundary_marker_kernel(GridDim g, int8_t *
 __global__ void __launch_bounds__(PT) p2g_normalize_kernel(GridDim g, const StepParams *__restrict__ params,
                                                            const int8_t *__restrict__ marker, float *__restrict__ ux,
                                                            float *__restrict__ uy, float *__restrict__ uz,
-                                                           const float *__restrict__ wx, const float *__restrict__ wy,
-                                                           const float *__restrict__ wz) {
+                                                           const float2 *__restrict__ nwx, const float2 *__restrict__ nwy,
+                                                           const float2 *__restrict__ nwz) {
     const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
     if (i >= g.n) return;
     const int ma = marker[i];
     const int mb[3] = {marker[i + 1], marker[i + g.sy], marker[i + g.sz]};
     float *const u[3] = {ux, uy, uz};
-    const float *const w[3] = {wx, wy, wz};
+    const float2 *const nw[3] = {nwx, nwy, nwz};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float out = 0.0f;
         if (ma == CELL_FLUID || mb[c] == CELL_FLUID) {
             if (ma != CELL_SOLID && mb[c] != CELL_SOLID) {
-                float v = u[c][i];
-                const float wt = w[c][i];
-                if (wt > 0.0f) v /= wt;
+                const float2 a = nw[c][i];
+                float v = a.x;
+                if (a.y > 0.0f) v /= a.y;
                 out = v + params->gravity_dt[c];
             }
-            u[c][i] = out;
-        } else {
-            u[c][i] = 0.0f;
         }
+        u[c][i] = out;
     }
 }
 
@@ -208,13 +225,32 @@ __device__ __forceinline__ bool valid_velocity(const GridDim &g, const int8_t *_
     const bool in = c == 0 ? x + 1 < g.nx : (c == 1 ? y + 1 < g.ny : z + 1 < g.nz);
     return in && marker[n] == CELL_FLUID;
 }
-__global__ void __launch_bounds__(PT) extrapolate_kernel(GridDim g, const int8_t *__restrict__ marker, float *__restrict__ ux,
+__global__ void __launch_bounds__(PT) extrapolate_kernel(GridDim g, const int8_t *__restrict__ marker, const uint8_t *__restrict__ seg_fluid,
+                                                         const uint8_t *__restrict__ row_fluid, int seg_shift, float *__restrict__ ux,
                                                          float *__restrict__ uy, float *__restrict__ uz) {
     const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
     if (i >= g.n) return;
     if (marker[i] == CELL_FLUID) return;
     int x, y, z;
     cell_of(g, i, x, y, z);
+    // Quick reject: a face is only written if a FLUID cell lies in [x-1,x+2] x [y-1,y+2] x [z-1,z+2] (the in-plane ring of
+    // candidate faces plus their +e_c neighbours).  Rows first (warp-uniform loads), then x-segments.
+    {
+        const int y0 = max(y - 1, 0), y1 = min(y + 2, g.ny - 1), z0 = max(z - 1, 0), z1 = min(z + 2, g.nz - 1);
+        bool near = false;
+        for (int zz = z0; zz <= z1; ++zz)
+            for (int yy = y0; yy <= y1; ++yy) near = near || row_fluid[zz * g.ny + yy];
+        if (!near) return;
+        near = false;
+        const int s0 = max(x - 1, 0) >> seg_shift, s1 = min(x + 2, g.nx - 1) >> seg_shift, segs = g.nx >> seg_shift;
+        for (int zz = z0; zz <= z1; ++zz)
+            for (int yy = y0; yy <= y1; ++yy) {
+                if (!row_fluid[zz * g.ny + yy]) continue;
+                const uint8_t *row = seg_fluid + (int64_t)(zz * g.ny + yy) * segs;
+                for (int ss = s0; ss <= s1; ++ss) near = near || row[ss];
+            }
+        if (!near) return;
+    }
     float *const u[3] = {ux, uy, uz};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -588,19 +624,20 @@ inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 
 } // namespace
 
 // ------------------------------------------------------------------------------------------------ launchers
+static void run_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, const uint2 *vox, const MarkerFlags &flags) {
+    BLUB_CUDA_CHECK(cudaMemsetAsync(flags.row_fluid, 0, (size_t)g.ny * g.nz, st));
+    BLUB_LAUNCH(boundary_marker_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, vox, flags.seg_fluid, flags.row_fluid, 1 << flags.seg_shift);
+}
+
 void launch_p2g(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float4 *const row[3],
-                float *const u[3], float *const w[3], int8_t *marker, const uint2 *vox) {
-    // transfer_clear.comp: marker <- AIR; the num / weight volumes replace the linked-list head volume
+                float *const u[3], float2 *const nw[3], int8_t *marker, const uint2 *vox, const MarkerFlags &flags) {
+    // transfer_clear.comp: marker <- AIR; the (num, weight) volumes replace the linked-list head volume
     BLUB_CUDA_CHECK(cudaMemsetAsync(marker, 0xFF, (size_t)g.n, st));
-    for (int c = 0; c < 3; ++c) {
-        BLUB_CUDA_CHECK(cudaMemsetAsync(u[c], 0, (size_t)g.n * sizeof(float), st));
-        BLUB_CUDA_CHECK(cudaMemsetAsync(w[c], 0, (size_t)g.n * sizeof(float), st));
-    }
+    for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(nw[c], 0, (size_t)g.n * sizeof(float2), st));
     if (np_upper > 0)
-        BLUB_LAUNCH(p2g_scatter_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2],
-                    w[0], w[1], w[2], marker);
-    BLUB_LAUNCH(boundary_marker_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, vox);
-    BLUB_LAUNCH(p2g_normalize_kernel, blocks_for(g.n, PT), PT, 0, st, g, params, marker, u[0], u[1], u[2], w[0], w[1], w[2]);
+        BLUB_LAUNCH(p2g_scatter_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
+    run_boundary_marker(st, g, marker, vox, flags);
+    BLUB_LAUNCH(p2g_normalize_kernel, blocks_for(g.n, PT), PT, 0, st, g, params, marker, u[0], u[1], u[2], nw[0], nw[1], nw[2]);
 }
 
 void launch_divergence_compute(cudaStream_t st, const GridDim &g, const int8_t *marker, float *const u[3], const uint2 *vox, float *rhs) {
@@ -611,8 +648,8 @@ void launch_divergence_remove(cudaStream_t st, const GridDim &g, const int8_t *m
     BLUB_LAUNCH(divergence_remove_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, p, vox, u[0], u[1], u[2]);
 }
 
-void launch_extrapolate(cudaStream_t st, const GridDim &g, const int8_t *marker, float *const u[3]) {
-    BLUB_LAUNCH(extrapolate_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, u[0], u[1], u[2]);
+void launch_extrapolate(cudaStream_t st, const GridDim &g, const int8_t *marker, const MarkerFlags &flags, float *const u[3]) {
+    BLUB_LAUNCH(extrapolate_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, flags.seg_fluid, flags.row_fluid, flags.seg_shift, u[0], u[1], u[2]);
 }
 
 void launch_clear_marker(cudaStream_t st, const GridDim &g, int8_t *marker) {
@@ -625,8 +662,8 @@ void launch_advect(cudaStream_t st, const GridDim &g, const StepParams *params, 
     BLUB_LAUNCH(advect_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2], vox, marker);
 }
 
-void launch_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, const uint2 *vox) {
-    BLUB_LAUNCH(boundary_marker_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, vox);
+void launch_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, const uint2 *vox, const MarkerFlags &flags) {
+    run_boundary_marker(st, g, marker, vox, flags);
 }
 
 void launch_density_rhs(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos,

@@ -36,10 +36,15 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
         BLUB_CUDA_CHECK(cudaMalloc(&row_[c], pbytes));
         BLUB_CUDA_CHECK(cudaMemset(row_[c], 0, pbytes));
         u_[c].alloc(grid_);
-        weight_[c].alloc(grid_);
+        numw_[c].alloc(grid_);
     }
     density_.alloc(grid_);
     marker_.alloc(grid_);
+    seg_shift_ = (nx % 32 == 0) ? 5 : 3;
+    BLUB_CUDA_CHECK(cudaMalloc(&seg_fluid_, (size_t)(grid_.n >> seg_shift_)));
+    BLUB_CUDA_CHECK(cudaMalloc(&row_fluid_, (size_t)ny * nz));
+    BLUB_CUDA_CHECK(cudaMemset(seg_fluid_, 0, (size_t)(grid_.n >> seg_shift_)));
+    BLUB_CUDA_CHECK(cudaMemset(row_fluid_, 0, (size_t)ny * nz));
     BLUB_CUDA_CHECK(cudaMalloc(&cell_count_, (size_t)grid_.n * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMalloc(&block_sums_, (size_t)(binning_scan_blocks(grid_) + 1024) * sizeof(uint32_t)));
     solver_.reset(new PressureSolver(grid_));
@@ -70,11 +75,13 @@ HybridFluid::~HybridFluid() {
     for (int c = 0; c < 3; ++c) {
         cudaFree(row_[c]);
         u_[c].release();
-        weight_[c].release();
+        numw_[c].release();
     }
     density_.release();
     marker_.release();
     cudaFree(cell_count_);
+    cudaFree(seg_fluid_);
+    cudaFree(row_fluid_);
     cudaFree(block_sums_);
     solver_.reset();
     field_velocity_.reset();
@@ -202,11 +209,12 @@ void HybridFluid::upload_step_params(float dt) {
 // Stage numbering shared with oracle/blub_oracle.c:orc_step_stages (the order of hybrid_fluid.rs:798-974).
 void HybridFluid::run_stage(int stage, float dt) {
     float *u[3] = {u_[0].ptr, u_[1].ptr, u_[2].ptr};
-    float *w[3] = {weight_[0].ptr, weight_[1].ptr, weight_[2].ptr};
+    float2 *nw[3] = {numw_[0].ptr, numw_[1].ptr, numw_[2].ptr};
+    const MarkerFlags flags = {seg_fluid_, row_fluid_, seg_shift_};
     const uint32_t np = num_particles_;
     switch (stage) {
     case 0: // transfer particle velocity to grid (:806-833)
-        launch_p2g(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, w, marker_.ptr, voxels_);
+        launch_p2g(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, nw, marker_.ptr, voxels_, flags);
         break;
     case 1: // compute divergence -> PCG residual (:835-840)
         launch_divergence_compute(stream_, grid_, marker_.ptr, u, voxels_, solver_->residual());
@@ -225,7 +233,7 @@ void HybridFluid::run_stage(int stage, float dt) {
         launch_divergence_remove(stream_, grid_, marker_.ptr, field_velocity_->pressure(), voxels_, u);
         break;
     case 5: // extrapolate velocity grid (:906-909)
-        launch_extrapolate(stream_, grid_, marker_.ptr, u);
+        launch_extrapolate(stream_, grid_, marker_.ptr, flags, u);
         break;
     case 6: // clear marker (& linked list) grids (:911-916)
         launch_clear_marker(stream_, grid_, marker_.ptr);
@@ -234,7 +242,7 @@ void HybridFluid::run_stage(int stage, float dt) {
         launch_advect(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, voxels_, marker_.ptr);
         break;
     case 8: // density projection: set boundary marker (:923-927)
-        launch_boundary_marker(stream_, grid_, marker_.ptr, voxels_);
+        launch_boundary_marker(stream_, grid_, marker_.ptr, voxels_, flags);
         break;
     case 9: // density projection: compute density error (:928-932)
         launch_density_rhs(stream_, grid_, params_dev_, np, pos_[cur_], marker_.ptr, density_.ptr, solver_->residual());
@@ -247,7 +255,7 @@ void HybridFluid::run_stage(int stage, float dt) {
         launch_position_change(stream_, grid_, params_dev_, marker_.ptr, field_density_->pressure(), u);
         break;
     case 12: // extrapolate (:963-966)
-        launch_extrapolate(stream_, grid_, marker_.ptr, u);
+        launch_extrapolate(stream_, grid_, marker_.ptr, flags, u);
         break;
     case 13: // correct particle density error (:968-972)
         launch_correct_particles(stream_, grid_, params_dev_, np, pos_[cur_], marker_.ptr, u);

@@ -147,7 +147,7 @@ def test_stagewise_parity_one_step(precond):
     eo, io = orc.last_solve(0)
     eg, ig = gpu.last_solve(0)
     assert io == ig, (io, ig)
-    grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), "p1", rel=2e-3, abs_=1e-4)
+    grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), "p1", rel=5e-3, abs_=1e-4)
     # continue from the ORACLE's pressure so that solver round-off does not leak into the per-stage comparison
     gpu.upload_grid(F.TAP_P_VEL, orc.grid(O.ARR_P_VEL))
     run(3, 5)  # (binning off) + divergence_remove
@@ -172,7 +172,7 @@ def test_stagewise_parity_one_step(precond):
     grid_close(orc.grid(O.ARR_RESIDUAL), gpu.download_grid(F.TAP_RESIDUAL), "rhs2", rel=1e-4, abs_=2e-3, mask=fl)
     run(10, 11)  # solve 2
     assert orc.last_solve(1)[1] == gpu.last_solve(1)[1]
-    grid_close(orc.grid(O.ARR_P_DEN), gpu.download_grid(F.TAP_P_DEN), "p2", rel=2e-3, abs_=1e-4)
+    grid_close(orc.grid(O.ARR_P_DEN), gpu.download_grid(F.TAP_P_DEN), "p2", rel=5e-3, abs_=1e-4)
     gpu.upload_grid(F.TAP_P_DEN, orc.grid(O.ARR_P_DEN))
     run(11, 13)  # position change + extrapolate
     for c, (tg, to) in enumerate(STAGE_TAPS):

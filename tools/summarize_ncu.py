@@ -1,0 +1,64 @@
+"""Turns ncu outputs (brought back in gpurun_out/) into the small text summaries kept under profiles/.
+
+    python tools/summarize_ncu.py launches gpurun_out/launches_step_v1.csv > profiles/r01_v1_launches_step.md
+    python tools/summarize_ncu.py report gpurun_out/pcg_v1.ncu-rep > profiles/r01_v1_pcg_kernels.md
+"""
+import collections
+import csv
+import io
+import re
+import subprocess
+import sys
+
+METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "smsp__inst_executed.sum", "smsp__cycles_active.avg", "sm__inst_executed_pipe_lsu.sum", "launch__occupancy_limit_registers",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def short(name):
+    name = re.sub(r"\(.*", "", name)
+    return name.replace("blub::<unnamed>::", "").replace("void ", "").replace("unnamed>::", "")
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    tot = 0.0
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        v = {"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(row["Metric Unit"], v)
+        k = short(row["Kernel Name"])
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+        tot += v
+    print(f"# ncu launch list: {path}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare SHARES)\n")
+    print(f"total {tot:.1f} us over {sum(a[0] for a in agg.values())} launches\n")
+    print("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|")
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{k}` | {c} | {t:.1f} | {t / c:.1f} | {100 * t / tot:.1f}% |")
+
+
+def report(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    print(f"# ncu --set full: {path}\n")
+    for r in rows[2:]:
+        print(f"## `{short(r[idx['Kernel Name']])}`  grid {r[idx['launch__grid_size']]} x block {r[idx['launch__block_size']]}\n")
+        print("| metric | value | unit |\n|---|---:|---|")
+        for m in METRICS:
+            if m in idx:
+                print(f"| {m} | {r[idx[m]]} | {units[idx[m]]} |")
+        print()
+
+
+if __name__ == "__main__":
+    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
