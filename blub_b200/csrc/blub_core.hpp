@@ -107,8 +107,14 @@ class PressureSolver {
     GridArray<float> residual_, search_, aux_, aux_temp_;
     GridArray<uint8_t> codes_;       // per-cell code (diag | fluid << 3), rebuilt from the markers at the start of every solve
     uint8_t *tile_active_ = nullptr; // per-tile "contains FLUID" flag
-    float *partials_ = nullptr;      // per-tile partial sums / maxima, 2 * tiles
+    float *partials_ = nullptr;      // per-tile partial sums / maxima, 2 * tiles (+ slack for the persistent solver)
+    int *tile_list_ = nullptr;       // compacted ids of the active tiles
+    int *num_active_ = nullptr;
     int num_blocks_ = 0;
+    int persistent_blocks_ = 0;      // co-resident blocks of the cooperative solver; 0 = not available
+
+  public:
+    bool use_persistent = true;      // one cooperative launch per solve (diag2 preconditioner); false = three kernels per iteration
 };
 
 // HybridFluid, hybrid_fluid.rs:24-72,92-977
@@ -140,6 +146,7 @@ class HybridFluid {
     bool use_graph = true; // replay the step as a CUDA graph (BLUB_NO_GRAPH=1 disables)
     void solve_only(int which, double simulation_delta_seconds);
     void synchronize();
+    void invalidate_graphs() { destroy_graphs(); }
 
     Quirks quirks;
 

