@@ -110,6 +110,59 @@ def pcg_roofline(device, n=256, reps=5):
             "algorithmic_bytes_per_solve": bytes_alg, "peak_source": src, "iterations": it}
 
 
+def pcg_sharded(rank, world, local, n=512, reps=5):
+    """Strong-scaling PCG microbench: the n^3 all-fluid box cut into `world` z-slabs, one per GPU; boundary planes travel as
+    P2P stores inside the persistent kernel, scalars through peer mailboxes (windows exchanged once via CUDA IPC)."""
+    import numpy as np
+    import torch.distributed as dist
+
+    import blub_b200
+    from blub_b200 import fluid as F
+
+    nz_owned = n // world
+    f = blub_b200.HybridFluid.create_slab(n, n, nz_owned, 8, rank=rank, world=world, device=local)
+    handles = [None] * world
+    dist.all_gather_object(handles, f.ipc_export_window())
+    own = f.slab_window()[0]
+    windows = [own if k == rank else F.ipc_open(handles[k], local) for k in range(world)]
+    f.attach_slab_peers(windows)
+    halo = 4
+    z0 = rank * nz_owned - halo
+    m = np.zeros((nz_owned + 2 * halo, n, n), dtype=np.int8)
+    zz = np.arange(z0, z0 + nz_owned + 2 * halo)
+    inside = (zz >= 1) & (zz <= n - 2)
+    m[inside, 1:-1, 1:-1] = 1
+    rng = np.random.default_rng(1234 + rank)
+    b = rng.uniform(-1.0, 1.0, m.shape).astype(np.float32)
+    b[m != 1] = 0
+    b[:halo] = 0
+    b[halo + nz_owned:] = 0
+    f.upload_grid(F.TAP_MARKER, m)
+    f.upload_grid(F.TAP_RESIDUAL, b)
+    f.set_solver_config(0, error_tolerance=0.0, max_num_iterations=32, error_check_frequency=4)
+    dist.barrier()
+    f.time_solve(0, F.DT_120HZ, 2)
+    dist.barrier()
+    ms = f.time_solve(0, F.DT_120HZ, reps)
+    t = torch_max(sorted(ms)[len(ms) // 2])
+    e, it = f.last_solve(0)
+    dist.barrier()
+    f.close()
+    bytes_alg = (42 * 33 + 21) * n ** 3
+    return {"grid": f"{n}^3 all-fluid, {world} z-slabs of {nz_owned} planes", "ms_per_solve": round(t, 4), "iterations": it,
+            "aggregate_GBps": round(bytes_alg / (t * 1e-3) / 1e9, 1), "per_gpu_GBps": round(bytes_alg / (t * 1e-3) / 1e9 / world, 1),
+            "exchange": "in-kernel P2P stores + mailbox all-reduce over NVLink (no NCCL in the solve)"}
+
+
+def torch_max(x):
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def cpu_baseline_sample(workload, steps):
     """Oracle (CPU port of the reference's algorithm) timed on this box's host cores on `steps` steps of the workload."""
     from oracle import oracle as O
@@ -159,6 +212,7 @@ def main():
     ap.add_argument("--workload", default="dam_256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-sharded-pcg", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 2
@@ -226,6 +280,9 @@ def main():
     stats = fluid.pressure_solver_stats(0)[-1], fluid.pressure_solver_stats(1)[-1]
     fluid.close()
 
+    sharded = None
+    if world > 1 and not args.no_sharded_pcg:
+        sharded = pcg_sharded(rank, world, local)
     roof = cpu = None
     if rank == 0 and not args.no_roofline:
         roof = pcg_roofline(local)
@@ -248,6 +305,8 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
         }
+        if sharded is not None:
+            line["pcg_sharded"] = sharded
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -36,14 +36,23 @@ struct Quirks {
 template <class T> struct GridArray {
     T *base = nullptr; // allocation
     T *ptr = nullptr;  // cell 0
+    bool owned = true;
+    static size_t bytes_for(const GridDim &g) { return (((size_t)(g.n + 2 * g.pad) * sizeof(T)) + 255) / 256 * 256; }
     void alloc(const GridDim &g) {
         size_t bytes = (size_t)(g.n + 2 * g.pad) * sizeof(T);
         BLUB_CUDA_CHECK(cudaMalloc(&base, bytes));
         BLUB_CUDA_CHECK(cudaMemset(base, 0, bytes));
         ptr = base + g.pad;
+        owned = true;
+    }
+    // place the array in caller-owned, zero-initialised memory (the peer-visible slab window)
+    void place(const GridDim &g, void *mem) {
+        base = static_cast<T *>(mem);
+        ptr = base + g.pad;
+        owned = false;
     }
     void release() {
-        if (base) cudaFree(base);
+        if (base && owned) cudaFree(base);
         base = ptr = nullptr;
     }
 };
@@ -57,7 +66,7 @@ class PressureField {
     static constexpr size_t SOLVER_STATISTIC_HISTORY_LENGTH = 100; // pressure_solver.rs:101
     static constexpr int NUM_PRESSURE_ERROR_BUFFER = 32;           // pressure_solver.rs:49
 
-    PressureField(const GridDim &grid, const SolverConfig &config);
+    PressureField(const GridDim &grid, const SolverConfig &config, void *external_volume = nullptr);
     ~PressureField();
     PressureField(const PressureField &) = delete;
 
@@ -92,7 +101,7 @@ class PressureField {
 // PressureSolver, pressure_solver.rs:22-47,228-729: scratch volumes shared by both solves and the PCG recording.
 class PressureSolver {
   public:
-    PressureSolver(const GridDim &grid);
+    PressureSolver(const GridDim &grid, void *external_residual = nullptr);
     ~PressureSolver();
     PressureSolver(const PressureSolver &) = delete;
 
@@ -101,6 +110,7 @@ class PressureSolver {
     // PressureSolver::solve, pressure_solver.rs:591-729.  Enqueue-only.
     void solve(cudaStream_t stream, PressureField &field, int which, const int8_t *marker, const StepParams *dparams,
                const Quirks &quirks);
+    SlabComm comm; // filled by HybridFluid::attach_slab_peers; world == 1 when not sharded
 
   private:
     GridDim grid_;
@@ -122,7 +132,10 @@ class HybridFluid {
   public:
     static constexpr uint32_t PARTICLES_PER_GRID_CELL = 8; // hybrid_fluid.rs:90
 
-    HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num_particles, int device, cudaStream_t stream);
+    // slab_world > 1: this fluid is rank `slab_rank` of a z-slab decomposition; `nz` is the number of OWNED planes and the
+    // local grid gets SLAB_HALO ghost planes on both sides (see SlabComm).
+    HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num_particles, int device, cudaStream_t stream, int slab_rank = 0,
+                int slab_world = 1);
     ~HybridFluid();
     HybridFluid(const HybridFluid &) = delete;
 
@@ -146,6 +159,12 @@ class HybridFluid {
     bool use_graph = true; // replay the step as a CUDA graph (BLUB_NO_GRAPH=1 disables)
     void solve_only(int which, double simulation_delta_seconds);
     void synchronize();
+    // peer-visible window (residual, both pressure volumes, mailbox) of a slab rank, and the peers' windows as mapped here
+    void *slab_window() const { return window_; }
+    size_t slab_window_bytes() const { return window_bytes_; }
+    void attach_slab_peers(void *const *windows, int world);
+    int slab_rank() const { return slab_rank_; }
+    int slab_world() const { return slab_world_; }
     void invalidate_graphs() { destroy_graphs(); }
 
     Quirks quirks;
@@ -207,6 +226,10 @@ class HybridFluid {
 
     std::unique_ptr<PressureSolver> solver_;
     std::unique_ptr<PressureField> field_velocity_, field_density_;
+
+    int slab_rank_ = 0, slab_world_ = 1;
+    void *window_ = nullptr;
+    size_t window_bytes_ = 0;
 
     StepParams *params_dev_ = nullptr;
     StepParams *params_host_ = nullptr; // pinned ring of 64

@@ -84,6 +84,70 @@ int blub_fluid_create(BlubFluid **out, uint32_t nx, uint32_t ny, uint32_t nz, ui
 
 void blub_fluid_destroy(BlubFluid *fluid) { delete fluid; }
 
+int blub_fluid_create_slab(BlubFluid **out, uint32_t nx, uint32_t ny, uint32_t nz_owned, uint32_t max_num_particles, int device, void *cuda_stream,
+                           int rank, int world) {
+    if (!out) return fail(BLUB_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    return guarded([&] {
+        std::unique_ptr<BlubFluid> f(new BlubFluid());
+        f->impl.reset(new blub::HybridFluid(nx, ny, nz_owned, max_num_particles, device, static_cast<cudaStream_t>(cuda_stream), rank, world));
+        *out = f.release();
+        return BLUB_OK;
+    });
+}
+
+int blub_fluid_slab_window(BlubFluid *fluid, void **window, size_t *bytes) {
+    if (!fluid || !window || !bytes) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *window = fluid->impl->slab_window();
+    *bytes = fluid->impl->slab_window_bytes();
+    return *window ? BLUB_OK : fail(BLUB_ERR_INVALID_ARGUMENT, "not a slab rank");
+}
+
+int blub_fluid_attach_slab_peers(BlubFluid *fluid, void *const *windows, int world) {
+    if (!fluid) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL fluid");
+    return guarded([&] { fluid->impl->attach_slab_peers(windows, world); return BLUB_OK; });
+}
+
+int blub_ipc_export(const void *device_ptr, unsigned char handle[64]) {
+    if (!device_ptr || !handle) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+        cudaIpcMemHandle_t h;
+        BLUB_CUDA_CHECK(cudaIpcGetMemHandle(&h, const_cast<void *>(device_ptr)));
+        std::memcpy(handle, &h, 64);
+        return BLUB_OK;
+    });
+}
+
+int blub_ipc_open(const unsigned char handle[64], int device, void **out) {
+    if (!handle || !out) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle, 64);
+        BLUB_CUDA_CHECK(cudaSetDevice(device));
+        BLUB_CUDA_CHECK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+        return BLUB_OK;
+    });
+}
+
+int blub_ipc_close(void *mapped) {
+    if (!mapped) return BLUB_OK;
+    return guarded([&] { BLUB_CUDA_CHECK(cudaIpcCloseMemHandle(mapped)); return BLUB_OK; });
+}
+
+int blub_enable_peer_access(int device, int peer) {
+    return guarded([&] {
+        int can = 0;
+        BLUB_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, device, peer));
+        if (!can) return fail(BLUB_ERR_CUDA, "devices cannot access each other's memory");
+        BLUB_CUDA_CHECK(cudaSetDevice(device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) BLUB_CUDA_CHECK(e);
+        cudaGetLastError();
+        return BLUB_OK;
+    });
+}
+
 int blub_fluid_add_cube(BlubFluid *fluid, const float min_grid[3], const float max_grid[3]) {
     if (!fluid || !min_grid || !max_grid) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
     return guarded([&] { return fluid->impl->add_fluid_cube(min_grid, max_grid) ? BLUB_WARN_TRUNCATED : BLUB_OK; });

@@ -82,6 +82,22 @@ struct PcgScalars {
     int pad_;
 };
 
+// z-slab sharding of the pressure solve (the reference is single-GPU).  Every rank owns `owned_nz` planes
+// of the global grid and keeps SLAB_HALO ghost planes on both sides; local plane SLAB_HALO is the first owned one.
+// Ghost planes of r and p are written by the NEIGHBOUR's kernels (P2P stores into this rank's memory over NVLink);
+// scalars are all-reduced through per-rank mailboxes that every peer writes into directly.
+constexpr int SLAB_HALO = 4;  // == PCG_TZ: owned planes start on a tile boundary
+constexpr int SLAB_MAX_WORLD = 8;
+struct SlabComm {
+    int rank = 0, world = 1;
+    int halo = 0;                 // 0 = not sharded
+    int owned_nz = 0;
+    unsigned long long *mailbox[SLAB_MAX_WORLD] = {}; // mailbox[k] = rank k's mailbox as mapped here (own one included)
+    float *peer_r[2] = {nullptr, nullptr};            // residual volume of the lower / upper neighbour (cell 0), or null
+    float *peer_p[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; // [field][lower/upper]
+    unsigned int *seq = nullptr;  // device counter of all-reduce rounds done so far (identical on every rank)
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -9,8 +9,12 @@
 
 namespace blub {
 
-HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num_particles, int device, cudaStream_t stream)
-    : device_(device), stream_(stream), owns_stream_(false), max_num_particles_(max_num_particles) {
+HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num_particles, int device, cudaStream_t stream, int slab_rank,
+                         int slab_world)
+    : device_(device), stream_(stream), owns_stream_(false), max_num_particles_(max_num_particles), slab_rank_(slab_rank), slab_world_(slab_world) {
+    if (slab_world < 1 || slab_world > SLAB_MAX_WORLD || slab_rank < 0 || slab_rank >= slab_world) throw std::invalid_argument("bad slab rank / world");
+    const uint32_t owned_nz = nz;
+    if (slab_world > 1) nz += 2 * SLAB_HALO; // ghost planes on both sides
     // the reference dispatches 8^3 groups without guards (hybrid_fluid.rs:735-741) and asserts N > 16384 (pressure_solver.rs:551)
     if (nx == 0 || ny == 0 || nz == 0 || nx % 8 || ny % 8 || nz % 8) throw std::invalid_argument("grid dimensions must be positive multiples of 8");
     if ((uint64_t)nx * ny * nz <= 16384) throw std::invalid_argument("grid must have more than 16384 cells");
@@ -47,10 +51,30 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
     BLUB_CUDA_CHECK(cudaMemset(row_fluid_, 0, (size_t)ny * nz));
     BLUB_CUDA_CHECK(cudaMalloc(&cell_count_, (size_t)grid_.n * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMalloc(&block_sums_, (size_t)(binning_scan_blocks(grid_) + 1024) * sizeof(uint32_t)));
-    solver_.reset(new PressureSolver(grid_));
     SolverConfig cfg; // defaults .1 / 32 / 4, hybrid_fluid.rs:253-257
-    field_velocity_.reset(new PressureField(grid_, cfg));
-    field_density_.reset(new PressureField(grid_, cfg));
+    if (slab_world_ > 1) {
+        // peer-visible window: [mailbox 4 KiB | residual | pressure (velocity) | pressure (density)], one cudaMalloc so that
+        // a single IPC handle (or peer pointer) exposes everything a neighbour writes into
+        const size_t vol = GridArray<float>::bytes_for(grid_);
+        window_bytes_ = 4096 + 3 * vol;
+        BLUB_CUDA_CHECK(cudaMalloc(&window_, window_bytes_));
+        BLUB_CUDA_CHECK(cudaMemset(window_, 0, window_bytes_));
+        char *w = static_cast<char *>(window_);
+        solver_.reset(new PressureSolver(grid_, w + 4096));
+        field_velocity_.reset(new PressureField(grid_, cfg, w + 4096 + vol));
+        field_density_.reset(new PressureField(grid_, cfg, w + 4096 + 2 * vol));
+        SlabComm &c = solver_->comm;
+        c.rank = slab_rank_;
+        c.world = 1; // becomes slab_world_ in attach_slab_peers
+        c.halo = SLAB_HALO;
+        c.owned_nz = (int)owned_nz;
+        BLUB_CUDA_CHECK(cudaMalloc(&c.seq, sizeof(unsigned int)));
+        BLUB_CUDA_CHECK(cudaMemset(c.seq, 0, sizeof(unsigned int)));
+    } else {
+        solver_.reset(new PressureSolver(grid_));
+        field_velocity_.reset(new PressureField(grid_, cfg));
+        field_density_.reset(new PressureField(grid_, cfg));
+    }
     BLUB_CUDA_CHECK(cudaMalloc(&params_dev_, sizeof(StepParams)));
     BLUB_CUDA_CHECK(cudaMallocHost(&params_host_, sizeof(StepParams) * 64));
     for (int k = 0; k < 64; ++k) BLUB_CUDA_CHECK(cudaEventCreateWithFlags(&param_events_[k], cudaEventDisableTiming));
@@ -83,9 +107,11 @@ HybridFluid::~HybridFluid() {
     cudaFree(seg_fluid_);
     cudaFree(row_fluid_);
     cudaFree(block_sums_);
+    if (solver_ && solver_->comm.seq) cudaFree(solver_->comm.seq);
     solver_.reset();
     field_velocity_.reset();
     field_density_.reset();
+    if (window_) cudaFree(window_);
     cudaFree(params_dev_);
     cudaFreeHost(params_host_);
     for (int k = 0; k < 64; ++k) cudaEventDestroy(param_events_[k]);
@@ -174,6 +200,29 @@ void HybridFluid::set_particles(uint32_t count, const float *pos4, const float *
     }
     BLUB_CUDA_CHECK(cudaStreamSynchronize(stream_));
     num_particles_ = count;
+}
+
+// windows[k] = rank k's slab window as mapped in THIS process (cudaIpcOpenMemHandle, or a plain peer pointer when all
+// ranks live in one process); windows[rank] must be this fluid's own window.
+void HybridFluid::attach_slab_peers(void *const *windows, int world) {
+    if (slab_world_ <= 1 || world != slab_world_ || !windows) throw std::invalid_argument("attach_slab_peers: not a slab rank / wrong world size");
+    if (windows[slab_rank_] != window_) throw std::invalid_argument("attach_slab_peers: windows[rank] is not this fluid's window");
+    destroy_graphs();
+    SlabComm &c = solver_->comm;
+    const size_t vol = GridArray<float>::bytes_for(grid_);
+    auto cell0 = [&](void *win, int volume) { return reinterpret_cast<float *>(static_cast<char *>(win) + 4096 + (size_t)volume * vol) + grid_.pad; };
+    for (int k = 0; k < world; ++k) {
+        if (!windows[k]) throw std::invalid_argument("attach_slab_peers: NULL window");
+        c.mailbox[k] = static_cast<unsigned long long *>(windows[k]);
+    }
+    for (int side = 0; side < 2; ++side) {
+        const int nb = slab_rank_ + (side == 0 ? -1 : 1);
+        const bool has = nb >= 0 && nb < world;
+        c.peer_r[side] = has ? cell0(windows[nb], 0) : nullptr;
+        c.peer_p[0][side] = has ? cell0(windows[nb], 1) : nullptr;
+        c.peer_p[1][side] = has ? cell0(windows[nb], 2) : nullptr;
+    }
+    c.world = world;
 }
 
 void HybridFluid::update_statistics() {

@@ -65,7 +65,7 @@ TileMap make_tilemap(const GridDim &g) {
 }
 
 struct TileCtx {
-    int tile;
+    int tile, tz;
     bool valid, first, last; // first/last quad of the block's row segment (x neighbours come from memory there)
     int i;                   // linear index of the quad in the block's first plane (fits: n < 2^31)
 };
@@ -74,6 +74,7 @@ __device__ __forceinline__ TileCtx tile_ctx_at(const GridDim &g, const TileMap &
     const int q = tx * t.bx + threadIdx.x;
     const int y = ty * t.by + threadIdx.y;
     c.tile = (tz * t.tiles_y + ty) * t.tiles_x + tx;
+    c.tz = tz;
     c.valid = q < t.qx && y < g.ny;
     c.first = threadIdx.x == 0;
     c.last = threadIdx.x == t.bx - 1 || q == t.qx - 1;
@@ -526,7 +527,53 @@ struct PcgSolveArgs {
     float *partials;        // 3 x gridDim.x
     const StepParams *params;
     int which, max_iterations, check_frequency;
+    SlabComm comm;          // world == 1: single GPU
 };
+
+// ---- cross-GPU all-reduce through peer-mapped mailboxes (z-slab sharding) ---------------------------------------
+// Round `seq` uses slot seq & 1.  Rank k stores {value bits, seq} as ONE 64-bit word into entry k of every rank's
+// mailbox (P2P store over NVLink), then every block of every rank spins on its OWN mailbox until all `world` entries
+// carry `seq` and adds them in rank order: identical result on every rank and in every block, no second barrier.
+// Two slots suffice: a rank can only be one round ahead of the slowest one, because finishing round n needs
+// everybody's n-th message.  The system-scope fences around it also publish / acquire the ghost planes pushed before.
+constexpr long long COMM_SPIN_LIMIT = 40LL * 1000 * 1000; // ~10 s: a dead peer ends the solve instead of hanging the GPU
+__device__ __forceinline__ void comm_allreduce(const SlabComm &c, unsigned seq, double &sum, float &mx, double *sh_sum, float *sh_max,
+                                               int *sh_dead) {
+    const int tid = linear_tid();
+    const int slot = (int)(seq & 1u) * 2 * SLAB_MAX_WORLD;
+    if (blockIdx.x == 0 && tid < c.world) {
+        __threadfence_system(); // everything this GPU wrote before (all blocks: ordered by the preceding grid barrier)
+        volatile unsigned long long *dst = c.mailbox[tid] + slot + 2 * c.rank;
+        dst[0] = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint((float)sum);
+        dst[1] = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(mx);
+    }
+    if (tid < c.world) {
+        volatile unsigned long long *src = c.mailbox[c.rank] + slot + 2 * tid;
+        unsigned long long v0 = 0, v1 = 0;
+        long long spins = 0;
+        bool ok = false;
+        while (!*sh_dead || spins == 0) {
+            v0 = src[0];
+            v1 = src[1];
+            if ((unsigned)(v0 >> 32) == seq && (unsigned)(v1 >> 32) == seq) { ok = true; break; }
+            if (++spins > COMM_SPIN_LIMIT) break;
+        }
+        if (!ok) *sh_dead = 1;
+        sh_sum[tid] = (double)__uint_as_float((unsigned)v0);
+        sh_max[tid] = __uint_as_float((unsigned)v1);
+    }
+    __threadfence_system(); // acquire: drop stale L1 lines of the ghost planes the peers just wrote
+    __syncthreads();
+    double t = 0.0;
+    float m = 0.0f;
+    for (int k = 0; k < c.world; ++k) {
+        t += sh_sum[k];
+        m = fmaxf(m, sh_max[k]);
+    }
+    __syncthreads();
+    sum = t;
+    mx = m;
+}
 
 // NOTE: r, s, p are written by other blocks between grid barriers: no __restrict__/read-only (LDG.NC) path for them.
 __device__ __forceinline__ float4 snew4(const float *r, const float *s, const uint8_t *__restrict__ codes, int i, float beta) {
@@ -558,11 +605,24 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_persistent_kernel(Pc
     __shared__ float sh[PCG_THREADS / 32];
     __shared__ double shd;
     __shared__ float shf;
+    __shared__ double sh_csum[SLAB_MAX_WORLD];
+    __shared__ float sh_cmax[SLAB_MAX_WORLD];
+    __shared__ int sh_dead;
     const GridDim g = a.g;
     const TileMap t = a.t;
+    const SlabComm &cm_ = a.comm;
+    const bool sharded = cm_.world > 1;
     const int nact = *a.num_active;
     const uint8_t *__restrict__ codes = a.codes;
     float *psumA = a.partials, *psumB = a.partials + gridDim.x, *pmax = a.partials + 2 * gridDim.x;
+    // slab geometry: tiles tz_first..tz_last are owned; the planes just outside are ghost planes fed by the neighbours
+    const int tz_first = cm_.halo / PCG_TZ, tz_last = t.tiles_z - 1 - cm_.halo / PCG_TZ;
+    const int push = cm_.owned_nz * g.sz; // index distance between an owned boundary plane and its image in the neighbour
+    float *const peer_r_lo = cm_.peer_r[0], *const peer_r_hi = cm_.peer_r[1];
+    unsigned seq = 0;
+    if (linear_tid() == 0) sh_dead = 0;
+    if (sharded) seq = *cm_.seq;
+    __syncthreads();
 
     // ---- init: r <- b - A p, sigma <- z.r (pressure_init.comp:45-83, pressure_solver.rs:625-649); s stays 0
     float acc = 0.0f;
@@ -586,6 +646,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_persistent_kernel(Pc
                 r4.z -= code.z ? Ap.z : 0.0f;
                 r4.w -= code.w ? Ap.w : 0.0f;
                 st4(a.r + i, r4);
+                if (sharded) { // boundary planes go straight into the neighbour's ghost planes (NVLink P2P stores)
+                    if (k == 0 && c.tz == tz_first && peer_r_lo) st4(peer_r_lo + i + push, r4);
+                    if (k == PCG_TZ - 1 && c.tz == tz_last && peer_r_hi) st4(peer_r_hi + i - push, r4);
+                }
                 acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
                        (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
             }
@@ -593,7 +657,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_persistent_kernel(Pc
             p0 = pp;
         }
     }
-    float sigma = (float)grid_sum(grid, psumB, acc, sh, &shd);
+    double tot = grid_sum(grid, psumB, acc, sh, &shd);
+    float gmax = 0.0f;
+    if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+    float sigma = (float)tot;
     float alpha = 0.0f, beta = 0.0f, max_error = 0.0f;
     int num_iterations = 0;
 
@@ -611,6 +678,9 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_persistent_kernel(Pc
                 cm = snew4(a.r, s_in, codes, i - g.sz, beta);
                 c0 = snew4(a.r, s_in, codes, i, beta);
                 code0 = ldcode(codes + i);
+                // ghost plane below an owned boundary tile: keep the recomputed s' so that phase B and the next
+                // iteration find it locally (bit-identical to what the neighbour computes for its own plane)
+                if (sharded && c.tz == tz_first) st4(s_out + i - g.sz, cm);
             }
 #pragma unroll
             for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
@@ -624,13 +694,16 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_persistent_kernel(Pc
                     const float4 As = stencil_quad(code0, c0, left, right, ym, yp, cm, cp);
                     acc += (c0.x * As.x + c0.y * As.y) + (c0.z * As.z + c0.w * As.w);
                     st4(s_out + i, c0);
+                    if (sharded && k == PCG_TZ - 1 && c.tz == tz_last) st4(s_out + i + g.sz, cp);
                     code0 = codep;
                 }
                 cm = c0;
                 c0 = cp;
             }
         }
-        alpha = guarded_div(sigma, (float)grid_sum(grid, psumA, acc, sh, &shd)); // RESULTMODE_ALPHA, pressure_reduce.comp:73-75
+        tot = grid_sum(grid, psumA, acc, sh, &shd);
+        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+        alpha = guarded_div(sigma, (float)tot); // RESULTMODE_ALPHA, pressure_reduce.comp:73-75
 
         // ---- phase B: p += alpha s', r -= alpha A s' (pressure_update_pressure_and_residual.comp), z.r, max|r|
         const bool with_err = (a.max_iterations == it) || (it > 0 && it % a.check_frequency == 0); // pressure_solver.rs:676-677
@@ -658,6 +731,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_persistent_kernel(Pc
                     r4.w -= alpha * (code.w ? As.w : 0.0f);
                     st4(a.p + i, p4);
                     st4(a.r + i, r4);
+                    if (sharded) {
+                        if (k == 0 && c.tz == tz_first && peer_r_lo) st4(peer_r_lo + i + push, r4);
+                        if (k == PCG_TZ - 1 && c.tz == tz_last && peer_r_hi) st4(peer_r_hi + i - push, r4);
+                    }
                     acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
                            (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
                     err = fmaxf(fmaxf(err, fmaxf(fabsf(r4.x), fabsf(r4.y))), fmaxf(fabsf(r4.z), fabsf(r4.w)));
@@ -666,20 +743,24 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_persistent_kernel(Pc
                 s0 = sp;
             }
         }
-        if (with_err) {
+        {
             const float bm = block_max(err, sh);
             if (linear_tid() == 0) pmax[blockIdx.x] = bm;
         }
-        const float zr = (float)grid_sum(grid, psumB, acc, sh, &shd); // the barrier inside also publishes pmax
-        if (with_err) {
+        tot = grid_sum(grid, psumB, acc, sh, &shd); // the barrier inside also publishes pmax
+        {
             const float e = final_max(pmax, gridDim.x, sh);
             if (linear_tid() == 0) shf = e;
             __syncthreads();
-            const float eall = shf;
+            gmax = shf;
             __syncthreads();
+        }
+        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+        const float zr = (float)tot;
+        if (with_err) {
             const float tol = a.params->tolerance[a.which];
-            if (a.max_iterations == it || eall < tol) { // pressure_reduce.comp:82-94: statistics + stop everything
-                max_error = eall;
+            if (a.max_iterations == it || gmax < tol) { // pressure_reduce.comp:82-94: statistics + stop everything
+                max_error = gmax;
                 num_iterations = it;
                 break;
             }
@@ -687,24 +768,43 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_persistent_kernel(Pc
         beta = guarded_div(zr, sigma); // RESULTMODE_BETA, pressure_reduce.comp:77-80
         sigma = zr;
     }
+    if (sharded) {
+        // hand the boundary planes of the solution to the neighbours (warm start of their next init, pressure gradient
+        // across the slab face), then one more round so that nobody leaves before its ghost planes are complete
+        float *const peer_p_lo = cm_.peer_p[a.which][0], *const peer_p_hi = cm_.peer_p[a.which][1];
+        for (int li = blockIdx.x; li < nact; li += gridDim.x) {
+            const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
+            if (!c.valid) continue;
+            if (c.tz == tz_first && peer_p_lo) st4(peer_p_lo + c.i + push, ld4(a.p + c.i));
+            if (c.tz == tz_last && peer_p_hi) {
+                const int i = c.i + (PCG_TZ - 1) * g.sz;
+                st4(peer_p_hi + i - push, ld4(a.p + i));
+            }
+        }
+        grid.sync();
+        double dummy = 0.0;
+        float dmax = 0.0f;
+        comm_allreduce(cm_, ++seq, dummy, dmax, sh_csum, sh_cmax, &sh_dead);
+        if (blockIdx.x == 0 && linear_tid() == 0) *cm_.seq = seq;
+    }
     if (blockIdx.x == 0 && linear_tid() == 0) {
         a.scal->alpha = alpha;
         a.scal->beta = beta;
         a.scal->sigma = sigma;
         a.scal->max_error = max_error;
         a.scal->num_iterations = num_iterations;
-        a.scal->done = 1;
+        a.scal->done = sh_dead ? -1 : 1;
     }
 }
 
 // deterministic compaction of the active tiles (ascending tile id) by one block
-__global__ void __launch_bounds__(1024) pcg_compact_tiles_kernel(const uint8_t *__restrict__ tile_active, int ntiles, int *__restrict__ tile_list,
-                                                                 int *__restrict__ num_active) {
+__global__ void __launch_bounds__(1024) pcg_compact_tiles_kernel(const uint8_t *__restrict__ tile_active, int tile_lo, int ntiles,
+                                                                 int *__restrict__ tile_list, int *__restrict__ num_active) {
     __shared__ int sh[1024];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < ntiles; base += 1024) {
+    for (int base = tile_lo; base < ntiles; base += 1024) { // [tile_lo, ntiles): the owned tiles of a slab, else all
         const int idx = base + threadIdx.x;
         const int v = idx < ntiles && tile_active[idx] ? 1 : 0;
         sh[threadIdx.x] = v;
@@ -732,8 +832,9 @@ __global__ void pcg_reset_scalars_kernel(PcgScalars *scal) {
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
-PressureField::PressureField(const GridDim &grid, const SolverConfig &cfg) : config(cfg) {
-    pressure_.alloc(grid);
+PressureField::PressureField(const GridDim &grid, const SolverConfig &cfg, void *external_volume) : config(cfg) {
+    if (external_volume) pressure_.place(grid, external_volume);
+    else pressure_.alloc(grid);
     BLUB_CUDA_CHECK(cudaMalloc(&scalars, sizeof(PcgScalars)));
     BLUB_CUDA_CHECK(cudaMemset(scalars, 0, sizeof(PcgScalars)));
     BLUB_CUDA_CHECK(cudaMallocHost(&pinned_, sizeof(float) * 2 * NUM_PRESSURE_ERROR_BUFFER));
@@ -797,8 +898,9 @@ void PressureField::read_last_solve(cudaStream_t stream, float *max_error, int *
     *iterations = h.num_iterations;
 }
 
-PressureSolver::PressureSolver(const GridDim &grid) : grid_(grid) {
-    residual_.alloc(grid);
+PressureSolver::PressureSolver(const GridDim &grid, void *external_residual) : grid_(grid) {
+    if (external_residual) residual_.place(grid, external_residual);
+    else residual_.alloc(grid);
     search_.alloc(grid);
     aux_.alloc(grid);
     aux_temp_.alloc(grid);
@@ -850,14 +952,18 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
         BLUB_CUDA_CHECK(cudaMemsetAsync(aux_.ptr, 0, (size_t)g.n * sizeof(float), stream));
         BLUB_CUDA_CHECK(cudaMemsetAsync(aux_temp_.ptr, 0, (size_t)g.n * sizeof(float), stream));
     }
+    if (comm.world > 1 && !(mode == 0 && persistent_blocks_ > 0 && use_persistent))
+        throw std::invalid_argument("the z-slab sharded solve needs the persistent solver with precond_mode 0");
     if (mode == 0 && persistent_blocks_ > 0 && use_persistent) {
         // one cooperative launch for the whole solve; s ping-pongs between search_ and aux_ (both zero off the active tiles)
         BLUB_CUDA_CHECK(cudaMemsetAsync(aux_.ptr, 0, (size_t)g.n * sizeof(float), stream));
-        BLUB_LAUNCH(pcg_compact_tiles_kernel, 1, 1024, 0, stream, tile_active_, t.ntiles, tile_list_, num_active_);
+        const int ghost_tiles = (comm.halo / PCG_TZ) * t.tiles_x * t.tiles_y; // ghost planes are whole tiles (SLAB_HALO == PCG_TZ)
+        BLUB_LAUNCH(pcg_compact_tiles_kernel, 1, 1024, 0, stream, tile_active_, ghost_tiles, t.ntiles - ghost_tiles, tile_list_, num_active_);
         PcgSolveArgs args;
         args.g = g; args.t = t; args.codes = st; args.tile_list = tile_list_; args.num_active = num_active_;
         args.p = p; args.r = r; args.s0 = s; args.s1 = aux_.ptr; args.scal = scal; args.partials = partials_;
         args.params = dparams; args.which = which; args.max_iterations = max_it; args.check_frequency = freq;
+        args.comm = comm;
         int nblocks = persistent_blocks_ < t.ntiles ? persistent_blocks_ : t.ntiles;
         void *kargs[] = {&args};
         BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_persistent_kernel, dim3(nblocks), t.block(), kargs, 0, stream));

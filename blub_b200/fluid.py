@@ -72,6 +72,13 @@ def lib():
     sig = {
         "blub_fluid_create": (C.c_int, [C.POINTER(vp), u32, u32, u32, u32, C.c_int, vp]),
         "blub_fluid_destroy": (None, [vp]),
+        "blub_fluid_create_slab": (C.c_int, [C.POINTER(vp), u32, u32, u32, u32, C.c_int, vp, C.c_int, C.c_int]),
+        "blub_fluid_slab_window": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "blub_fluid_attach_slab_peers": (C.c_int, [vp, C.POINTER(vp), C.c_int]),
+        "blub_ipc_export": (C.c_int, [vp, C.c_char_p]),
+        "blub_ipc_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
+        "blub_ipc_close": (C.c_int, [vp]),
+        "blub_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
         "blub_fluid_add_cube": (C.c_int, [vp, f3, f3]),
         "blub_fluid_set_gravity_grid": (C.c_int, [vp, f3]),
         "blub_fluid_num_particles": (u32, [vp]),
@@ -120,6 +127,16 @@ def _f3(v):
     return (C.c_float * 3)(*[float(x) for x in v])
 
 
+def ipc_open(handle: bytes, device: int) -> int:
+    out = C.c_void_p()
+    _check(lib().blub_ipc_open(handle, device, C.byref(out)))
+    return int(out.value)
+
+
+def enable_peer_access(device: int, peer: int):
+    _check(lib().blub_enable_peer_access(device, peer))
+
+
 def kernel_launch_count(reset=False) -> int:
     return int(lib().blub_kernel_launch_count(1 if reset else 0))
 
@@ -147,6 +164,28 @@ class HybridFluid:
         self.L.blub_fluid_grid_dimension(self.h, d)
         self.nx, self.ny, self.nz = int(d[0]), int(d[1]), int(d[2])
         self.n = self.nx * self.ny * self.nz
+
+    @classmethod
+    def create_slab(cls, nx, ny, nz_owned, max_num_particles, rank, world, device=0, cuda_stream=None):
+        """Rank `rank` of a z-slab decomposition (4 ghost planes on both sides of the nz_owned owned planes)."""
+        L = lib()
+        h = C.c_void_p()
+        _check(L.blub_fluid_create_slab(C.byref(h), nx, ny, nz_owned, max_num_particles, device, cuda_stream, rank, world))
+        return cls(0, 0, 0, 0, _handle=h)
+
+    def slab_window(self):
+        w, n = C.c_void_p(), C.c_size_t()
+        _check(self.L.blub_fluid_slab_window(self.h, C.byref(w), C.byref(n)))
+        return int(w.value), int(n.value)
+
+    def attach_slab_peers(self, windows):
+        arr = (C.c_void_p * len(windows))(*windows)
+        _check(self.L.blub_fluid_attach_slab_peers(self.h, arr, len(windows)))
+
+    def ipc_export_window(self):
+        buf = C.create_string_buffer(64)
+        _check(self.L.blub_ipc_export(self.slab_window()[0], buf))
+        return bytes(buf.raw)
 
     @classmethod
     def from_scene(cls, path, device=0, cuda_stream=None):

@@ -143,6 +143,24 @@ typedef struct {
 } BlubSceneInfo;
 int blub_scene_info(const char *scene_json_path, BlubSceneInfo *out);
 
+/* ---- multi-GPU: z-slab sharding of the pressure solve (the reference is single-GPU) ---------------
+ * Rank `rank` of `world` (<= 8) owns nz_owned planes of a global nx x ny x (world * nz_owned) grid; its local grid has 4
+ * ghost planes on both sides (local plane 4 = first owned plane).  Each rank exposes ONE device allocation (the "window":
+ * mailbox + residual + both pressure volumes).  After every rank's window has been mapped into every process
+ * (blub_ipc_export / blub_ipc_open across processes, or plain pointers + blub_enable_peer_access inside one process),
+ * blub_fluid_attach_slab_peers switches the solver to the sharded mode: the persistent PCG kernel then pushes its
+ * boundary planes of r and p into the neighbours' ghost planes with P2P stores over NVLink and all-reduces its scalars
+ * through the peers' mailboxes -- no host involvement, no NCCL call inside the solve.  All ranks must enqueue the same
+ * solves in the same order. */
+int blub_fluid_create_slab(BlubFluid **out, uint32_t nx, uint32_t ny, uint32_t nz_owned, uint32_t max_num_particles, int device,
+                           void *cuda_stream, int rank, int world);
+int blub_fluid_slab_window(BlubFluid *fluid, void **window, size_t *bytes);
+int blub_fluid_attach_slab_peers(BlubFluid *fluid, void *const *windows, int world);
+int blub_ipc_export(const void *device_ptr, unsigned char handle[64]);
+int blub_ipc_open(const unsigned char handle[64], int device, void **out);
+int blub_ipc_close(void *mapped);
+int blub_enable_peer_access(int device, int peer);
+
 /* ---- test / bench taps (not part of the reference surface) ---------------------------------------------------- */
 enum {
     BLUB_TAP_PARTICLE_POS = 0, BLUB_TAP_PARTICLE_VX = 1, BLUB_TAP_PARTICLE_VY = 2, BLUB_TAP_PARTICLE_VZ = 3,
