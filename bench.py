@@ -121,8 +121,9 @@ def pcg_sharded(rank, world, local, n=512, reps=5):
 
     nz_owned = n // world
     f = blub_b200.HybridFluid.create_slab(n, n, nz_owned, 8, rank=rank, world=world, device=local)
-    handles = [None] * world
-    dist.all_gather_object(handles, f.ipc_export_window())
+    from blub_b200 import slab
+
+    handles = slab.exchange_handles(f.ipc_export_window(), dist)
     own = f.slab_window()[0]
     windows = [own if k == rank else F.ipc_open(handles[k], local) for k in range(world)]
     f.attach_slab_peers(windows)

@@ -46,6 +46,14 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
+        # OpenMP: never more threads than CPUs this process may run on, and sleep (not spin) at barriers -- the oracle's
+        # loops are short, and a spinning 128-thread team on a CPU-limited box is slower than one thread
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, min(ncpu, 64))))
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
         build()
         L = C.CDLL(_LIB_PATH)
         L.orc_create.restype = C.c_void_p

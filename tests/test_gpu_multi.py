@@ -5,11 +5,12 @@ import pytest
 
 import blub_b200
 from blub_b200 import fluid as F
+from blub_b200 import slab
 from oracle import oracle as O
 from tests.util import DT, grid_close
 
 pytestmark = pytest.mark.gpu
-HALO = 4
+HALO = slab.HALO
 
 
 def _gpu_count():
@@ -30,13 +31,7 @@ def make_slabs(world, nx, ny, nz_owned):
 
 
 def local_view(glob, k, nz_owned, fill=0):
-    """global [NZ, ny, nx] volume -> rank k's local volume with ghost planes (outside the domain: `fill`)."""
-    nz = glob.shape[0]
-    out = np.full((nz_owned + 2 * HALO,) + glob.shape[1:], fill, dtype=glob.dtype)
-    lo, hi = k * nz_owned - HALO, (k + 1) * nz_owned + HALO
-    a, b = max(lo, 0), min(hi, nz)
-    out[a - lo:b - lo] = glob[a:b]
-    return out
+    return slab.local_view(glob, k, glob.shape[0] // nz_owned, fill)
 
 
 @pytest.mark.parametrize("world", [2, 4])
