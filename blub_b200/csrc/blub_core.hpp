@@ -142,8 +142,8 @@ class HybridFluid {
     // returns true when the cube was truncated to max_num_particles (hybrid_fluid.rs:627-633)
     bool add_fluid_cube(const float min_grid[3], const float max_grid[3]);
     void set_gravity_grid(const float g[3]) { gravity_[0] = g[0]; gravity_[1] = g[1]; gravity_[2] = g[2]; }
-    uint32_t num_particles() const { return num_particles_; }
-    uint32_t num_active_particles() const { return num_particles_; }
+    uint32_t num_particles() const;
+    uint32_t num_active_particles() const { return num_particles(); }
     const GridDim &grid_dimension() const { return grid_; }
     SolverConfig &pressure_solver_config_velocity() { return field_velocity_->config; }
     SolverConfig &pressure_solver_config_density() { return field_density_->config; }
@@ -165,6 +165,9 @@ class HybridFluid {
     void attach_slab_peers(void *const *windows, int world);
     int slab_rank() const { return slab_rank_; }
     int slab_world() const { return slab_world_; }
+    bool sharded() const { return slab_world_ > 1; }
+    // 0 = fine; 1 = a peer timed out in a barrier; 2 = particle capacity exceeded; 3 = migration buffer overflow (synchronises)
+    int slab_error();
     void invalidate_graphs() { destroy_graphs(); }
 
     Quirks quirks;
@@ -185,6 +188,27 @@ class HybridFluid {
     void upload_step_params(float dt);
     void run_stage(int stage, float dt);
     void destroy_graphs();
+
+    // ---- z-slab sharding of the whole step (slab.cu) ----
+    struct SlabHaloItem {
+        void *cell0;           // cell-0 pointer of a grid volume
+        size_t bytes_per_cell;
+        int kind;              // 0 SUM (float data) / 1 MAX (int8) over the 4 overlap planes, 2 COPY of 2 owned planes into the ghost planes
+    };
+    size_t slab_extra_window_bytes() const;
+    uint32_t slab_migrant_capacity() const;
+    void slab_layout(void *window, char *&halo0, size_t &halo_bytes, char *&part0, size_t &part_bytes, unsigned int *&counts) const;
+    void slab_barrier();
+    void slab_halo_exchange(const SlabHaloItem *items, int n_items);
+    void slab_migrate();
+    void set_device_particle_count(uint32_t n);
+    bool add_fluid_cube_slab(const uint32_t mn[3], const uint32_t ext[3]);
+    uint32_t seeded_global_ = 0;
+    float4 *row_alt_[3] = {nullptr, nullptr, nullptr}; // spare velocity rows: migration compacts out of place
+    unsigned int *mig_counters_ = nullptr;
+    int *slab_error_ = nullptr;
+    void *slab_peer_window_[2] = {nullptr, nullptr};
+    uint32_t slab_exchange_index_ = 0;
 
     // Cached executable graphs of one step, keyed by (position buffer in use, binning step?).  Everything a graph bakes
     // in besides that key is in `GraphSignature`; a change drops the cache.

@@ -108,6 +108,13 @@ int blub_fluid_attach_slab_peers(BlubFluid *fluid, void *const *windows, int wor
     return guarded([&] { fluid->impl->attach_slab_peers(windows, world); return BLUB_OK; });
 }
 
+int blub_fluid_slab_error(BlubFluid *fluid) {
+    if (!fluid) return -1;
+    int e = -1;
+    guarded([&] { e = fluid->impl->slab_error(); return BLUB_OK; });
+    return e;
+}
+
 int blub_ipc_export(const void *device_ptr, unsigned char handle[64]) {
     if (!device_ptr || !handle) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
     return guarded([&] {

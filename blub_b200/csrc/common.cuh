@@ -49,6 +49,10 @@ struct GridDim {
     int sz;      // stride of +1 in z (= nx * ny)
     int64_t n;   // cells
     int64_t pad; // slack elements before/after each array
+    // z walls: cells with z <= z_wall_lo or z >= z_wall_hi are SOLID and particles are kept in
+    // [z_wall_lo + 1.001, z_wall_hi - 0.001].  Single GPU: 0 and nz-1 (transfer_set_boundary_marker.comp:14-16,
+    // advect_particles.comp:137); interior ranks of a z-slab decomposition have no z wall (+-2^20).
+    int z_wall_lo, z_wall_hi;
 };
 
 inline GridDim make_grid(int nx, int ny, int nz) {
@@ -57,6 +61,8 @@ inline GridDim make_grid(int nx, int ny, int nz) {
     g.sy = nx; g.sz = nx * ny;
     g.n = (int64_t)nx * ny * nz;
     g.pad = (((int64_t)nx * ny + 8) + 255) / 256 * 256;
+    g.z_wall_lo = 0;
+    g.z_wall_hi = nz - 1;
     return g;
 }
 

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(PT) boundary_marker_kernel(GridDim g, int8_t *
     int x, y, z;
     cell_of(g, i, x, y, z);
     int m = marker[i];
-    if (x == 0 || y == 0 || z == 0 || x == g.nx - 1 || y == g.ny - 1 || z == g.nz - 1) {
+    if (x == 0 || y == 0 || z <= g.z_wall_lo || x == g.nx - 1 || y == g.ny - 1 || z >= g.z_wall_hi) {
         m = CELL_SOLID;
         marker[i] = (int8_t)m;
     } else if (vox != nullptr) {
@@ -400,10 +400,11 @@ __global__ void __launch_bounds__(PT) advect_kernel(GridDim g, const StepParams 
         mv[k] = dt * (1.0f / 6.0f) * (nv[k] + 2.0f * (k2[k] + k3[k]) + k4[k]);
         x1[k] = x0[k] + mv[k];
     }
-    const float hi[3] = {(float)g.nx - 1.001f, (float)g.ny - 1.001f, (float)g.nz - 1.001f};
+    const float lo[3] = {1.001f, 1.001f, (float)g.z_wall_lo + 1.001f};
+    const float hi[3] = {(float)g.nx - 1.001f, (float)g.ny - 1.001f, (float)(g.z_wall_hi + 1) - 1.001f};
     bool hit = false;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) hit = hit || (fminf(fmaxf(x1[k], 1.001f), hi[k]) != x1[k]);
+    for (int k = 0; k < 3; ++k) hit = hit || (fminf(fmaxf(x1[k], lo[k]), hi[k]) != x1[k]);
     if (!hit && vox != nullptr) hit = voxel_point_clamp(g, vox, x1[0], x1[1], x1[2]).w > 0.0f;
     if (hit) { // :134-173
         const float len = sqrtf(mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]) + 1e-10f;
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(PT) advect_kernel(GridDim g, const StepParams 
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            x1[k] = fminf(fmaxf(x0[k] + mv[k], 1.001f), hi[k]);
+            x1[k] = fminf(fmaxf(x0[k] + mv[k], lo[k]), hi[k]);
             nv[k] = (dir[k] * maxstep) / dt;
         }
     }
@@ -501,10 +502,11 @@ __global__ void __launch_bounds__(PT) correct_particles_kernel(GridDim g, const 
     ch[1] = grid_trilinear_clamp(g, uy, fmaxf(0.0f, x0[0]), fmaxf(0.0f, x0[1] - 0.5f), fmaxf(0.0f, x0[2]));
     ch[2] = grid_trilinear_clamp(g, uz, fmaxf(0.0f, x0[0]), fmaxf(0.0f, x0[1]), fmaxf(0.0f, x0[2] - 0.5f));
     float x1[3] = {x0[0] + ch[0], x0[1] + ch[1], x0[2] + ch[2]};
-    const float hi[3] = {(float)g.nx - 1.001f, (float)g.ny - 1.001f, (float)g.nz - 1.001f};
+    const float lo[3] = {1.001f, 1.001f, (float)g.z_wall_lo + 1.001f};
+    const float hi[3] = {(float)g.nx - 1.001f, (float)g.ny - 1.001f, (float)(g.z_wall_hi + 1) - 1.001f};
     bool hit = false;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) hit = hit || (fminf(fmaxf(x1[k], 1.001f), hi[k]) != x1[k]);
+    for (int k = 0; k < 3; ++k) hit = hit || (fminf(fmaxf(x1[k], lo[k]), hi[k]) != x1[k]);
     if (!hit) {
         const int x = clampi((int)floorf(x1[0]), 0, g.nx - 1), y = clampi((int)floorf(x1[1]), 0, g.ny - 1), z = clampi((int)floorf(x1[2]), 0, g.nz - 1);
         hit = marker[lin(g, x, y, z)] == CELL_SOLID;
@@ -519,7 +521,7 @@ __global__ void __launch_bounds__(PT) correct_particles_kernel(GridDim g, const 
             maxstep = fminf(maxstep, (dir[k] > 0.0f ? pc : 1.0f - pc) / fabsf(dir[k]) - 0.001f);
         }
 #pragma unroll
-        for (int k = 0; k < 3; ++k) x1[k] = fminf(fmaxf(x0[k] + dir[k] * maxstep, 1.001f), hi[k]);
+        for (int k = 0; k < 3; ++k) x1[k] = fminf(fmaxf(x0[k] + dir[k] * maxstep, lo[k]), hi[k]);
     }
     pos[i] = make_float4(x1[0], x1[1], x1[2], p4.w);
 }
@@ -629,15 +631,25 @@ static void run_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marke
     BLUB_LAUNCH(boundary_marker_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, vox, flags.seg_fluid, flags.row_fluid, 1 << flags.seg_shift);
 }
 
-void launch_p2g(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float4 *const row[3],
-                float *const u[3], float2 *const nw[3], int8_t *marker, const uint2 *vox, const MarkerFlags &flags) {
+void launch_p2g_scatter(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float4 *const row[3],
+                        float2 *const nw[3], int8_t *marker) {
     // transfer_clear.comp: marker <- AIR; the (num, weight) volumes replace the linked-list head volume
     BLUB_CUDA_CHECK(cudaMemsetAsync(marker, 0xFF, (size_t)g.n, st));
     for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(nw[c], 0, (size_t)g.n * sizeof(float2), st));
     if (np_upper > 0)
         BLUB_LAUNCH(p2g_scatter_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
+}
+
+void launch_p2g_finish(cudaStream_t st, const GridDim &g, const StepParams *params, float *const u[3], float2 *const nw[3], int8_t *marker,
+                       const uint2 *vox, const MarkerFlags &flags) {
     run_boundary_marker(st, g, marker, vox, flags);
     BLUB_LAUNCH(p2g_normalize_kernel, blocks_for(g.n, PT), PT, 0, st, g, params, marker, u[0], u[1], u[2], nw[0], nw[1], nw[2]);
+}
+
+void launch_p2g(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float4 *const row[3],
+                float *const u[3], float2 *const nw[3], int8_t *marker, const uint2 *vox, const MarkerFlags &flags) {
+    launch_p2g_scatter(st, g, params, np_upper, pos, row, nw, marker);
+    launch_p2g_finish(st, g, params, u, nw, marker, vox, flags);
 }
 
 void launch_divergence_compute(cudaStream_t st, const GridDim &g, const int8_t *marker, float *const u[3], const uint2 *vox, float *rhs) {
@@ -666,11 +678,19 @@ void launch_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, c
     run_boundary_marker(st, g, marker, vox, flags);
 }
 
-void launch_density_rhs(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos,
-                        const int8_t *marker, float *density, float *rhs) {
+void launch_density_scatter(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float *density) {
     BLUB_CUDA_CHECK(cudaMemsetAsync(density, 0, (size_t)g.n * sizeof(float), st));
     if (np_upper > 0) BLUB_LAUNCH(density_scatter_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, density);
+}
+
+void launch_density_finish(cudaStream_t st, const GridDim &g, const StepParams *params, const int8_t *marker, const float *density, float *rhs) {
     BLUB_LAUNCH(density_rhs_kernel, blocks_for(g.n, PT), PT, 0, st, g, params, marker, density, rhs);
+}
+
+void launch_density_rhs(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos,
+                        const int8_t *marker, float *density, float *rhs) {
+    launch_density_scatter(st, g, params, np_upper, pos, density);
+    launch_density_finish(st, g, params, marker, density, rhs);
 }
 
 void launch_position_change(cudaStream_t st, const GridDim &g, const StepParams *params, const int8_t *marker, const float *p, float *const u[3]) {

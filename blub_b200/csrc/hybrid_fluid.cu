@@ -1,6 +1,7 @@
 // hybrid_fluid.cu -- host side of the fluid: allocation, particle seeding and the recording of one step.
 // Counterpart of src/simulation/hybrid_fluid.rs (HybridFluid::{new, add_fluid_cube, step, ...}).
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 
@@ -31,6 +32,10 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
         owns_stream_ = true;
     }
     grid_ = make_grid((int)nx, (int)ny, (int)nz);
+    if (slab_world_ > 1) { // only the first / last rank has a z wall; local plane SLAB_HALO is global plane rank * owned_nz
+        grid_.z_wall_lo = slab_rank_ == 0 ? SLAB_HALO : -(1 << 20);
+        grid_.z_wall_hi = slab_rank_ == slab_world_ - 1 ? SLAB_HALO + (int)owned_nz - 1 : (1 << 20);
+    }
     const size_t pbytes = ((size_t)max_num_particles + 64) * sizeof(float4);
     for (int k = 0; k < 2; ++k) {
         BLUB_CUDA_CHECK(cudaMalloc(&pos_[k], pbytes));
@@ -56,7 +61,7 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
         // peer-visible window: [mailbox 4 KiB | residual | pressure (velocity) | pressure (density)], one cudaMalloc so that
         // a single IPC handle (or peer pointer) exposes everything a neighbour writes into
         const size_t vol = GridArray<float>::bytes_for(grid_);
-        window_bytes_ = 4096 + 3 * vol;
+        window_bytes_ = 4096 + 3 * vol + slab_extra_window_bytes();
         BLUB_CUDA_CHECK(cudaMalloc(&window_, window_bytes_));
         BLUB_CUDA_CHECK(cudaMemset(window_, 0, window_bytes_));
         char *w = static_cast<char *>(window_);
@@ -70,6 +75,15 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
         c.owned_nz = (int)owned_nz;
         BLUB_CUDA_CHECK(cudaMalloc(&c.seq, sizeof(unsigned int)));
         BLUB_CUDA_CHECK(cudaMemset(c.seq, 0, sizeof(unsigned int)));
+        for (int k = 0; k < 3; ++k) {
+            BLUB_CUDA_CHECK(cudaMalloc(&row_alt_[k], pbytes));
+            BLUB_CUDA_CHECK(cudaMemset(row_alt_[k], 0, pbytes));
+        }
+        BLUB_CUDA_CHECK(cudaMalloc(&mig_counters_, 4 * sizeof(unsigned int)));
+        BLUB_CUDA_CHECK(cudaMemset(mig_counters_, 0, 4 * sizeof(unsigned int)));
+        BLUB_CUDA_CHECK(cudaMalloc(&slab_error_, sizeof(int)));
+        BLUB_CUDA_CHECK(cudaMemset(slab_error_, 0, sizeof(int)));
+        use_graph = false; // the sharded step interleaves exchanges with the stages and is launched eagerly
     } else {
         solver_.reset(new PressureSolver(grid_));
         field_velocity_.reset(new PressureField(grid_, cfg));
@@ -112,6 +126,9 @@ HybridFluid::~HybridFluid() {
     field_velocity_.reset();
     field_density_.reset();
     if (window_) cudaFree(window_);
+    for (int k = 0; k < 3; ++k) cudaFree(row_alt_[k]);
+    cudaFree(mig_counters_);
+    cudaFree(slab_error_);
     cudaFree(params_dev_);
     cudaFreeHost(params_host_);
     for (int k = 0; k < 64; ++k) cudaEventDestroy(param_events_[k]);
@@ -156,7 +173,9 @@ uint32_t clamp_to_grid(uint32_t dim, float v) { // hybrid_fluid.rs:609-617; Rust
 
 bool HybridFluid::add_fluid_cube(const float min_grid[3], const float max_grid[3]) {
     BLUB_CUDA_CHECK(cudaSetDevice(device_));
-    const uint32_t dim[3] = {(uint32_t)grid_.nx, (uint32_t)grid_.ny, (uint32_t)grid_.nz};
+    // a slab rank takes GLOBAL grid coordinates: the cube is clamped against the global grid and every rank keeps its part
+    const uint32_t dim[3] = {(uint32_t)grid_.nx, (uint32_t)grid_.ny,
+                             slab_world_ > 1 ? (uint32_t)(solver_->comm.owned_nz * slab_world_) : (uint32_t)grid_.nz};
     uint32_t mn[3], ext[3];
     for (int k = 0; k < 3; ++k) {
         mn[k] = clamp_to_grid(dim[k], min_grid[k]);
@@ -168,6 +187,7 @@ bool HybridFluid::add_fluid_cube(const float min_grid[3], const float max_grid[3
         num_new = max_num_particles_ - num_particles_;
         truncated = true;
     }
+    if (slab_world_ > 1) return add_fluid_cube_slab(mn, ext);
     if (num_new == 0) return truncated;
     Xoshiro256pp rng((uint64_t)(num_particles_ + num_new)); // :637
     std::vector<float4> fresh(num_new);
@@ -188,6 +208,69 @@ bool HybridFluid::add_fluid_cube(const float min_grid[3], const float max_grid[3
     return truncated;
 }
 
+// Slab rank: the same particle stream as the single-GPU seeding (same RNG draws in the same order -- the seed is the GLOBAL
+// particle count, hybrid_fluid.rs:637), of which this rank keeps the particles whose cell lies in its planes, re-based to
+// local z.  `seeded_global_` mirrors the reference's running num_particles for the seed of the next cube.
+bool HybridFluid::add_fluid_cube_slab(const uint32_t mn[3], const uint32_t ext[3]) {
+    const uint32_t num_new = ext[0] * ext[1] * ext[2] * PARTICLES_PER_GRID_CELL;
+    if (num_new == 0) return false;
+    const int zs = solver_->comm.owned_nz;
+    const uint32_t z0 = (uint32_t)(slab_rank_ * zs), z1 = z0 + (uint32_t)zs;
+    Xoshiro256pp rng((uint64_t)(seeded_global_ + num_new));
+    std::vector<float4> fresh;
+    fresh.reserve((size_t)num_new / slab_world_ + 1024);
+    for (uint32_t i = 0; i < num_new; ++i) {
+        const uint32_t cz = mn[2] + i / 8u / ext[0] / ext[1];
+        const float cell[3] = {(float)(mn[0] + i / 8u % ext[0]), (float)(mn[1] + i / 8u / ext[0] % ext[1]), (float)cz};
+        const uint32_t s = i % 8u;
+        const float strat[3] = {(float)(s % 2u), (float)(s / 2u % 2u), (float)(s / 4u % 2u)};
+        float p[3];
+        for (int k = 0; k < 3; ++k) {
+            const float r = rng.next_f32();
+            p[k] = cell[k] + (strat[k] * 0.5f + r * 0.5f);
+        }
+        if (cz >= z0 && cz < z1) fresh.push_back(make_float4(p[0], p[1], p[2] - (float)z0 + (float)SLAB_HALO, 0.0f));
+    }
+    seeded_global_ += num_new;
+    bool truncated = false;
+    size_t keep = fresh.size();
+    if (num_particles_ + keep > max_num_particles_) {
+        keep = max_num_particles_ - num_particles_;
+        truncated = true;
+    }
+    if (keep) {
+        BLUB_CUDA_CHECK(cudaMemcpyAsync(pos_[cur_] + num_particles_, fresh.data(), keep * sizeof(float4), cudaMemcpyHostToDevice, stream_));
+        BLUB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+    num_particles_ += (uint32_t)keep;
+    set_device_particle_count(num_particles_);
+    return truncated;
+}
+
+void HybridFluid::set_device_particle_count(uint32_t n) {
+    BLUB_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(params_dev_) + offsetof(StepParams, num_particles), &n, sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice, stream_));
+    BLUB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+uint32_t HybridFluid::num_particles() const {
+    if (slab_world_ <= 1) return num_particles_;
+    uint32_t n = 0; // authoritative count lives on the device (migration)
+    cudaSetDevice(device_);
+    cudaMemcpyAsync(&n, reinterpret_cast<const char *>(params_dev_) + offsetof(StepParams, num_particles), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_);
+    cudaStreamSynchronize(stream_);
+    return n;
+}
+
+int HybridFluid::slab_error() {
+    if (!slab_error_) return 0;
+    int e = 0;
+    BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    BLUB_CUDA_CHECK(cudaMemcpyAsync(&e, slab_error_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    BLUB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return e;
+}
+
 void HybridFluid::set_particles(uint32_t count, const float *pos4, const float *vx4, const float *vy4, const float *vz4) {
     BLUB_CUDA_CHECK(cudaSetDevice(device_));
     if (count > max_num_particles_) throw std::invalid_argument("count exceeds max_num_particles");
@@ -200,6 +283,7 @@ void HybridFluid::set_particles(uint32_t count, const float *pos4, const float *
     }
     BLUB_CUDA_CHECK(cudaStreamSynchronize(stream_));
     num_particles_ = count;
+    if (slab_world_ > 1) set_device_particle_count(count);
 }
 
 // windows[k] = rank k's slab window as mapped in THIS process (cudaIpcOpenMemHandle, or a plain peer pointer when all
@@ -221,6 +305,7 @@ void HybridFluid::attach_slab_peers(void *const *windows, int world) {
         c.peer_r[side] = has ? cell0(windows[nb], 0) : nullptr;
         c.peer_p[0][side] = has ? cell0(windows[nb], 1) : nullptr;
         c.peer_p[1][side] = has ? cell0(windows[nb], 2) : nullptr;
+        slab_peer_window_[side] = has ? windows[nb] : nullptr;
     }
     c.world = world;
 }
@@ -251,7 +336,9 @@ void HybridFluid::upload_step_params(float dt) {
     h->tolerance[0] = field_velocity_->config.error_tolerance / dt; // pressure_solver.rs:193-201
     h->tolerance[1] = field_density_->config.error_tolerance / dt;
     h->num_particles = num_particles_;
-    BLUB_CUDA_CHECK(cudaMemcpyAsync(params_dev_, h, sizeof(StepParams), cudaMemcpyHostToDevice, stream_));
+    // sharded: the particle count changes on the device (migration) and is the last field: leave it alone
+    const size_t bytes = slab_world_ > 1 ? offsetof(StepParams, num_particles) : sizeof(StepParams);
+    BLUB_CUDA_CHECK(cudaMemcpyAsync(params_dev_, h, bytes, cudaMemcpyHostToDevice, stream_));
     BLUB_CUDA_CHECK(cudaEventRecord(param_events_[slot], stream_));
 }
 
@@ -260,10 +347,18 @@ void HybridFluid::run_stage(int stage, float dt) {
     float *u[3] = {u_[0].ptr, u_[1].ptr, u_[2].ptr};
     float2 *nw[3] = {numw_[0].ptr, numw_[1].ptr, numw_[2].ptr};
     const MarkerFlags flags = {seg_fluid_, row_fluid_, seg_shift_};
-    const uint32_t np = num_particles_;
+    const bool shard = slab_world_ > 1 && solver_->comm.world > 1;
+    const uint32_t np = slab_world_ > 1 ? max_num_particles_ : num_particles_; // sharded: the device-side count guards the kernels
     switch (stage) {
     case 0: // transfer particle velocity to grid (:806-833)
-        launch_p2g(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, nw, marker_.ptr, voxels_, flags);
+        if (!shard) {
+            launch_p2g(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, nw, marker_.ptr, voxels_, flags);
+        } else {
+            launch_p2g_scatter(stream_, grid_, params_dev_, np, pos_[cur_], row_, nw, marker_.ptr);
+            const SlabHaloItem items[4] = {{nw[0], sizeof(float2), 0}, {nw[1], sizeof(float2), 0}, {nw[2], sizeof(float2), 0}, {marker_.ptr, 1, 1}};
+            slab_halo_exchange(items, 4); // X1
+            launch_p2g_finish(stream_, grid_, params_dev_, u, nw, marker_.ptr, voxels_, flags);
+        }
         break;
     case 1: // compute divergence -> PCG residual (:835-840)
         launch_divergence_compute(stream_, grid_, marker_.ptr, u, voxels_, solver_->residual());
@@ -283,18 +378,34 @@ void HybridFluid::run_stage(int stage, float dt) {
         break;
     case 5: // extrapolate velocity grid (:906-909)
         launch_extrapolate(stream_, grid_, marker_.ptr, flags, u);
+        if (shard) {
+            const SlabHaloItem items[3] = {{u[0], sizeof(float), 2}, {u[1], sizeof(float), 2}, {u[2], sizeof(float), 2}};
+            slab_halo_exchange(items, 3); // X2
+        }
         break;
     case 6: // clear marker (& linked list) grids (:911-916)
         launch_clear_marker(stream_, grid_, marker_.ptr);
         break;
     case 7: // advect particles (:917-921)
         launch_advect(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, voxels_, marker_.ptr);
+        if (shard) {
+            slab_migrate();
+            const SlabHaloItem items[1] = {{marker_.ptr, 1, 1}};
+            slab_halo_exchange(items, 1); // X3
+        }
         break;
     case 8: // density projection: set boundary marker (:923-927)
         launch_boundary_marker(stream_, grid_, marker_.ptr, voxels_, flags);
         break;
     case 9: // density projection: compute density error (:928-932)
-        launch_density_rhs(stream_, grid_, params_dev_, np, pos_[cur_], marker_.ptr, density_.ptr, solver_->residual());
+        if (!shard) {
+            launch_density_rhs(stream_, grid_, params_dev_, np, pos_[cur_], marker_.ptr, density_.ptr, solver_->residual());
+        } else {
+            launch_density_scatter(stream_, grid_, params_dev_, np, pos_[cur_], density_.ptr);
+            const SlabHaloItem items[1] = {{density_.ptr, sizeof(float), 0}};
+            slab_halo_exchange(items, 1); // X4
+            launch_density_finish(stream_, grid_, params_dev_, marker_.ptr, density_.ptr, solver_->residual());
+        }
         break;
     case 10: // secondary pressure solver (:940-949)
         solver_->solve(stream_, *field_density_, 1, marker_.ptr, params_dev_, quirks);
@@ -305,6 +416,10 @@ void HybridFluid::run_stage(int stage, float dt) {
         break;
     case 12: // extrapolate (:963-966)
         launch_extrapolate(stream_, grid_, marker_.ptr, flags, u);
+        if (shard) {
+            const SlabHaloItem items[3] = {{u[0], sizeof(float), 2}, {u[1], sizeof(float), 2}, {u[2], sizeof(float), 2}};
+            slab_halo_exchange(items, 3); // X5
+        }
         break;
     case 13: // correct particle density error (:968-972)
         launch_correct_particles(stream_, grid_, params_dev_, np, pos_[cur_], marker_.ptr, u);

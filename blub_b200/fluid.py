@@ -75,6 +75,7 @@ def lib():
         "blub_fluid_create_slab": (C.c_int, [C.POINTER(vp), u32, u32, u32, u32, C.c_int, vp, C.c_int, C.c_int]),
         "blub_fluid_slab_window": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "blub_fluid_attach_slab_peers": (C.c_int, [vp, C.POINTER(vp), C.c_int]),
+        "blub_fluid_slab_error": (C.c_int, [vp]),
         "blub_ipc_export": (C.c_int, [vp, C.c_char_p]),
         "blub_ipc_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
         "blub_ipc_close": (C.c_int, [vp]),
@@ -181,6 +182,9 @@ class HybridFluid:
     def attach_slab_peers(self, windows):
         arr = (C.c_void_p * len(windows))(*windows)
         _check(self.L.blub_fluid_attach_slab_peers(self.h, arr, len(windows)))
+
+    def slab_error(self):
+        return int(self.L.blub_fluid_slab_error(self.h))
 
     def ipc_export_window(self):
         buf = C.create_string_buffer(64)

@@ -156,6 +156,12 @@ int blub_fluid_create_slab(BlubFluid **out, uint32_t nx, uint32_t ny, uint32_t n
                            void *cuda_stream, int rank, int world);
 int blub_fluid_slab_window(BlubFluid *fluid, void **window, size_t *bytes);
 int blub_fluid_attach_slab_peers(BlubFluid *fluid, void *const *windows, int world);
+/* Once peers are attached, blub_fluid_step runs the WHOLE step sharded: halo sums of the P2G / density accumulators,
+ * marker and velocity halos, and particle migration across the slab faces travel as stream-ordered peer copies and P2P
+ * stores (blub_b200/csrc/slab.cu).  blub_fluid_add_cube then takes GLOBAL grid coordinates and every rank keeps its part
+ * of the same particle stream; particle taps are in local coordinates (global z = local z - 4 + rank * nz_owned).
+ * Returns 0, or 1 = a peer timed out, 2 = particle capacity exceeded, 3 = migration buffer overflow (synchronises). */
+int blub_fluid_slab_error(BlubFluid *fluid);
 int blub_ipc_export(const void *device_ptr, unsigned char handle[64]);
 int blub_ipc_open(const unsigned char handle[64], int device, void **out);
 int blub_ipc_close(void *mapped);
