@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- steps/sec of the blub fluid step on B200 + PCG roofline + CPU baseline (contract: see DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl blub|reference] [--workload dam_256]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl blub|reference] [--workload dam_256] [--multi sharded|replicas]
 
 A "step" is one HybridFluid::step (P2G, PCG solve, G2P/advection, density rhs, PCG solve, particle correction) over the
 synthetic 256^3 / 16,387,064-particle dam break that BASELINE.json's metric is quoted on.  N > 1 (torchrun, one rank per
-GPU): every rank advances its own replica of the scene (the path has no cross-GPU exchange yet), `value` = ranks * steps/s.
+GPU): ONE simulation of N such scenes stacked along z, sharded into N z-slabs (weak scaling: per-GPU work fixed); `value` =
+slab-steps/s = N * steps/s, so that N = 1 is exactly the single-GPU number.  `--multi replicas` runs N independent scenes.
 `--impl reference`: the reference (Rust + wgpu/Vulkan) cannot run on this image, so this arm times the CPU restatement of
 its algorithm (oracle/) on the host cores -- the only place besides cpu_baseline where bench.py executes oracle/.
 """
@@ -214,6 +215,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-sharded-pcg", action="store_true")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
+                    help="N > 1: one z-slab sharded simulation (default) or N independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 2
@@ -244,8 +247,35 @@ def main():
 
     sc, desc = workload_desc(args.workload)
     dt = F.DT_120HZ
-    fluid = blub_b200.HybridFluid.from_scene(scene_path(args.workload), device=local)
-    npart = fluid.num_particles
+    sharded_step = world > 1 and args.multi == "sharded"
+    if not sharded_step:
+        fluid = blub_b200.HybridFluid.from_scene(scene_path(args.workload), device=local)
+        npart = fluid.num_particles
+        parallelism = "single GPU" if world == 1 else f"{world} independent replicas (one scene per GPU, no exchange)"
+    else:
+        # Weak scaling of ONE simulation: `world` copies of the workload stacked along z in a single connected domain, one
+        # z-slab (= one copy's worth of grid and particles) per GPU; particles migrate and halos are exchanged across the faces.
+        from blub_b200 import slab
+
+        d = sc["fluid"]["grid_dimension"]
+        scale = sc["fluid"]["grid_to_world_scale"]
+        fluid = blub_b200.HybridFluid.create_slab(d["x"], d["y"], d["z"], sc["fluid"]["max_num_particles"], rank=rank, world=world, device=local)
+        handles = slab.exchange_handles(fluid.ipc_export_window(), dist)
+        own = fluid.slab_window()[0]
+        fluid.attach_slab_peers([own if k == rank else F.ipc_open(handles[k], local) for k in range(world)])
+        for k in range(world):
+            for cube in sc["fluid"]["fluid_cubes"]:
+                mn = [cube["min"][c] / scale for c in "xyz"]
+                mx = [cube["max"][c] / scale for c in "xyz"]
+                mn[2] += k * d["z"]
+                mx[2] = min(mx[2], d["z"] - 1) + k * d["z"]
+                fluid.add_fluid_cube(mn, mx)
+        fluid.set_gravity_grid([sc["gravity"][c] / scale for c in "xyz"])
+        counts = [None] * world
+        dist.all_gather_object(counts, fluid.num_particles)
+        npart = sum(counts)
+        desc = f"{world} x ({desc}) stacked along z = {d['x']}x{d['y']}x{d['z'] * world} grid"
+        parallelism = f"one simulation on {world} z-slabs (P2P halo exchange + particle migration, in-kernel PCG exchange)"
     for _ in range(max(args.warmup, 3)):
         fluid.step(dt)
     fluid.synchronize()
@@ -279,6 +309,9 @@ def main():
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e.item())
     stats = fluid.pressure_solver_stats(0)[-1], fluid.pressure_solver_stats(1)[-1]
+    slab_err = fluid.slab_error() if sharded_step else 0
+    if world > 1:
+        dist.barrier()
     fluid.close()
 
     sharded = None
@@ -296,13 +329,14 @@ def main():
             "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc, "particles": npart, "dt": dt, "solver": "tol 0.1 / max 32 / check 4 (reference defaults)", "rebin_every": 60,
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one scene per GPU, no exchange)",
+                       "parallelism": parallelism,
                        "l2": "inputs larger than L2 (>= 1 GB of particle state, 64 MiB per grid volume)",
                        "last_solver_stats": {"velocity": stats[0], "density": stats[1]}},
             "clocks": clocks,
             "e2e": {"value": round(world * args.steps / e2e_s, 3), "unit": "steps/s", "h2d_bytes_per_step": 36, "d2h_bytes_per_step": 16,
                     "note": "blub_fluid_step + blub_fluid_synchronize + blub_fluid_update_statistics per step (host-timed)"},
             "gpu_launches": int(launches),
+            "slab_error": slab_err,
             "roofline": roof,
             "cpu_baseline": cpu,
         }

@@ -119,7 +119,8 @@ def test_sharded_full_step_matches_single_gpu():
     assert sum(s.num_particles for s in slabs) == n_ref
     a, _ = sort_rows3(ref.download_particles()[:, :3])
     b, _ = sort_rows3(_global_particles(slabs, nz_owned)[:, :3])
-    assert np.array_equal(a, b)  # same particle stream, split by slab
+    # same particle stream, split by slab; re-basing z into the local frame and back costs an ulp
+    assert np.array_equal(a[:, :2], b[:, :2]) and np.abs(a[:, 2] - b[:, 2]).max() <= 8e-6
 
     def step_all():
         ref.step(DT)
