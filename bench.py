@@ -259,7 +259,8 @@ def main():
 
         d = sc["fluid"]["grid_dimension"]
         scale = sc["fluid"]["grid_to_world_scale"]
-        fluid = blub_b200.HybridFluid.create_slab(d["x"], d["y"], d["z"], sc["fluid"]["max_num_particles"], rank=rank, world=world, device=local)
+        cap = int(sc["fluid"]["max_num_particles"] * 1.3)  # head room: slabs exchange particles
+        fluid = blub_b200.HybridFluid.create_slab(d["x"], d["y"], d["z"], cap, rank=rank, world=world, device=local)
         handles = slab.exchange_handles(fluid.ipc_export_window(), dist)
         own = fluid.slab_window()[0]
         fluid.attach_slab_peers([own if k == rank else F.ipc_open(handles[k], local) for k in range(world)])

@@ -241,7 +241,7 @@ class HybridFluid {
     float4 *row_[3] = {nullptr, nullptr, nullptr};
     GridArray<float> u_[3], density_;
     GridArray<float2> numw_[3];        // P2G accumulators: (sum w*value, sum w) per face
-    uint8_t *seg_fluid_ = nullptr, *row_fluid_ = nullptr; // coarse occupancy maps of the marker volume
+    uint8_t *seg_fluid_ = nullptr, *row_fluid_ = nullptr, *row_near_ = nullptr; // coarse occupancy maps of the marker volume
     int seg_shift_ = 5;
     GridArray<int8_t> marker_;
     uint32_t *cell_count_ = nullptr; // binning: per-cell counters / offsets

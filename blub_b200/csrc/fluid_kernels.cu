@@ -108,6 +108,18 @@ __global__ void __launch_bounds__(PT) boundary_marker_kernel(GridDim g, int8_t *
     }
 }
 
+// row_near[z * ny + y] = any FLUID cell in rows [y-1, y+2] x [z-1, z+2]: one byte answers "nothing to extrapolate here"
+__global__ void __launch_bounds__(PT) row_near_kernel(GridDim g, const uint8_t *__restrict__ row_fluid, uint8_t *__restrict__ row_near) {
+    const int r = blockIdx.x * PT + threadIdx.x;
+    if (r >= g.ny * g.nz) return;
+    const int y = r % g.ny, z = r / g.ny;
+    const int y0 = max(y - 1, 0), y1 = min(y + 2, g.ny - 1), z0 = max(z - 1, 0), z1 = min(z + 2, g.nz - 1);
+    unsigned near = 0;
+    for (int zz = z0; zz <= z1; ++zz)
+        for (int yy = y0; yy <= y1; ++yy) near |= row_fluid[zz * g.ny + yy];
+    row_near[r] = near ? 1 : 0;
+}
+
 // Normalisation + global forces + "don't flow into solid": transfer_gather_velocity.comp:116-127.
 // Faces that touch no FLUID cell are written 0 here (the reference leaves them stale; never observable).
 __global__ void __launch_bounds__(PT) p2g_normalize_kernel(GridDim g, const StepParams *__restrict__ params,
@@ -226,7 +238,8 @@ __device__ __forceinline__ bool valid_velocity(const GridDim &g, const int8_t *_
     return in && marker[n] == CELL_FLUID;
 }
 __global__ void __launch_bounds__(PT) extrapolate_kernel(GridDim g, const int8_t *__restrict__ marker, const uint8_t *__restrict__ seg_fluid,
-                                                         const uint8_t *__restrict__ row_fluid, int seg_shift, float *__restrict__ ux,
+                                                         const uint8_t *__restrict__ row_fluid, const uint8_t *__restrict__ row_near, int seg_shift,
+                                                         float *__restrict__ ux,
                                                          float *__restrict__ uy, float *__restrict__ uz) {
     const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
     if (i >= g.n) return;
@@ -236,12 +249,9 @@ __global__ void __launch_bounds__(PT) extrapolate_kernel(GridDim g, const int8_t
     // Quick reject: a face is only written if a FLUID cell lies in [x-1,x+2] x [y-1,y+2] x [z-1,z+2] (the in-plane ring of
     // candidate faces plus their +e_c neighbours).  Rows first (warp-uniform loads), then x-segments.
     {
+        if (!row_near[z * g.ny + y]) return;
         const int y0 = max(y - 1, 0), y1 = min(y + 2, g.ny - 1), z0 = max(z - 1, 0), z1 = min(z + 2, g.nz - 1);
         bool near = false;
-        for (int zz = z0; zz <= z1; ++zz)
-            for (int yy = y0; yy <= y1; ++yy) near = near || row_fluid[zz * g.ny + yy];
-        if (!near) return;
-        near = false;
         const int s0 = max(x - 1, 0) >> seg_shift, s1 = min(x + 2, g.nx - 1) >> seg_shift, segs = g.nx >> seg_shift;
         for (int zz = z0; zz <= z1; ++zz)
             for (int yy = y0; yy <= y1; ++yy) {
@@ -629,6 +639,7 @@ inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 
 static void run_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, const uint2 *vox, const MarkerFlags &flags) {
     BLUB_CUDA_CHECK(cudaMemsetAsync(flags.row_fluid, 0, (size_t)g.ny * g.nz, st));
     BLUB_LAUNCH(boundary_marker_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, vox, flags.seg_fluid, flags.row_fluid, 1 << flags.seg_shift);
+    BLUB_LAUNCH(row_near_kernel, blocks_for((int64_t)g.ny * g.nz, PT), PT, 0, st, g, flags.row_fluid, flags.row_near);
 }
 
 void launch_p2g_scatter(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float4 *const row[3],
@@ -661,7 +672,7 @@ void launch_divergence_remove(cudaStream_t st, const GridDim &g, const int8_t *m
 }
 
 void launch_extrapolate(cudaStream_t st, const GridDim &g, const int8_t *marker, const MarkerFlags &flags, float *const u[3]) {
-    BLUB_LAUNCH(extrapolate_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, flags.seg_fluid, flags.row_fluid, flags.seg_shift, u[0], u[1], u[2]);
+    BLUB_LAUNCH(extrapolate_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, flags.seg_fluid, flags.row_fluid, flags.row_near, flags.seg_shift, u[0], u[1], u[2]);
 }
 
 void launch_clear_marker(cudaStream_t st, const GridDim &g, int8_t *marker) {

@@ -10,6 +10,7 @@ namespace blub {
 struct MarkerFlags {
     uint8_t *seg_fluid; // n >> seg_shift entries
     uint8_t *row_fluid; // ny * nz entries
+    uint8_t *row_near;  // ny * nz entries: row_fluid dilated by [-1, +2] in y and z
     int seg_shift;      // 5 (32-cell segments) or 3 when nx is not a multiple of 32
 };
 

@@ -60,5 +60,26 @@ def report(path):
         print()
 
 
+def traffic(path):
+    """dram bytes of the persistent PCG solve kernel -> profiles/pcg_traffic.json (read by bench.py as roofline.traffic)."""
+    import json
+
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    best = None
+    for r in rows[2:]:
+        if "pcg_solve_persistent" not in r[idx["Kernel Name"]]:
+            continue
+        rd = float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
+        wr = float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+        t = r[idx["gpu__time_duration.sum"]] + " " + units[idx["gpu__time_duration.sum"]]
+        best = {"dram_bytes_per_solve": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr), "kernel_time_under_ncu": t,
+                "kernel": "pcg_solve_persistent_kernel (256^3 all-fluid microbench, 33 iterations)", "source": path}
+    print(json.dumps(best, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2])
