@@ -47,6 +47,13 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    # headless runner over the C ABI only: a plain C++ program linked against libblubcore.so
+    runner, rsrc = os.path.join(HERE, "blub_run"), os.path.join(CSRC, "blub_run.cpp")
+    if force or _stale(runner, [rsrc, LIB, os.path.join(HERE, "..", "include", "blub_fluid.h")]):
+        cmd = [NVCC, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", runner, rsrc, "-L" + HERE, "-lblubcore", "-Xlinker", "-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
     return LIB
 
 

@@ -1,0 +1,128 @@
+// blub_run -- headless scene runner over the C ABI (include/blub_fluid.h only; links libblubcore.so).
+//
+// The reference has no headless mode; its closest thing to a batch run is the GUI's "fast forward"
+// (src/simulation_controller.rs:96-157): batches of 16 steps, a device.poll(Maintain::Wait) after each batch, wall time
+// logged as "Fast forward of {:?} took {:?} to compute".  This tool reproduces that protocol on an unchanged blub scene
+// file, and stands in for three more pieces of the reference's shell:
+//   --stats FILE   solver statistics history as JSON (the GUI's residual / iteration plots, src/gui/mod.rs:177-210)
+//   --trace FILE   one step as a Chrome trace with the reference's profiler scope labels (src/gui/mod.rs:487-491,
+//                  hybrid_fluid.rs:780-973)
+//   --dump FILE    particle positions (float32 x,y,z,pad) for an external viewer -- the renderer hand-off
+//                  (hybrid_fluid.rs:351-369) without wgpu
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/blub_fluid.h"
+
+static const char *kScopeLabels[14] = {
+    "transfer particle velocity to grid", "compute divergence", "primary pressure solver (divergence)", "Particle Binning",
+    "make velocity grid divergence free", "extrapolate velocity grid", "clear marker & linked list grids",
+    "advect particles & write new linked list grid", "density projection: set boundary marker",
+    "density projection: compute density error via gather", "secondary pressure solver (density)", "compute position change",
+    "extrapolate velocity grid", "correct particle density error"};
+
+static void die(const char *what) {
+    std::fprintf(stderr, "blub_run: %s: %s\n", what, blub_last_error());
+    std::exit(1);
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) {
+        std::fprintf(stderr, "usage: blub_run scene.json [--steps N] [--batch 16] [--hz 120] [--device 0] [--no-graph]\n"
+                             "                [--stats out.json] [--trace out.json] [--dump particles.f32]\n");
+        return 2;
+    }
+    const char *scene = argv[1];
+    int steps = 160, batch = 16, device = 0, graph = 1;
+    long hz = 120;
+    std::string stats_path, trace_path, dump_path;
+    for (int i = 2; i < argc; ++i) {
+        auto next = [&](const char *flag) -> const char * {
+            if (i + 1 >= argc) { std::fprintf(stderr, "blub_run: %s needs a value\n", flag); std::exit(2); }
+            return argv[++i];
+        };
+        if (!std::strcmp(argv[i], "--steps")) steps = std::atoi(next("--steps"));
+        else if (!std::strcmp(argv[i], "--batch")) batch = std::atoi(next("--batch"));
+        else if (!std::strcmp(argv[i], "--hz")) hz = std::atol(next("--hz"));
+        else if (!std::strcmp(argv[i], "--device")) device = std::atoi(next("--device"));
+        else if (!std::strcmp(argv[i], "--no-graph")) graph = 0;
+        else if (!std::strcmp(argv[i], "--stats")) stats_path = next("--stats");
+        else if (!std::strcmp(argv[i], "--trace")) trace_path = next("--trace");
+        else if (!std::strcmp(argv[i], "--dump")) dump_path = next("--dump");
+        else { std::fprintf(stderr, "blub_run: unknown option %s\n", argv[i]); return 2; }
+    }
+    if (steps < 1 || batch < 1 || hz < 1) { std::fprintf(stderr, "blub_run: bad --steps/--batch/--hz\n"); return 2; }
+    // delta_from_steps_per_second: Duration::from_nanos(1e9 / hz), then as_secs_f32 (simulation_controller.rs:33-35)
+    const double dt = (double)(float)((double)(1000000000L / hz) * 1e-9);
+
+    BlubSceneInfo info;
+    if (blub_scene_info(scene, &info)) die("cannot read scene");
+    BlubFluid *fluid = nullptr;
+    if (blub_scene_load(&fluid, scene, device, nullptr)) die("cannot create fluid");
+    blub_fluid_set_graph_replay(fluid, graph);
+    std::printf("scene %s: grid %ux%ux%u, %u particles (max %u), %u static object(s) ignored, dt %.9f s\n", scene, info.grid_dimension[0],
+                info.grid_dimension[1], info.grid_dimension[2], blub_fluid_num_particles(fluid), info.max_num_particles, info.num_static_objects, dt);
+
+    const auto t0 = std::chrono::steady_clock::now();
+    int done = 0;
+    while (done < steps) { // MAX_FAST_FORWARD_SIMULATION_BATCH_SIZE = 16, then wait for the GPU
+        const int n = steps - done < batch ? steps - done : batch;
+        for (int k = 0; k < n; ++k)
+            if (blub_fluid_step(fluid, dt)) die("step failed");
+        if (blub_fluid_synchronize(fluid)) die("synchronize failed");
+        blub_fluid_update_statistics(fluid);
+        done += n;
+        std::printf("simulation fast forwarding batch finished (progress %d/%d)\n", done, steps);
+    }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("Fast forward of %.6fs took %.6fs to compute (%.2f steps/s)\n", steps * dt, secs, steps / secs);
+
+    if (!stats_path.empty()) {
+        FILE *f = std::fopen(stats_path.c_str(), "w");
+        if (!f) { std::perror("blub_run: --stats"); return 1; }
+        std::fprintf(f, "{\"steps\": %d, \"seconds\": %.6f", steps, secs);
+        const char *names[2] = {"velocity", "density"};
+        for (int which = 0; which < 2; ++which) {
+            BlubSolverSample s[100];
+            const size_t n = blub_fluid_solver_stats(fluid, which, s, 100);
+            std::fprintf(f, ", \"%s\": [", names[which]);
+            for (size_t k = 0; k < n; ++k) std::fprintf(f, "%s{\"error\": %.9g, \"iteration_count\": %d}", k ? ", " : "", s[k].error, s[k].iteration_count);
+            std::fprintf(f, "]");
+        }
+        std::fprintf(f, "}\n");
+        std::fclose(f);
+    }
+    if (!trace_path.empty()) { // "Write Chrometrace" (src/gui/mod.rs:487-491): one eagerly launched, event-timed step
+        float ms[14];
+        if (blub_fluid_step_timed(fluid, dt, ms)) die("timed step failed");
+        FILE *f = std::fopen(trace_path.c_str(), "w");
+        if (!f) { std::perror("blub_run: --trace"); return 1; }
+        std::fprintf(f, "{\"traceEvents\": [\n");
+        double ts = 0.0, total = 0.0;
+        for (int s = 0; s < 14; ++s) total += ms[s];
+        std::fprintf(f, " {\"name\": \"HybridFluid step\", \"ph\": \"X\", \"pid\": 1, \"tid\": 1, \"ts\": 0, \"dur\": %.3f}", total * 1e3);
+        for (int s = 0; s < 14; ++s) {
+            std::fprintf(f, ",\n {\"name\": \"%s\", \"ph\": \"X\", \"pid\": 1, \"tid\": 1, \"ts\": %.3f, \"dur\": %.3f}", kScopeLabels[s], ts, ms[s] * 1e3);
+            ts += ms[s] * 1e3;
+        }
+        std::fprintf(f, "\n]}\n");
+        std::fclose(f);
+    }
+    if (!dump_path.empty()) {
+        const uint32_t n = blub_fluid_num_particles(fluid);
+        std::vector<float> pos((size_t)n * 4);
+        if (n && blub_fluid_download(fluid, BLUB_TAP_PARTICLE_POS, pos.data(), pos.size() * sizeof(float))) die("download failed");
+        FILE *f = std::fopen(dump_path.c_str(), "wb");
+        if (!f) { std::perror("blub_run: --dump"); return 1; }
+        std::fwrite(pos.data(), sizeof(float), pos.size(), f);
+        std::fclose(f);
+        std::printf("wrote %u particles (float32 x y z pad, grid units; world = grid * %g + (%g, %g, %g)) to %s\n", n, info.grid_to_world_scale,
+                    info.world_position[0], info.world_position[1], info.world_position[2], dump_path.c_str());
+    }
+    blub_fluid_destroy(fluid);
+    return 0;
+}

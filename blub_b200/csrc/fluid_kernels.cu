@@ -16,12 +16,15 @@ namespace {
 
 constexpr int PT = 256; // threads per block for particle and cell kernels
 
-__device__ __forceinline__ int64_t lin(const GridDim &g, int x, int y, int z) { return ((int64_t)z * g.ny + y) * g.nx + x; }
-__device__ __forceinline__ void cell_of(const GridDim &g, int64_t i, int &x, int &y, int &z) {
-    x = (int)(i % g.nx);
-    int64_t t = i / g.nx;
-    y = (int)(t % g.ny);
-    z = (int)(t / g.ny);
+// Cell indices fit 32 bits (HybridFluid::new rejects grids of 2^31 cells or more): no 64-bit multiplies / divisions in the
+// per-cell and per-particle kernels.
+__device__ __forceinline__ int lin(const GridDim &g, int x, int y, int z) { return (z * g.ny + y) * g.nx + x; }
+__device__ __forceinline__ void cell_of(const GridDim &g, int64_t i64, int &x, int &y, int &z) {
+    const unsigned i = (unsigned)i64, nx = (unsigned)g.nx, ny = (unsigned)g.ny;
+    const unsigned t = i / nx;
+    x = (int)(i - t * nx);
+    z = (int)(t / ny);
+    y = (int)(t - (unsigned)z * ny);
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepPa
         float wxs[2] = {saturatef(1.0f - fabsf(tx[0])), saturatef(1.0f - fabsf(tx[1]))};
         float wys[2] = {saturatef(1.0f - fabsf(ty[0])), saturatef(1.0f - fabsf(ty[1]))};
         float wzs[2] = {saturatef(1.0f - fabsf(tz[0])), saturatef(1.0f - fabsf(tz[1]))};
-        const int64_t base = lin(g, dx, dy, dz);
+        const int base = lin(g, dx, dy, dz);
 #pragma unroll
         for (int oz_ = 0; oz_ < 2; ++oz_)
 #pragma unroll
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepPa
                     const float w = wxs[ox_] * wys[oy_] * wzs[oz_];
                     if (w <= 0.0f) continue;
                     const float v = r.x * tx[ox_] + r.y * ty[oy_] + r.z * tz[oz_] + r.w;
-                    const int64_t f = base + ox_ + (int64_t)oy_ * g.sy + (int64_t)oz_ * g.sz;
+                    const int f = base + ox_ + oy_ * g.sy + oz_ * g.sz;
                     // one 8-byte vector reduction (RED.E.ADD.F32x2) per face instead of two scalar ones
                     atomicAdd(nw[c] + f, make_float2(w * v, w));
                 }
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(PT) density_scatter_kernel(GridDim g, const St
     const float wx[2] = {saturatef(1.0f - fabsf(qx - p.x)), saturatef(1.0f - fabsf(qx + 1.0f - p.x))};
     const float wy[2] = {saturatef(1.0f - fabsf(qy - p.y)), saturatef(1.0f - fabsf(qy + 1.0f - p.y))};
     const float wz[2] = {saturatef(1.0f - fabsf(qz - p.z)), saturatef(1.0f - fabsf(qz + 1.0f - p.z))};
-    const int64_t base = lin(g, dx, dy, dz);
+    const int base = lin(g, dx, dy, dz);
 #pragma unroll
     for (int oz = 0; oz < 2; ++oz)
 #pragma unroll
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(PT) density_scatter_kernel(GridDim g, const St
 #pragma unroll
             for (int ox = 0; ox < 2; ++ox) {
                 const float w = wx[ox] * wy[oy] * wz[oz];
-                if (w > 0.0f) atomicAdd(density + base + ox + (int64_t)oy * g.sy + (int64_t)oz * g.sz, w);
+                if (w > 0.0f) atomicAdd(density + base + ox + oy * g.sy + oz * g.sz, w);
             }
 }
 

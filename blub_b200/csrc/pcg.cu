@@ -599,7 +599,7 @@ __device__ __forceinline__ double grid_sum(cooperative_groups::grid_group &grid,
     return v;
 }
 
-__global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_persistent_kernel(PcgSolveArgs a) {
+__global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(PcgSolveArgs a) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ float sh[PCG_THREADS / 32];
