@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libblubcore.so")
-SOURCES = ["pcg.cu", "fluid_kernels.cu", "hybrid_fluid.cu", "slab.cu", "scene.cpp", "c_api.cpp"]
+SOURCES = ["pcg.cu", "fluid_kernels.cu", "hybrid_fluid.cu", "slab.cu", "solids.cu", "scene.cpp", "c_api.cpp"]
 HEADERS = ["common.cuh", "blub_core.hpp", "fluid_kernels.hpp", os.path.join("..", "..", "include", "blub_fluid.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

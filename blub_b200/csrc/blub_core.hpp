@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/blub_fluid.h"
 #include "common.cuh"
 
 namespace blub {
@@ -260,6 +261,9 @@ class HybridFluid {
     uint32_t step_param_slot_ = 0;
     cudaEvent_t param_events_[64] = {};
 };
+
+void voxelize_rigid_solid(void *rgba16f, const uint32_t dim[3], const BlubRigidObject &o, float grid_to_world_scale, const float fluid_world_position[3],
+                          double total_time, double delta, int clear_first, cudaStream_t stream, BlubRigidState *state_out);
 
 // scene JSON (src/scene/mod.rs:19-43)
 struct SceneBox {

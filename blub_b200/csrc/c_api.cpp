@@ -108,6 +108,16 @@ int blub_fluid_attach_slab_peers(BlubFluid *fluid, void *const *windows, int wor
     return guarded([&] { fluid->impl->attach_slab_peers(windows, world); return BLUB_OK; });
 }
 
+int blub_solid_voxelize(void *rgba16f, const uint32_t dim[3], const BlubRigidObject *object, float scale, const float fluid_world_position[3],
+                        double total_time, double delta, int clear_first, void *cuda_stream, BlubRigidState *state_out) {
+    if (!rgba16f || !dim || !object || !fluid_world_position) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!(scale > 0.0f) || !(delta > 0.0)) return fail(BLUB_ERR_INVALID_ARGUMENT, "scale and delta must be positive");
+    return guarded([&] {
+        blub::voxelize_rigid_solid(rgba16f, dim, *object, scale, fluid_world_position, total_time, delta, clear_first, static_cast<cudaStream_t>(cuda_stream), state_out);
+        return BLUB_OK;
+    });
+}
+
 int blub_fluid_slab_error(BlubFluid *fluid) {
     if (!fluid) return -1;
     int e = -1;

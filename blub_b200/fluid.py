@@ -46,6 +46,39 @@ class FluidView(C.Structure):
         "grid_velocity_x", "grid_velocity_y", "grid_velocity_z", "marker", "pressure_from_velocity", "pressure_from_density")]
 
 
+class RigidObject(C.Structure):
+    """BlubRigidObject: StaticObjectConfig + RigidAnimation (src/scene/models.rs:11-46) for an analytic box / sphere."""
+
+    _fields_ = [("world_position", C.c_float * 3), ("scale", C.c_float), ("rotation_angles_deg", C.c_float * 3), ("shape", C.c_int32),
+                ("half_extent", C.c_float * 3), ("has_translation", C.c_int32), ("translation_target", C.c_float * 3),
+                ("translation_curve", C.c_int32), ("translation_duration", C.c_float), ("has_rotation", C.c_int32),
+                ("rotation_axis", C.c_float * 3), ("rotation_deg_per_sec", C.c_float)]
+
+    @classmethod
+    def from_dict(cls, obj):
+        o = cls()
+        o.world_position[:] = [float(v) for v in obj["world_position"]]
+        o.scale = float(obj.get("scale", 1.0))
+        o.rotation_angles_deg[:] = [float(v) for v in obj.get("rotation_angles", (0, 0, 0))]
+        o.shape = 1 if obj.get("shape", "box") == "sphere" else 0
+        o.half_extent[:] = [float(v) for v in obj["half_extent"]]
+        tr, rot = obj.get("translation"), obj.get("rotation")
+        if tr:
+            o.has_translation = 1
+            o.translation_target[:] = [float(v) for v in tr["target"]]
+            o.translation_curve = 1 if tr.get("curve", "Linear") == "SmoothStep" else 0
+            o.translation_duration = float(tr["duration"])
+        if rot:
+            o.has_rotation = 1
+            o.rotation_axis[:] = [float(v) for v in rot["axis"]]
+            o.rotation_deg_per_sec = float(rot["deg_per_sec"])
+        return o
+
+
+class RigidState(C.Structure):
+    _fields_ = [("centre_voxel", C.c_float * 3), ("velocity_voxel", C.c_float * 3), ("axis_scaled", C.c_float * 3), ("rotation", C.c_float * 9)]
+
+
 class SceneInfo(C.Structure):
     _fields_ = [("grid_dimension", C.c_uint32 * 3), ("max_num_particles", C.c_uint32), ("grid_to_world_scale", C.c_float),
                 ("world_position", C.c_float * 3), ("gravity", C.c_float * 3), ("num_fluid_cubes", C.c_uint32),
@@ -76,6 +109,8 @@ def lib():
         "blub_fluid_slab_window": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "blub_fluid_attach_slab_peers": (C.c_int, [vp, C.POINTER(vp), C.c_int]),
         "blub_fluid_slab_error": (C.c_int, [vp]),
+        "blub_solid_voxelize": (C.c_int, [vp, C.POINTER(u32), C.POINTER(RigidObject), C.c_float, f3, C.c_double, C.c_double, C.c_int, vp,
+                                          C.POINTER(RigidState)]),
         "blub_ipc_export": (C.c_int, [vp, C.c_char_p]),
         "blub_ipc_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
         "blub_ipc_close": (C.c_int, [vp]),
@@ -136,6 +171,15 @@ def ipc_open(handle: bytes, device: int) -> int:
 
 def enable_peer_access(device: int, peer: int):
     _check(lib().blub_enable_peer_access(device, peer))
+
+
+def solid_voxelize(rgba16f_device_ptr, dims, obj, scale, fluid_world_position, t, dt, clear_first=True, cuda_stream=None):
+    """Write one analytic rigid solid (dict, see RigidObject.from_dict) into an RGBA16F device volume; returns its RigidState."""
+    d = (C.c_uint32 * 3)(*[int(v) for v in dims])
+    st = RigidState()
+    _check(lib().blub_solid_voxelize(rgba16f_device_ptr, d, C.byref(RigidObject.from_dict(obj)), float(scale), _f3(fluid_world_position), float(t),
+                                     float(dt), 1 if clear_first else 0, cuda_stream, C.byref(st)))
+    return st
 
 
 def kernel_launch_count(reset=False) -> int:

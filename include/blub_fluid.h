@@ -143,6 +143,32 @@ typedef struct {
 } BlubSceneInfo;
 int blub_scene_info(const char *scene_json_path, BlubSceneInfo *out);
 
+/* ---- analytic rigid solids (stand-in for the mesh voxelizer, src/scene/voxelization.rs:118-157) ---------------------------
+ * One oriented box or sphere with the reference's rigid animation (StaticObjectConfig / RigidAnimation, src/scene/models.rs:11-46,
+ * 154-224) written into an RGBA16F voxel volume: xyz = solid velocity in cells/s, w = 1 inside. */
+typedef struct {
+    float world_position[3];
+    float scale;
+    float rotation_angles_deg[3];   /* static Euler angles (cgmath Euler<Deg>) */
+    int32_t shape;                  /* 0 = box with half_extent (model space), 1 = sphere of radius half_extent[0] */
+    float half_extent[3];
+    int32_t has_translation;        /* TranslationAnimation: ping-pong between world_position and target */
+    float translation_target[3];
+    int32_t translation_curve;      /* 0 = Linear, 1 = SmoothStep */
+    float translation_duration;
+    int32_t has_rotation;           /* RotationAnimation */
+    float rotation_axis[3];
+    float rotation_deg_per_sec;
+} BlubRigidObject;
+typedef struct {                    /* what the animation evaluated to (for tests / logging) */
+    float centre_voxel[3], velocity_voxel[3], axis_scaled[3], rotation[9];
+} BlubRigidState;
+/* Evaluates the animation at `total_simulated_time` (velocity = finite difference over `simulation_delta`, models.rs:186-191)
+ * and enqueues the voxelization on `cuda_stream`.  clear_first != 0 zeroes the rest of the volume (first object of a step). */
+int blub_solid_voxelize(void *rgba16f_device_ptr, const uint32_t grid_dimension[3], const BlubRigidObject *object, float grid_to_world_scale,
+                        const float fluid_world_position[3], double total_simulated_time, double simulation_delta, int clear_first,
+                        void *cuda_stream, BlubRigidState *state_out);
+
 /* ---- multi-GPU: z-slab sharding of the pressure solve (the reference is single-GPU) ---------------
  * Rank `rank` of `world` (<= 8) owns nz_owned planes of a global nx x ny x (world * nz_owned) grid; its local grid has 4
  * ghost planes on both sides (local plane 4 = first owned plane).  Each rank exposes ONE device allocation (the "window":
