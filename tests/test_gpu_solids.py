@@ -21,9 +21,9 @@ OBJ = {"world_position": [0.44, 0.12, 0.16], "scale": 1.0, "rotation_angles": [0
 @pytest.mark.parametrize("shape", ["box", "sphere"])
 def test_voxelizer_matches_numpy_restatement(t, shape):
     import torch
-    dims, scale, origin = (32, 32, 32), 0.01, (0.0, 0.0, 0.0)
+    dims, scale, origin = (64, 32, 32), 0.01, (0.0, 0.0, 0.0)  # the object travels between x = 44 and x = 20 cells
     obj = dict(OBJ, shape=shape)
-    vol = torch.full((32, 32, 32, 4), 7.0, dtype=torch.float16, device="cuda")
+    vol = torch.full((32, 32, 64, 4), 7.0, dtype=torch.float16, device="cuda")
     st = F.solid_voxelize(vol.data_ptr(), dims, obj, scale, origin, t, DT)
     torch.cuda.synchronize()
     got = vol.float().cpu().numpy()
