@@ -259,7 +259,7 @@ def main():
 
         d = sc["fluid"]["grid_dimension"]
         scale = sc["fluid"]["grid_to_world_scale"]
-        cap = int(sc["fluid"]["max_num_particles"] * 1.3)  # head room: slabs exchange particles
+        cap = int(sc["fluid"]["max_num_particles"] * 2)  # head room: fluid flows between slabs
         fluid = blub_b200.HybridFluid.create_slab(d["x"], d["y"], d["z"], cap, rank=rank, world=world, device=local)
         handles = slab.exchange_handles(fluid.ipc_export_window(), dist)
         own = fluid.slab_window()[0]
@@ -311,6 +311,12 @@ def main():
     e2e_s = float(t_e.item())
     stats = fluid.pressure_solver_stats(0)[-1], fluid.pressure_solver_stats(1)[-1]
     slab_err = fluid.slab_error() if sharded_step else 0
+    slab_counts = None
+    if sharded_step:
+        info = [None] * world
+        dist.all_gather_object(info, (fluid.num_particles, slab_err))
+        slab_counts = [c for c, _ in info]
+        slab_err = max(e for _, e in info)
     if world > 1:
         dist.barrier()
     fluid.close()
@@ -338,6 +344,7 @@ def main():
                     "note": "blub_fluid_step + blub_fluid_synchronize + blub_fluid_update_statistics per step (host-timed)"},
             "gpu_launches": int(launches),
             "slab_error": slab_err,
+            "slab_particles": slab_counts,
             "roofline": roof,
             "cpu_baseline": cpu,
         }

@@ -126,6 +126,14 @@ class PressureSolver {
 
   public:
     bool use_persistent = true;      // one cooperative launch per solve (diag2 preconditioner); false = three kernels per iteration
+    bool use_tma = false;            // persistent solver with TMA-staged tiles (nx % 128 == 0); BLUB_PCG=tma or blub_fluid_set_solver_path(f, 2)
+    bool tma_available() const { return tma_blocks_ > 0; }
+
+  private:
+    void *tma_maps_ = nullptr;       // PcgTmaMaps (tensor maps of r, s0, s1, codes)
+    int tma_blocks_ = 0;
+
+  public:
 };
 
 // HybridFluid, hybrid_fluid.rs:24-72,92-977

@@ -392,7 +392,9 @@ int blub_fluid_step_timed(BlubFluid *fluid, double dt, float ms_per_stage[14]) {
 int blub_fluid_set_solver_path(BlubFluid *fluid, int persistent) {
     if (!fluid) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL fluid");
     fluid->impl->solver().use_persistent = persistent != 0;
+    fluid->impl->solver().use_tma = persistent == 2;
     fluid->impl->invalidate_graphs();
+    if (persistent == 2 && !fluid->impl->solver().tma_available()) return fail(BLUB_ERR_INVALID_ARGUMENT, "TMA solver needs nx % 128 == 0 and cooperative launch");
     return BLUB_OK;
 }
 

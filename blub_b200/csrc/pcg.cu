@@ -18,6 +18,8 @@
 // the x-neighbours exchanged by warp shuffles; fp32 vectors, 1-byte cell codes, padded arrays (common.cuh); tiles without
 // any FLUID cell exit at once.  Because p, r and s are kept at exactly 0 off-fluid the 7-point stencil needs no masks.
 #include <cooperative_groups.h>
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cudaTypedefs.h>  // PFN_cuTensorMapEncodeTiled
 
 #include <cstdlib>
 
@@ -797,6 +799,287 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-tiled variant of the persistent solver (grids whose x extent is a multiple of 128 cells).
+//
+// Same algorithm, phases, barriers and multi-GPU protocol as pcg_solve_persistent_kernel; what changes is how a tile's
+// stencil operands reach the SM.  One elected thread issues 3-D tensor-map bulk loads (cp.async.bulk.tensor.3d, SASS
+// UTMALDG) of the tile PLUS its halo -- box (128+8) x (8+2) x (4+2) of r, s and (128+32) x 10 x 6 of the codes -- into
+// shared memory; completion is an mbarrier transaction count, out-of-range parts of a box are zero-filled by the TMA
+// unit (== SOLID / 0, the same convention as the padded arrays).  Phase A then evaluates s' = z + beta s ONCE per box
+// cell in shared memory (the register-marching kernel re-derives it for the y and z neighbours of every thread: 9
+// global vector loads per 4 cells and plane instead of 3 here), and both phases take all seven stencil operands from
+// shared memory.  Three blocks per SM, each single-buffered: while one block waits for its boxes the others compute.
+constexpr int TMA_BX = 136, TMA_BY = 10, TMA_BZ = 6; // float box: x0-4 .. x0+131, y0-1 .. y0+8, z0-1 .. z0+4
+constexpr int TMA_CX = 160;                           // code box:  x0-16 .. x0+143 (inner extent must be a multiple of 16 bytes)
+constexpr int TMA_F32_BYTES = TMA_BX * TMA_BY * TMA_BZ * 4; // 32,640 (multiple of 128)
+constexpr int TMA_U8_BYTES = TMA_CX * TMA_BY * TMA_BZ;      // 9,600
+constexpr int TMA_SMEM_BYTES = 2 * TMA_F32_BYTES + TMA_U8_BYTES; // 74,880 per block
+constexpr long long TMA_SPIN_LIMIT = 1LL << 26;
+
+struct PcgTmaMaps {
+    CUtensorMap r, s0, s1, codes;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// all threads: wait for the boxes of the current tile; a lost transaction ends the solve instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity, int *sh_dead) {
+    long long spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > TMA_SPIN_LIMIT) { *sh_dead = 1; break; }
+    }
+}
+
+__global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_tma_kernel(const __grid_constant__ PcgSolveArgs a, const __grid_constant__ PcgTmaMaps maps) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *const shR = reinterpret_cast<float *>(smem_raw);
+    float *const shS = reinterpret_cast<float *>(smem_raw + TMA_F32_BYTES);
+    uint8_t *const shC = smem_raw + 2 * TMA_F32_BYTES;
+    __shared__ uint64_t bar;
+    __shared__ float sh[PCG_THREADS / 32];
+    __shared__ double shd;
+    __shared__ float shf;
+    __shared__ double sh_csum[SLAB_MAX_WORLD];
+    __shared__ float sh_cmax[SLAB_MAX_WORLD];
+    __shared__ int sh_dead;
+    const GridDim g = a.g;
+    const TileMap t = a.t;
+    const SlabComm &cm_ = a.comm;
+    const bool sharded = cm_.world > 1;
+    const int nact = *a.num_active;
+    const uint8_t *__restrict__ codes = a.codes;
+    float *psumA = a.partials, *psumB = a.partials + gridDim.x, *pmax = a.partials + 2 * gridDim.x;
+    const int tz_first = cm_.halo / PCG_TZ, tz_last = t.tiles_z - 1 - cm_.halo / PCG_TZ;
+    const int push = cm_.owned_nz * g.sz;
+    float *const peer_r_lo = cm_.peer_r[0], *const peer_r_hi = cm_.peer_r[1];
+    const int tid = linear_tid(), lx = threadIdx.x, ly = threadIdx.y;
+    unsigned seq = 0, parity = 0;
+    if (tid == 0) {
+        sh_dead = 0;
+        mbar_init(&bar, 1);
+        fence_proxy_async(); // make the initialised barrier visible to the async (TMA) proxy
+    }
+    if (sharded) seq = *cm_.seq;
+    __syncthreads();
+
+    // ---- init: r <- b - A p, sigma <- z.r (as in the register-marching kernel: runs once, plain loads)
+    float acc = 0.0f;
+    for (int li = blockIdx.x; li < nact; li += gridDim.x) {
+        const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
+        int i = c.i;
+        float4 pm = zero4(), p0 = zero4(), pp = zero4();
+        if (c.valid) { pm = ld4(a.p + i - g.sz); p0 = ld4(a.p + i); }
+#pragma unroll
+        for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+            float left, right;
+            x_neighbours(a.p, i, p0, c, left, right);
+            if (c.valid) {
+                pp = ld4(a.p + i + g.sz);
+                const uchar4 code = ldcode(codes + i);
+                const float4 ym = ld4(a.p + i - g.sy), yp = ld4(a.p + i + g.sy);
+                float4 r4 = ld4(a.r + i);
+                const float4 Ap = stencil_quad(code, p0, left, right, ym, yp, pm, pp);
+                r4.x -= code.x ? Ap.x : 0.0f;
+                r4.y -= code.y ? Ap.y : 0.0f;
+                r4.z -= code.z ? Ap.z : 0.0f;
+                r4.w -= code.w ? Ap.w : 0.0f;
+                st4(a.r + i, r4);
+                if (sharded) {
+                    if (k == 0 && c.tz == tz_first && peer_r_lo) st4(peer_r_lo + i + push, r4);
+                    if (k == PCG_TZ - 1 && c.tz == tz_last && peer_r_hi) st4(peer_r_hi + i - push, r4);
+                }
+                acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
+                       (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
+            }
+            pm = p0;
+            p0 = pp;
+        }
+    }
+    double tot = grid_sum(grid, psumB, acc, sh, &shd);
+    float gmax = 0.0f;
+    if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+    float sigma = (float)tot;
+    float alpha = 0.0f, beta = 0.0f, max_error = 0.0f;
+    int num_iterations = 0;
+
+    // offsets of this thread's quad inside a box: row (ly + 1), columns 4 + 4 lx .. 7 + 4 lx
+    const int qoff = (ly + 1) * TMA_BX + 4 + 4 * lx;
+    const int coff = (ly + 1) * TMA_CX + 16 + 4 * lx;
+    constexpr int PLANE = TMA_BX * TMA_BY, CPLANE = TMA_CX * TMA_BY;
+
+    for (int it = 0;; ++it) {
+        const CUtensorMap *map_in = (it & 1) ? &maps.s1 : &maps.s0;
+        const CUtensorMap *map_out = (it & 1) ? &maps.s0 : &maps.s1;
+        float *s_out = (it & 1) ? a.s0 : a.s1;
+        // ---- phase A: boxes of r, s, codes -> smem; s' once per box cell; s'.A s' from smem
+        acc = 0.0f;
+        for (int li = blockIdx.x; li < nact; li += gridDim.x) {
+            const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
+            const int tile = c.tile, tx = tile % t.tiles_x, rest = tile / t.tiles_x, ty = rest % t.tiles_y, tz = rest / t.tiles_y;
+            const int x0 = tx * 128, y0 = ty * 8, z0 = tz * PCG_TZ;
+            __syncthreads(); // every thread is done with the previous tile's boxes
+            if (tid == 0) {
+                fence_proxy_async(); // generic-proxy reads of the boxes above happen-before the async writes below
+                mbar_arrive_expect_tx(&bar, 2 * TMA_F32_BYTES + TMA_U8_BYTES);
+                tma_load_3d(shR, &maps.r, x0 - 4, y0 - 1, z0 - 1, &bar);
+                tma_load_3d(shS, map_in, x0 - 4, y0 - 1, z0 - 1, &bar);
+                tma_load_3d(shC, &maps.codes, x0 - 16, y0 - 1, z0 - 1, &bar);
+            }
+            mbar_wait(&bar, parity, &sh_dead);
+            parity ^= 1u;
+            // s' = z + beta s for the whole box, in place over s (60 rows x 34 quads)
+            for (int qd = tid; qd < TMA_BY * TMA_BZ * (TMA_BX / 4); qd += PCG_THREADS) {
+                const int row = qd / (TMA_BX / 4), col = (qd - row * (TMA_BX / 4)) * 4;
+                const float4 r4 = *reinterpret_cast<const float4 *>(shR + row * TMA_BX + col);
+                float4 s4 = *reinterpret_cast<const float4 *>(shS + row * TMA_BX + col);
+                const uchar4 cd = *reinterpret_cast<const uchar4 *>(shC + row * TMA_CX + col + 12);
+                s4.x = precond_diag2(r4.x, cd.x) + beta * s4.x;
+                s4.y = precond_diag2(r4.y, cd.y) + beta * s4.y;
+                s4.z = precond_diag2(r4.z, cd.z) + beta * s4.z;
+                s4.w = precond_diag2(r4.w, cd.w) + beta * s4.w;
+                *reinterpret_cast<float4 *>(shS + row * TMA_BX + col) = s4;
+            }
+            __syncthreads();
+            int i = c.i;
+            if (sharded && c.tz == tz_first) st4(s_out + i - g.sz, *reinterpret_cast<const float4 *>(shS + qoff));
+#pragma unroll
+            for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+                const float *S = shS + (k + 1) * PLANE + qoff;
+                const float4 c0 = *reinterpret_cast<const float4 *>(S);
+                const float4 ym = *reinterpret_cast<const float4 *>(S - TMA_BX), yp = *reinterpret_cast<const float4 *>(S + TMA_BX);
+                const float4 zm = *reinterpret_cast<const float4 *>(S - PLANE), zp = *reinterpret_cast<const float4 *>(S + PLANE);
+                const uchar4 code = *reinterpret_cast<const uchar4 *>(shC + (k + 1) * CPLANE + coff);
+                const float4 As = stencil_quad(code, c0, S[-1], S[4], ym, yp, zm, zp);
+                acc += (c0.x * As.x + c0.y * As.y) + (c0.z * As.z + c0.w * As.w);
+                st4(s_out + i, c0);
+                if (sharded && k == PCG_TZ - 1 && c.tz == tz_last) st4(s_out + i + g.sz, zp);
+            }
+        }
+        tot = grid_sum(grid, psumA, acc, sh, &shd);
+        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+        alpha = guarded_div(sigma, (float)tot);
+
+        // ---- phase B: box of s' -> smem (p, r, codes: plain loads issued before the wait); update; z.r, max|r|
+        const bool with_err = (a.max_iterations == it) || (it > 0 && it % a.check_frequency == 0);
+        acc = 0.0f;
+        float err = 0.0f;
+        for (int li = blockIdx.x; li < nact; li += gridDim.x) {
+            const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
+            const int tile = c.tile, tx = tile % t.tiles_x, rest = tile / t.tiles_x, ty = rest % t.tiles_y, tz = rest / t.tiles_y;
+            __syncthreads();
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&bar, TMA_F32_BYTES);
+                tma_load_3d(shS, map_out, tx * 128 - 4, ty * 8 - 1, tz * PCG_TZ - 1, &bar);
+            }
+            float4 p4[PCG_TZ], r4[PCG_TZ];
+            uchar4 code[PCG_TZ];
+#pragma unroll
+            for (int k = 0; k < PCG_TZ; ++k) { // independent of the box: in flight while the TMA load lands
+                p4[k] = ld4(a.p + c.i + k * g.sz);
+                r4[k] = ld4(a.r + c.i + k * g.sz);
+                code[k] = ldcode(codes + c.i + k * g.sz);
+            }
+            mbar_wait(&bar, parity, &sh_dead);
+            parity ^= 1u;
+            int i = c.i;
+#pragma unroll
+            for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+                const float *S = shS + (k + 1) * PLANE + qoff;
+                const float4 s0 = *reinterpret_cast<const float4 *>(S);
+                const float4 ym = *reinterpret_cast<const float4 *>(S - TMA_BX), yp = *reinterpret_cast<const float4 *>(S + TMA_BX);
+                const float4 zm = *reinterpret_cast<const float4 *>(S - PLANE), zp = *reinterpret_cast<const float4 *>(S + PLANE);
+                const float4 As = stencil_quad(code[k], s0, S[-1], S[4], ym, yp, zm, zp);
+                float4 pq = p4[k], rq = r4[k];
+                pq.x += alpha * s0.x; pq.y += alpha * s0.y; pq.z += alpha * s0.z; pq.w += alpha * s0.w;
+                rq.x -= alpha * (code[k].x ? As.x : 0.0f);
+                rq.y -= alpha * (code[k].y ? As.y : 0.0f);
+                rq.z -= alpha * (code[k].z ? As.z : 0.0f);
+                rq.w -= alpha * (code[k].w ? As.w : 0.0f);
+                st4(a.p + i, pq);
+                st4(a.r + i, rq);
+                if (sharded) {
+                    if (k == 0 && c.tz == tz_first && peer_r_lo) st4(peer_r_lo + i + push, rq);
+                    if (k == PCG_TZ - 1 && c.tz == tz_last && peer_r_hi) st4(peer_r_hi + i - push, rq);
+                }
+                acc += (precond_diag2(rq.x, code[k].x) * rq.x + precond_diag2(rq.y, code[k].y) * rq.y) +
+                       (precond_diag2(rq.z, code[k].z) * rq.z + precond_diag2(rq.w, code[k].w) * rq.w);
+                err = fmaxf(fmaxf(err, fmaxf(fabsf(rq.x), fabsf(rq.y))), fmaxf(fabsf(rq.z), fabsf(rq.w)));
+            }
+        }
+        {
+            const float bm = block_max(err, sh);
+            if (tid == 0) pmax[blockIdx.x] = bm;
+        }
+        tot = grid_sum(grid, psumB, acc, sh, &shd);
+        {
+            const float e = final_max(pmax, gridDim.x, sh);
+            if (tid == 0) shf = e;
+            __syncthreads();
+            gmax = shf;
+            __syncthreads();
+        }
+        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+        const float zr = (float)tot;
+        if (with_err) {
+            const float tol = a.params->tolerance[a.which];
+            if (a.max_iterations == it || gmax < tol) {
+                max_error = gmax;
+                num_iterations = it;
+                break;
+            }
+        }
+        beta = guarded_div(zr, sigma);
+        sigma = zr;
+    }
+    if (sharded) {
+        float *const peer_p_lo = cm_.peer_p[a.which][0], *const peer_p_hi = cm_.peer_p[a.which][1];
+        for (int li = blockIdx.x; li < nact; li += gridDim.x) {
+            const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
+            if (c.tz == tz_first && peer_p_lo) st4(peer_p_lo + c.i + push, ld4(a.p + c.i));
+            if (c.tz == tz_last && peer_p_hi) {
+                const int i = c.i + (PCG_TZ - 1) * g.sz;
+                st4(peer_p_hi + i - push, ld4(a.p + i));
+            }
+        }
+        grid.sync();
+        double dummy = 0.0;
+        float dmax = 0.0f;
+        comm_allreduce(cm_, ++seq, dummy, dmax, sh_csum, sh_cmax, &sh_dead);
+        if (blockIdx.x == 0 && tid == 0) *cm_.seq = seq;
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        a.scal->alpha = alpha;
+        a.scal->beta = beta;
+        a.scal->sigma = sigma;
+        a.scal->max_error = max_error;
+        a.scal->num_iterations = num_iterations;
+        a.scal->done = sh_dead ? -1 : 1;
+    }
+}
+
 // deterministic compaction of the active tiles (ascending tile id) by one block
 __global__ void __launch_bounds__(1024) pcg_compact_tiles_kernel(const uint8_t *__restrict__ tile_active, int tile_lo, int ntiles,
                                                                  int *__restrict__ tile_list, int *__restrict__ num_active) {
@@ -898,6 +1181,32 @@ void PressureField::read_last_solve(cudaStream_t stream, float *max_error, int *
     *iterations = h.num_iterations;
 }
 
+namespace {
+// 3-D tensor maps (x fastest).  The encoder lives in libcuda; it is fetched through the runtime so that libblubcore.so
+// does not link against the driver library.
+bool encode_map(PFN_cuTensorMapEncodeTiled encode, CUtensorMap *map, CUtensorMapDataType type, size_t elem, void *base, const GridDim &g, unsigned bx,
+                unsigned by, unsigned bz) {
+    const cuuint64_t dims[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)g.nz};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.nx * elem, (cuuint64_t)g.nx * g.ny * elem};
+    const cuuint32_t box[3] = {bx, by, bz}, estr[3] = {1, 1, 1};
+    return encode(map, type, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool make_tma_maps(const GridDim &g, float *r, float *s0, float *s1, uint8_t *codes, PcgTmaMaps &m) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    return encode_map(encode, &m.r, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, r, g, TMA_BX, TMA_BY, TMA_BZ) &&
+           encode_map(encode, &m.s0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, s0, g, TMA_BX, TMA_BY, TMA_BZ) &&
+           encode_map(encode, &m.s1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, s1, g, TMA_BX, TMA_BY, TMA_BZ) &&
+           encode_map(encode, &m.codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, codes, g, TMA_CX, TMA_BY, TMA_BZ);
+}
+} // namespace
+
 PressureSolver::PressureSolver(const GridDim &grid, void *external_residual) : grid_(grid) {
     if (external_residual) residual_.place(grid, external_residual);
     else residual_.alloc(grid);
@@ -922,6 +1231,18 @@ PressureSolver::PressureSolver(const GridDim &grid, void *external_residual) : g
     if (persistent_blocks_ > 2048) persistent_blocks_ = 2048;
     const char *env = std::getenv("BLUB_PCG");
     if (env && std::string(env) == "multikernel") persistent_blocks_ = 0;
+    // TMA-tiled variant: 128-cell-wide tiles, tensor maps over r, both s buffers and the codes
+    tma_blocks_ = 0;
+    if (persistent_blocks_ > 0 && grid.nx % 128 == 0 && !(env && std::string(env) == "registers")) {
+        tma_maps_ = new PcgTmaMaps();
+        if (make_tma_maps(grid, residual_.ptr, search_.ptr, aux_.ptr, codes_.ptr, *static_cast<PcgTmaMaps *>(tma_maps_))) {
+            BLUB_CUDA_CHECK(cudaFuncSetAttribute(pcg_solve_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+            int per = 0;
+            BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_tma_kernel, PCG_THREADS, TMA_SMEM_BYTES));
+            tma_blocks_ = sms * per;
+        }
+    }
+    use_tma = tma_blocks_ > 0 && env && std::string(env) == "tma";
 }
 
 PressureSolver::~PressureSolver() {
@@ -929,6 +1250,7 @@ PressureSolver::~PressureSolver() {
     if (partials_) cudaFree(partials_);
     if (tile_active_) cudaFree(tile_active_);
     if (tile_list_) cudaFree(tile_list_);
+    delete static_cast<PcgTmaMaps *>(tma_maps_);
 }
 
 void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which, const int8_t *marker, const StepParams *dparams,
@@ -964,6 +1286,13 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
         args.p = p; args.r = r; args.s0 = s; args.s1 = aux_.ptr; args.scal = scal; args.partials = partials_;
         args.params = dparams; args.which = which; args.max_iterations = max_it; args.check_frequency = freq;
         args.comm = comm;
+        if (use_tma && tma_blocks_ > 0) {
+            int nblocks = tma_blocks_ < t.ntiles ? tma_blocks_ : t.ntiles;
+            void *kargs[] = {&args, tma_maps_};
+            BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_tma_kernel, dim3(nblocks), t.block(), kargs, TMA_SMEM_BYTES, stream));
+            g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+            return;
+        }
         int nblocks = persistent_blocks_ < t.ntiles ? persistent_blocks_ : t.ntiles;
         void *kargs[] = {&args};
         BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_persistent_kernel, dim3(nblocks), t.block(), kargs, 0, stream));

@@ -355,7 +355,9 @@ class HybridFluid:
         return [float(x) for x in ms]
 
     def set_solver_path(self, persistent):
-        _check(self.L.blub_fluid_set_solver_path(self.h, 1 if persistent else 0))
+        """True / 1: persistent cooperative PCG (default); False / 0: three kernels per iteration; 2 or "tma": TMA-staged tiles."""
+        mode = 2 if persistent in (2, "tma") else (1 if persistent else 0)
+        _check(self.L.blub_fluid_set_solver_path(self.h, mode))
 
     def set_graph_replay(self, enabled):
         _check(self.L.blub_fluid_set_graph_replay(self.h, 1 if enabled else 0))

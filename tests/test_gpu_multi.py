@@ -34,11 +34,11 @@ def local_view(glob, k, nz_owned, fill=0):
     return slab.local_view(glob, k, glob.shape[0] // nz_owned, fill)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_sharded_pcg_matches_single_gpu(world):
+@pytest.mark.parametrize("world,nx,tma", [(2, 64, False), (4, 64, False), (2, 128, True)])
+def test_sharded_pcg_matches_single_gpu(world, nx, tma):
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    nx, ny, nz_owned = 64, 48, 16
+    ny, nz_owned = 48, 16
     NZ = world * nz_owned
     rng = np.random.default_rng(world)
     m = np.full((NZ, ny, nx), O.AIR, dtype=np.int8)
@@ -52,6 +52,8 @@ def test_sharded_pcg_matches_single_gpu(world):
     ref.upload_grid(F.TAP_MARKER, m)
     slabs = make_slabs(world, nx, ny, nz_owned)
     for k, s in enumerate(slabs):
+        if tma:
+            s.set_solver_path("tma")
         s.set_solver_config(0, 1e-3, 64, 4)
         s.upload_grid(F.TAP_MARKER, local_view(m, k, nz_owned))
     for rep in range(2):  # second solve: warm start through the pushed ghost planes of p

@@ -342,3 +342,37 @@ def test_pcg_paths_agree_on_nonsquare_grid():
         gpu.solve_only(0, DT)
         assert gpu.last_solve(0)[1] == 20
         grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), f"pressure persistent={persistent}", rel=2e-3, abs_=1e-5)
+
+
+@pytest.mark.parametrize("max_it,freq,tol", [(32, 4, 0.0), (9, 2, 0.0), (128, 4, 1e-3)])
+def test_tma_tiled_pcg_matches_oracle(max_it, freq, tol):
+    """The TMA-staged persistent solver (tensor-map box loads, nx % 128 == 0) against the oracle and the register path."""
+    nx, ny, nz = 128, 40, 24
+    rng = np.random.default_rng(21)
+    m = np.full((nz, ny, nx), O.AIR, dtype=np.int8)
+    m[rng.random((nz, ny, nx)) < 0.8] = O.FLUID
+    m[rng.random((nz, ny, nx)) < 0.04] = O.SOLID
+    m[0], m[-1], m[:, 0], m[:, -1], m[:, :, 0], m[:, :, -1] = 0, 0, 0, 0, 0, 0
+    b = rng.uniform(-1, 1, (nz, ny, nx)).astype(np.float32)
+    orc = O.OracleFluid(nx, ny, nz, 8)
+    orc.set_solver_config(0, tol, max_it, freq)
+    orc.grid(O.ARR_MARKER)[:] = m
+    orc.grid(O.ARR_RESIDUAL)[:] = b
+    orc.solve(0, DT)
+    results = {}
+    for path in ("tma", True):
+        gpu = blub_b200.HybridFluid(nx, ny, nz, 8)
+        gpu.set_solver_path(path)
+        gpu.set_solver_config(0, tol, max_it, freq)
+        gpu.upload_grid(F.TAP_MARKER, m)
+        gpu.upload_grid(F.TAP_RESIDUAL, b)
+        for rep in range(2):  # the second solve warm-starts (and re-arms the mbarrier phases)
+            gpu.upload_grid(F.TAP_RESIDUAL, b)
+            gpu.solve_only(0, DT)
+            if rep == 0:
+                e, it = gpu.last_solve(0)
+                assert abs(it - orc.last_solve(0)[1]) <= (0 if tol == 0.0 else freq), (path, it, orc.last_solve(0))
+                grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), f"pressure path={path}", rel=3e-3, abs_=1e-4)
+        results[path] = gpu.download_grid(F.TAP_P_VEL)
+        assert gpu.last_solve(0)[0] >= 0.0
+    grid_close(results[True], results["tma"], "tma vs register path", rel=2e-3, abs_=1e-4)
