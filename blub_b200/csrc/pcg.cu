@@ -837,6 +837,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// r and s are written with ordinary (generic-proxy) stores and later read by TMA (async proxy): every writer orders its
+// global stores before later async-proxy accesses with this fence, then the grid barrier makes them visible device-wide.
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
                  "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
@@ -917,6 +920,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_tma_kernel(const __g
             p0 = pp;
         }
     }
+    fence_proxy_async_global();
     double tot = grid_sum(grid, psumB, acc, sh, &shd);
     float gmax = 0.0f;
     if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
@@ -941,6 +945,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_tma_kernel(const __g
             const int x0 = tx * 128, y0 = ty * 8, z0 = tz * PCG_TZ;
             __syncthreads(); // every thread is done with the previous tile's boxes
             if (tid == 0) {
+                fence_proxy_async_global();
                 fence_proxy_async(); // generic-proxy reads of the boxes above happen-before the async writes below
                 mbar_arrive_expect_tx(&bar, 2 * TMA_F32_BYTES + TMA_U8_BYTES);
                 tma_load_3d(shR, &maps.r, x0 - 4, y0 - 1, z0 - 1, &bar);
@@ -977,6 +982,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_tma_kernel(const __g
                 if (sharded && k == PCG_TZ - 1 && c.tz == tz_last) st4(s_out + i + g.sz, zp);
             }
         }
+        fence_proxy_async_global();
         tot = grid_sum(grid, psumA, acc, sh, &shd);
         if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
         alpha = guarded_div(sigma, (float)tot);
@@ -990,6 +996,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_tma_kernel(const __g
             const int tile = c.tile, tx = tile % t.tiles_x, rest = tile / t.tiles_x, ty = rest % t.tiles_y, tz = rest / t.tiles_y;
             __syncthreads();
             if (tid == 0) {
+                fence_proxy_async_global();
                 fence_proxy_async();
                 mbar_arrive_expect_tx(&bar, TMA_F32_BYTES);
                 tma_load_3d(shS, map_out, tx * 128 - 4, ty * 8 - 1, tz * PCG_TZ - 1, &bar);
@@ -1029,6 +1036,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_tma_kernel(const __g
                 err = fmaxf(fmaxf(err, fmaxf(fabsf(rq.x), fabsf(rq.y))), fmaxf(fabsf(rq.z), fabsf(rq.w)));
             }
         }
+        fence_proxy_async_global();
         {
             const float bm = block_max(err, sh);
             if (tid == 0) pmax[blockIdx.x] = bm;

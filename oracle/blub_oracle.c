@@ -26,6 +26,11 @@
  *                      transfer_gather_velocity.comp:61, density_projection_gather_error.comp:69);
  *                      0 = no cap [default]
  *   binning_mode   0 = fixed stable counting sort [default], 1 = as written (off-by-one, unguarded)
+ *   reduce_mode    0 = every partial of the first reduce level is summed [default]
+ *                  1 = as written: the final pass reads N / 16384 (FLOOR, pressure_solver.rs:571) partials although
+ *                      ceil(N / 16384) groups wrote one (pressure_init.comp:27-30), so the last group's partial is dropped
+ *                      whenever N is not a multiple of 16384.  Every shipped scene has N % 16384 == 0, where both modes
+ *                      coincide (B16).
  */
 #include <math.h>
 #include <stdint.h>
@@ -70,7 +75,7 @@ typedef struct OrcFluid {
     OrcSolverConfig cfg[2];
     OrcSolveResult last[2];
     uint32_t rebin_frequency, step_counter;
-    int precond_mode, cap_p2g, cap_density, binning_mode;
+    int precond_mode, cap_p2g, cap_density, binning_mode, reduce_mode;
 } OrcFluid;
 
 /* ------------------------------------------------------------------ helpers */
@@ -216,6 +221,7 @@ void orc_set_rebin_frequency(OrcFluid *f, uint32_t fr) { f->rebin_frequency = fr
 void orc_set_quirks(OrcFluid *f, int precond_mode, int cap_p2g, int cap_density, int binning_mode) {
     f->precond_mode = precond_mode; f->cap_p2g = cap_p2g; f->cap_density = cap_density; f->binning_mode = binning_mode;
 }
+void orc_set_reduce_mode(OrcFluid *f, int mode) { f->reduce_mode = mode; }
 void orc_set_voxels(OrcFluid *f, const float *rgba) { memcpy(f->voxel, rgba, f->n * 16); }
 uint32_t orc_num_particles(const OrcFluid *f) { return f->num_particles; }
 uint32_t orc_step_counter(const OrcFluid *f) { return f->step_counter; }
@@ -424,7 +430,7 @@ static float reduce_all(OrcFluid *f, int is_max) {
 #pragma omp parallel for
         for (uint32_t g = 0; g < groups; ++g) dst[g] = reduce_group(src, remaining, g, groups, is_max);
         float *t = src; src = dst; dst = t;
-        remaining /= 16384;
+        remaining = f->reduce_mode == 1 ? remaining / 16384 : (size_t)groups; /* B16 */
     }
     float r = reduce_group(src, remaining, 0, 1, is_max);
     return r;

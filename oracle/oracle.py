@@ -67,6 +67,7 @@ def lib():
         L.orc_set_rebin_frequency.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_set_quirks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_set_voxels.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_reduce_mode.argtypes = [C.c_void_p, C.c_int]
         L.orc_num_particles.restype = C.c_uint32
         L.orc_num_particles.argtypes = [C.c_void_p]
         L.orc_step_counter.restype = C.c_uint32
@@ -132,6 +133,10 @@ class OracleFluid:
 
     def set_quirks(self, precond_mode=0, cap_p2g=0, cap_density=0, binning_mode=0):
         self.L.orc_set_quirks(self.h, precond_mode, cap_p2g, cap_density, binning_mode)
+
+    def set_reduce_mode(self, as_written):
+        """B16: True = drop the last first-level partial when N % 16384 != 0, as the reference's host code does."""
+        self.L.orc_set_reduce_mode(self.h, 1 if as_written else 0)
 
     def set_voxels(self, rgba):
         rgba = np.ascontiguousarray(rgba, dtype=np.float32).reshape(self.n, 4)
