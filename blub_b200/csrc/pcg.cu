@@ -588,20 +588,6 @@ __device__ __forceinline__ float snew1(const float *r, const float *s, const uin
     return precond_diag2(r[i], codes[i]) + beta * s[i];
 }
 
-// Software prefetch of the block's NEXT tile into L2 while the current one is being processed: the kernel is bound by
-// the latency of its global loads (long-scoreboard stalls, DRAM at ~60 %), not by any throughput limit.  One 128-byte line
-// per 8 lanes (8 quads x 16 B); interior planes only -- the halo rows / planes belong to neighbouring tiles.
-__device__ __forceinline__ void prefetch_tile(const GridDim &g, const TileCtx &c, const float *a0, const float *a1, const float *a2) {
-    if (!c.valid || (threadIdx.x & 7) != 0) return;
-#pragma unroll
-    for (int k = 0; k < PCG_TZ; ++k) {
-        const int i = c.i + k * g.sz;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + i));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a1 + i));
-        if (a2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a2 + i));
-    }
-}
-
 // every thread of every block returns the same value
 __device__ __forceinline__ double grid_sum(cooperative_groups::grid_group &grid, float *partials, float acc, float *sh, double *shd) {
     const float bs = block_sum(acc, sh);
@@ -687,7 +673,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
         acc = 0.0f;
         for (int li = blockIdx.x; li < nact; li += gridDim.x) {
             const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
-            if (li + (int)gridDim.x < nact) prefetch_tile(g, tile_ctx_id(g, t, a.tile_list[li + gridDim.x]), a.r, s_in, nullptr);
             int i = c.i;
             float4 cm = zero4(), c0 = zero4(), cp = zero4();
             uchar4 code0 = make_uchar4(0, 0, 0, 0);
@@ -728,7 +713,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
         float err = 0.0f;
         for (int li = blockIdx.x; li < nact; li += gridDim.x) {
             const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
-            if (li + (int)gridDim.x < nact) prefetch_tile(g, tile_ctx_id(g, t, a.tile_list[li + gridDim.x]), a.p, a.r, s_out);
             int i = c.i;
             float4 sm = zero4(), s0 = zero4(), sp = zero4();
             if (c.valid) { sm = ld4(s_out + i - g.sz); s0 = ld4(s_out + i); }

@@ -372,11 +372,12 @@ def test_tma_tiled_pcg_matches_oracle(max_it, freq, tol):
             if rep == 0:
                 e, it = gpu.last_solve(0)
                 assert abs(it - orc.last_solve(0)[1]) <= (0 if tol == 0.0 else freq), (path, it, orc.last_solve(0))
-                if tol == 0.0 or it == orc.last_solve(0)[1]:
+                if tol == 0.0:
                     grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), f"pressure path={path}", rel=3e-3, abs_=1e-4)
-                else:  # stopped one check later/earlier than the oracle: both are within the solver tolerance of the solution
-                    assert e < tol / DT
-                    grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), f"pressure path={path}", rel=5e-2, abs_=1e-3)
+                else:  # converged: the stopping iterate depends on the last bits; check the defining property instead
+                    pg = gpu.download_grid(F.TAP_P_VEL)
+                    res = np.where(m == O.FLUID, b, 0.0) - util.apply_A(m, pg)
+                    assert e < tol / DT and np.abs(res).max() <= 1.02 * tol / DT + 1e-4, (e, np.abs(res).max())
         results[path] = gpu.download_grid(F.TAP_P_VEL)
         assert gpu.last_solve(0)[0] >= 0.0
     grid_close(results[True], results["tma"], "tma vs register path", rel=2e-3, abs_=1e-4)

@@ -51,3 +51,17 @@ def sort_rows(p):
     p = np.asarray(p)
     key = np.lexsort((p[:, 2], p[:, 1], p[:, 0]))
     return p[key], key
+
+
+def apply_A(m, x):
+    """(A x) on FLUID cells of marker volume m (pressure.glsl:34-75), float64, via np.roll (border cells are never FLUID)."""
+    fl = m == O.FLUID
+    x = np.asarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    diag = np.zeros_like(x)
+    for ax in range(3):
+        for sh in (1, -1):
+            mm = np.roll(m, sh, axis=ax)
+            diag += (mm != O.SOLID)
+            out -= np.where(mm == O.FLUID, np.roll(x, sh, axis=ax), 0.0)
+    return np.where(fl, out + diag * x, 0.0)
