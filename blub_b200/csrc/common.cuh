@@ -53,6 +53,9 @@ struct GridDim {
     // [z_wall_lo + 1.001, z_wall_hi - 0.001].  Single GPU: 0 and nz-1 (transfer_set_boundary_marker.comp:14-16,
     // advect_particles.comp:137); interior ranks of a z-slab decomposition have no z wall (+-2^20).
     int z_wall_lo, z_wall_hi;
+    // z-slab ranks: after the density correction a particle may overhang its slab by at most half a cell (the halo sums
+    // cover that); single GPU: +-3e38 (no effect).
+    float z_keep_lo, z_keep_hi;
 };
 
 inline GridDim make_grid(int nx, int ny, int nz) {
@@ -63,6 +66,8 @@ inline GridDim make_grid(int nx, int ny, int nz) {
     g.pad = (((int64_t)nx * ny + 8) + 255) / 256 * 256;
     g.z_wall_lo = 0;
     g.z_wall_hi = nz - 1;
+    g.z_keep_lo = -3.0e38f;
+    g.z_keep_hi = 3.0e38f;
     return g;
 }
 

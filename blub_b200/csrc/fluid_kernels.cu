@@ -46,8 +46,13 @@ __global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepPa
                                                          int8_t *__restrict__ marker) {
     const uint32_t i = blockIdx.x * PT + threadIdx.x;
     if (i >= params->num_particles) return;
-    const float4 p = pos[i];
-    if (MARK) marker[lin(g, (int)p.x, (int)p.y, (int)p.z)] = (int8_t)CELL_FLUID;
+    float4 p = pos[i];
+    // memory safety for ANY input: the eight faces of every dual cell must exist (a simulated particle is always inside
+    // [1.001, dim - 1.001], so this only ever changes particles handed in from outside the domain)
+    p.x = fminf(fmaxf(p.x, 1.0f), (float)g.nx - 1.0f);
+    p.y = fminf(fmaxf(p.y, 1.0f), (float)g.ny - 1.0f);
+    p.z = fminf(fmaxf(p.z, 1.0f), (float)g.nz - 1.0f);
+    if (MARK) marker[lin(g, min((int)p.x, g.nx - 1), min((int)p.y, g.ny - 1), min((int)p.z, g.nz - 1))] = (int8_t)CELL_FLUID;
     const float4 rows[3] = {rowx[i], rowy[i], rowz[i]};
     float2 *const nw[3] = {nwx, nwy, nwz};
 #pragma unroll
@@ -463,7 +468,10 @@ __global__ void __launch_bounds__(PT) density_scatter_kernel(GridDim g, const St
                                                              const float4 *__restrict__ pos, float *__restrict__ density) {
     const uint32_t i = blockIdx.x * PT + threadIdx.x;
     if (i >= params->num_particles) return;
-    const float4 p = pos[i];
+    float4 p = pos[i];
+    p.x = fminf(fmaxf(p.x, 0.5f), (float)g.nx - 1.0f); // memory safety, see p2g_scatter_kernel
+    p.y = fminf(fmaxf(p.y, 0.5f), (float)g.ny - 1.0f);
+    p.z = fminf(fmaxf(p.z, 0.5f), (float)g.nz - 1.0f);
     const int dx = (int)(p.x - 0.5f), dy = (int)(p.y - 0.5f), dz = (int)(p.z - 0.5f);
     const float qx = (float)dx + 0.5f, qy = (float)dy + 0.5f, qz = (float)dz + 0.5f;
     const float wx[2] = {saturatef(1.0f - fabsf(qx - p.x)), saturatef(1.0f - fabsf(qx + 1.0f - p.x))};
@@ -538,6 +546,7 @@ __global__ void __launch_bounds__(PT) correct_particles_kernel(GridDim g, const 
 #pragma unroll
         for (int k = 0; k < 3; ++k) x1[k] = fminf(fmaxf(x0[k] + dir[k] * maxstep, lo[k]), hi[k]);
     }
+    x1[2] = fminf(fmaxf(x1[2], g.z_keep_lo), g.z_keep_hi); // slab ranks only (no-op on one GPU)
     pos[i] = make_float4(x1[0], x1[1], x1[2], p4.w);
 }
 

@@ -35,6 +35,8 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
     if (slab_world_ > 1) { // only the first / last rank has a z wall; local plane SLAB_HALO is global plane rank * owned_nz
         grid_.z_wall_lo = slab_rank_ == 0 ? SLAB_HALO : -(1 << 20);
         grid_.z_wall_hi = slab_rank_ == slab_world_ - 1 ? SLAB_HALO + (int)owned_nz - 1 : (1 << 20);
+        if (slab_rank_ > 0) grid_.z_keep_lo = (float)SLAB_HALO - 0.5f;
+        if (slab_rank_ < slab_world_ - 1) grid_.z_keep_hi = (float)(SLAB_HALO + owned_nz) + 0.499f;
     }
     const size_t pbytes = ((size_t)max_num_particles + 64) * sizeof(float4);
     for (int k = 0; k < 2; ++k) {

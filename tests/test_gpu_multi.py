@@ -34,7 +34,7 @@ def local_view(glob, k, nz_owned, fill=0):
     return slab.local_view(glob, k, glob.shape[0] // nz_owned, fill)
 
 
-@pytest.mark.parametrize("world,nx,tma", [(2, 64, False), (4, 64, False), (2, 128, True)])
+@pytest.mark.parametrize("world,nx,tma", [(2, 64, False), (4, 64, False), (2, 128, "tma"), (2, 128, "tma2")])
 def test_sharded_pcg_matches_single_gpu(world, nx, tma):
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -53,7 +53,7 @@ def test_sharded_pcg_matches_single_gpu(world, nx, tma):
     slabs = make_slabs(world, nx, ny, nz_owned)
     for k, s in enumerate(slabs):
         if tma:
-            s.set_solver_path("tma")
+            s.set_solver_path(tma)
         s.set_solver_config(0, 1e-3, 64, 4)
         s.upload_grid(F.TAP_MARKER, local_view(m, k, nz_owned))
     for rep in range(2):  # second solve: warm start through the pushed ghost planes of p

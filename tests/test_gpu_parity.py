@@ -360,7 +360,7 @@ def test_tma_tiled_pcg_matches_oracle(max_it, freq, tol):
     orc.grid(O.ARR_RESIDUAL)[:] = b
     orc.solve(0, DT)
     results = {}
-    for path in ("tma", True):
+    for path in ("tma", "tma2", True):
         gpu = blub_b200.HybridFluid(nx, ny, nz, 8)
         gpu.set_solver_path(path)
         gpu.set_solver_config(0, tol, max_it, freq)
@@ -380,4 +380,6 @@ def test_tma_tiled_pcg_matches_oracle(max_it, freq, tol):
                     assert e < tol / DT and np.abs(res).max() <= 1.02 * tol / DT + 1e-4, (e, np.abs(res).max())
         results[path] = gpu.download_grid(F.TAP_P_VEL)
         assert gpu.last_solve(0)[0] >= 0.0
-    grid_close(results[True], results["tma"], "tma vs register path", rel=2e-3, abs_=1e-4)
+    if tol == 0.0:  # same arithmetic per cell; only the per-block partial sums are grouped differently (148 vs 592 blocks)
+        grid_close(results[True], results["tma"], "tma vs register path", rel=2e-3, abs_=1e-4)
+        grid_close(results[True], results["tma2"], "tma2 vs register path", rel=2e-3, abs_=1e-4)
