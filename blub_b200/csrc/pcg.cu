@@ -4,19 +4,24 @@
 // shader/simulation/pressure_solver/.  Same recurrence, same iteration schedule (error checks at i % freq == 0 and
 // i == max, pressure_solver.rs:676-677), same epsilon guards (pressure_reduce.comp:73-80) -- but not the same pass
 // structure: the reference records 9 dispatches + 3 two-level reductions per iteration (313 dispatches per solve,
-// ~85 B/cell/iteration); here one iteration is three kernels
-//     prepare : marker -> 1-byte codes (diag, fluid) + tile activity; p, r, s <- 0 off-fluid   (once per solve)
-//     dot     : s.As                                       (pressure_apply_coeff.comp + reduce ALPHA)
-//     update  : p += a s, r -= a As, z.r and max|r| fused  (pressure_update_pressure_and_residual.comp + both
-//                                                           preconditioner passes + reduce BETA / MAX_ERROR)
-//     search  : s = z + b s                                (pressure_update_search.comp)
-// each ending in a deterministic last-block-done reduction, with the diagonal ("diag2") preconditioner evaluated on
-// the fly so that z is never stored.  Convergence is a device flag that turns the remaining launches into no-ops
-// (the reference zeroes its indirect-dispatch arguments instead, pressure_reduce.comp:89-92).
+// ~85 B/cell/iteration).  Here a solve is
+//     prepare  (once): marker -> 1-byte codes (diag, fluid) + tile activity; p, r, s <- 0 off-fluid ("zero invariant": the
+//              7-point stencil, the dot products and the maxima then need no masks at all)
+//     solve    ONE persistent cooperative kernel (pcg_solve_persistent_kernel): per iteration
+//                 phase A  s' = z + beta s fused with s'.A s'   (pressure_update_search.comp + pressure_apply_coeff.comp)
+//                 phase B  p += a s', r -= a A s', z.r, max|r|  (pressure_update_pressure_and_residual.comp + both
+//                          preconditioner passes + the BETA / MAX_ERROR reductions)
+//              with two grid barriers per iteration, redundant fixed-order fp64 reductions (deterministic), the diagonal
+//              ("diag2") preconditioner evaluated on the fly so that z is never stored, an immediate stop on convergence
+//              (the reference zeroes its indirect-dispatch arguments instead, pressure_reduce.comp:89-92), and -- for z-slab
+//              sharded fluids -- the halo exchange and the scalar all-reduce INSIDE the kernel (P2P stores, mailboxes).
+// Alternatives kept and tested: a three-kernel-per-iteration path (dot / update / search with last-block-done reductions;
+// used for precond_mode 1 and when cooperative launch is unavailable) and two TMA-staged forms of the persistent kernel
+// (tensor-map box loads into shared memory; bit-compatible, measured slower -- see DESIGN.md 3.1).
 //
 // Layout: four cells per thread along x (128-bit loads) marching 4 z-planes with the z-neighbours kept in registers and
 // the x-neighbours exchanged by warp shuffles; fp32 vectors, 1-byte cell codes, padded arrays (common.cuh); tiles without
-// any FLUID cell exit at once.  Because p, r and s are kept at exactly 0 off-fluid the 7-point stencil needs no masks.
+// any FLUID cell are never visited.
 #include <cooperative_groups.h>
 #include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cudaTypedefs.h>  // PFN_cuTensorMapEncodeTiled
