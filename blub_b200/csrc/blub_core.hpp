@@ -234,8 +234,15 @@ class HybridFluid {
         }
     };
     GraphSignature graph_signature_;
-    cudaGraphExec_t graph_exec_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    uint64_t graph_kernel_nodes_[2][2] = {{0, 0}, {0, 0}}; // kernels inside each graph (for blub_kernel_launch_count)
+    // key: [position buffer][binning step?][velocity-row buffer (slab migration)][halo receive buffer (slab exchanges)]
+    cudaGraphExec_t graph_exec_[2][2][2][2] = {};
+    uint64_t graph_kernel_nodes_[2][2][2][2] = {}; // kernels inside each graph (for blub_kernel_launch_count)
+    int row_parity_ = 0;                           // toggled by every slab migration (row_ <-> row_alt_)
+    struct GraphRolesAfter {
+        int cur, row_parity;
+        uint32_t exchanges;
+    };
+    GraphRolesAfter graph_roles_after_[2][2][2][2] = {};
     bool capturing_ = false;
 
     GridDim grid_;

@@ -87,7 +87,6 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
         BLUB_CUDA_CHECK(cudaMemset(mig_counters_, 0, 4 * sizeof(unsigned int)));
         BLUB_CUDA_CHECK(cudaMalloc(&slab_error_, sizeof(int)));
         BLUB_CUDA_CHECK(cudaMemset(slab_error_, 0, sizeof(int)));
-        use_graph = false; // the sharded step interleaves exchanges with the stages and is launched eagerly
     } else {
         solver_.reset(new PressureSolver(grid_));
         field_velocity_.reset(new PressureField(grid_, cfg));
@@ -102,11 +101,11 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
 }
 
 void HybridFluid::destroy_graphs() {
-    for (auto &row : graph_exec_)
-        for (auto &e : row) {
-            if (e) cudaGraphExecDestroy(e);
-            e = nullptr;
-        }
+    cudaGraphExec_t *e = &graph_exec_[0][0][0][0];
+    for (int k = 0; k < 16; ++k) {
+        if (e[k]) cudaGraphExecDestroy(e[k]);
+        e[k] = nullptr;
+    }
 }
 
 HybridFluid::~HybridFluid() {
@@ -460,10 +459,25 @@ void HybridFluid::step(double simulation_delta_seconds) {
     }
     const uint32_t rebin = dynamic_settings_.particle_rebinning_step_frequency;
     const bool binning = rebin != 0 && step_counter_ % rebin == 0 && num_particles_ > 0;
-    const int cur0 = cur_;
-    cudaGraphExec_t &exec = graph_exec_[cur0][binning ? 1 : 0];
+    // Host-side buffer roles that a captured step bakes in (and changes): the graph is keyed by them.
+    struct Roles {
+        int cur, row_parity;
+        uint32_t exchange_index, step_counter;
+        float4 *row[3], *row_alt[3];
+    };
+    auto save_roles = [&]() {
+        Roles r{cur_, row_parity_, slab_exchange_index_, step_counter_, {row_[0], row_[1], row_[2]}, {row_alt_[0], row_alt_[1], row_alt_[2]}};
+        return r;
+    };
+    auto restore_roles = [&](const Roles &r) {
+        cur_ = r.cur; row_parity_ = r.row_parity; slab_exchange_index_ = r.exchange_index; step_counter_ = r.step_counter;
+        for (int k = 0; k < 3; ++k) { row_[k] = r.row[k]; row_alt_[k] = r.row_alt[k]; }
+    };
+    const Roles before = save_roles();
+    const int kb = binning ? 1 : 0, kx = (int)(before.exchange_index & 1u);
+    cudaGraphExec_t &exec = graph_exec_[before.cur][kb][before.row_parity][kx];
+    uint64_t &nodes_in_graph = graph_kernel_nodes_[before.cur][kb][before.row_parity][kx];
     if (!exec) {
-        const uint32_t counter0 = step_counter_;
         const uint64_t launches0 = g_kernel_launches.load();
         cudaGraph_t graph = nullptr;
         capturing_ = true;
@@ -474,25 +488,30 @@ void HybridFluid::step(double simulation_delta_seconds) {
             cudaStreamEndCapture(stream_, &graph);
             if (graph) cudaGraphDestroy(graph);
             capturing_ = false;
-            cur_ = cur0;
-            step_counter_ = counter0;
+            restore_roles(before);
             throw;
         }
         capturing_ = false;
-        cur_ = cur0; // capture only recorded; replay below performs the step
-        step_counter_ = counter0;
-        const uint64_t nodes = g_kernel_launches.load() - launches0; // recorded, not launched
-        g_kernel_launches.fetch_sub(nodes);
-        graph_kernel_nodes_[cur0][binning ? 1 : 0] = nodes;
+        graph_roles_after_[before.cur][kb][before.row_parity][kx] = {cur_, row_parity_, slab_exchange_index_ - before.exchange_index};
+        restore_roles(before); // capture only recorded; the replay below performs the step
+        nodes_in_graph = g_kernel_launches.load() - launches0; // recorded, not launched
+        g_kernel_launches.fetch_sub(nodes_in_graph);
         BLUB_CUDA_CHECK(cudaStreamEndCapture(stream_, &graph));
         cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         BLUB_CUDA_CHECK(err);
     }
     BLUB_CUDA_CHECK(cudaGraphLaunch(exec, stream_));
-    g_kernel_launches.fetch_add(graph_kernel_nodes_[cur0][binning ? 1 : 0], std::memory_order_relaxed);
-    if (binning) cur_ = 1 - cur0;
-    step_counter_ += 1;
+    g_kernel_launches.fetch_add(nodes_in_graph, std::memory_order_relaxed);
+    // what the recorded stages did to the buffer roles
+    const GraphRolesAfter &after = graph_roles_after_[before.cur][kb][before.row_parity][kx];
+    cur_ = after.cur;
+    if (after.row_parity != before.row_parity) {
+        for (int k = 0; k < 3; ++k) std::swap(row_[k], row_alt_[k]);
+        row_parity_ = after.row_parity;
+    }
+    slab_exchange_index_ = before.exchange_index + after.exchanges;
+    step_counter_ = before.step_counter + 1;
     field_velocity_->enqueue_error_buffer_read(stream_, dt);
     field_density_->enqueue_error_buffer_read(stream_, dt);
 }

@@ -272,6 +272,7 @@ void HybridFluid::slab_migrate() {
     BLUB_LAUNCH(migrate_finish_kernel, 1, 32, 0, stream_, params_dev_, mig_counters_, counts, max_num_particles_, slab_error_);
     cur_ = 1 - cur_;
     for (int k = 0; k < 3; ++k) std::swap(row_[k], row_alt_[k]);
+    row_parity_ ^= 1;
 }
 
 } // namespace blub
