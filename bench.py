@@ -5,8 +5,9 @@
 
 A "step" is one HybridFluid::step (P2G, PCG solve, G2P/advection, density rhs, PCG solve, particle correction) over the
 synthetic 256^3 / 16,387,064-particle dam break that BASELINE.json's metric is quoted on.  N > 1 (torchrun, one rank per
-GPU): ONE simulation of N such scenes stacked along z, sharded into N z-slabs (weak scaling: per-GPU work fixed); `value` =
-slab-steps/s = N * steps/s, so that N = 1 is exactly the single-GPU number.  `--multi replicas` runs N independent scenes.
+GPU): ONE simulation on a 256 x 256 x 256N grid sharded into N z-slabs (weak scaling: per-GPU work fixed -- a z-uniform dam
+with the same 16.3 M particles per slab); `value` = slab-steps/s = N * steps/s.  The N = 1 line carries `scaling_reference`, the
+same per-slab scene on one GPU.  `--multi stacked` stacks N dam_256 cubes instead, `--multi replicas` runs N independent scenes.
 `--impl reference`: the reference (Rust + wgpu/Vulkan) cannot run on this image, so this arm times the CPU restatement of
 its algorithm (oracle/) on the host cores -- the only place besides cpu_baseline where bench.py executes oracle/.
 """
@@ -195,15 +196,9 @@ def run_reference(args):
 
         d, scale = sc["fluid"]["grid_dimension"], np.float32(sc["fluid"]["grid_to_world_scale"])
         f = O.OracleFluid(d["x"], d["y"], d["z"] * n, int(sc["fluid"]["max_num_particles"]) * n)
-        for k in range(n):
-            for cube in sc["fluid"]["fluid_cubes"]:
-                mn = [np.float32(cube["min"][c]) / scale for c in "xyz"]
-                mx = [np.float32(cube["max"][c]) / scale for c in "xyz"]
-                mn[2] += k * d["z"]
-                mx[2] = min(mx[2], d["z"] - 1) + k * d["z"]
-                f.add_fluid_cube(mn, mx)
+        f.add_fluid_cube([0.0, 0.0, 0.0], [d["x"] / 2.0, d["y"] / 4.0, float(d["z"] * n)])
         f.set_gravity_grid([np.float32(sc["gravity"][c]) / scale for c in "xyz"])
-        desc = f"{n} x ({desc}) stacked along z = {d['x']}x{d['y']}x{d['z'] * n} grid"
+        desc = f"{n} z-slabs of {d['x']}x{d['y']}x{d['z']} cells = {d['x']}x{d['y']}x{d['z'] * n} grid, z-uniform dam (x < {d['x'] // 2}, y < {d['y'] // 4})"
     # bounded sample: one CPU step of the 256^3 workload takes seconds, so time as many of the K requested steps as fit
     # into the budget (at least one) after at most one untimed step
     budget = float(os.environ.get("BLUB_REF_BUDGET_S", "150"))
@@ -239,8 +234,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-sharded-pcg", action="store_true")
-    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
-                    help="N > 1: one z-slab sharded simulation (default) or N independent replicas")
+    ap.add_argument("--no-scaling-reference", action="store_true")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "stacked", "replicas"],
+                    help="N > 1: one z-slab sharded simulation of a z-uniform dam (default, balanced), of N stacked dam_256 cubes, or N independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 2
@@ -271,7 +267,7 @@ def main():
 
     sc, desc = workload_desc(args.workload)
     dt = F.DT_120HZ
-    sharded_step = world > 1 and args.multi == "sharded"
+    sharded_step = world > 1 and args.multi in ("sharded", "stacked")
     if not sharded_step:
         fluid = blub_b200.HybridFluid.from_scene(scene_path(args.workload), device=local)
         npart = fluid.num_particles
@@ -288,18 +284,28 @@ def main():
         handles = slab.exchange_handles(fluid.ipc_export_window(), dist)
         own = fluid.slab_window()[0]
         fluid.attach_slab_peers([own if k == rank else F.ipc_open(handles[k], local) for k in range(world)])
-        for k in range(world):
-            for cube in sc["fluid"]["fluid_cubes"]:
-                mn = [cube["min"][c] / scale for c in "xyz"]
-                mx = [cube["max"][c] / scale for c in "xyz"]
-                mn[2] += k * d["z"]
-                mx[2] = min(mx[2], d["z"] - 1) + k * d["z"]
-                fluid.add_fluid_cube(mn, mx)
+        if args.multi == "sharded":
+            # balanced weak-scaling scene: the dam is uniform along z (x < 128, y < 64 cells, every plane), so the break runs in
+            # the x-y plane and no slab gains or loses fluid: per-GPU work really is fixed (16.3 M particles per slab, as in
+            # dam_256).  `--multi stacked` stacks N copies of the dam_256 cube instead; they drain towards z = 0 and unbalance.
+            zmax = float(d["z"] * world)
+            fluid.add_fluid_cube([0.0, 0.0, 0.0], [d["x"] / 2.0, d["y"] / 4.0, zmax])
+        else:
+            for k in range(world):
+                for cube in sc["fluid"]["fluid_cubes"]:
+                    mn = [cube["min"][c] / scale for c in "xyz"]
+                    mx = [cube["max"][c] / scale for c in "xyz"]
+                    mn[2] += k * d["z"]
+                    mx[2] = min(mx[2], d["z"] - 1) + k * d["z"]
+                    fluid.add_fluid_cube(mn, mx)
         fluid.set_gravity_grid([sc["gravity"][c] / scale for c in "xyz"])
         counts = [None] * world
         dist.all_gather_object(counts, fluid.num_particles)
         npart = sum(counts)
-        desc = f"{world} x ({desc}) stacked along z = {d['x']}x{d['y']}x{d['z'] * world} grid"
+        if args.multi == "sharded":
+            desc = f"{world} z-slabs of {d['x']}x{d['y']}x{d['z']} cells = {d['x']}x{d['y']}x{d['z'] * world} grid, z-uniform dam (x < {d['x'] // 2}, y < {d['y'] // 4})"
+        else:
+            desc = f"{world} x ({desc}) stacked along z = {d['x']}x{d['y']}x{d['z'] * world} grid"
         parallelism = f"one simulation on {world} z-slabs (P2P halo exchange + particle migration, in-kernel PCG exchange)"
     for _ in range(max(args.warmup, 3)):
         fluid.step(dt)
@@ -348,6 +354,19 @@ def main():
     sharded = None
     if world > 1 and not args.no_sharded_pcg:
         sharded = pcg_sharded(rank, world, local)
+    scaling_ref = None
+    if world == 1 and not args.no_scaling_reference:
+        d = sc["fluid"]["grid_dimension"]
+        g1 = blub_b200.HybridFluid(d["x"], d["y"], d["z"], sc["fluid"]["max_num_particles"], device=local)
+        g1.add_fluid_cube([0.0, 0.0, 0.0], [d["x"] / 2.0, d["y"] / 4.0, float(d["z"])])
+        g1.set_gravity_grid([sc["gravity"][c] / sc["fluid"]["grid_to_world_scale"] for c in "xyz"])
+        for _ in range(max(args.warmup, 3)):
+            g1.step(dt)
+        g1.synchronize()
+        ms1 = g1.time_steps(dt, args.steps)
+        scaling_ref = {"workload": f"z-uniform dam (x < {d['x'] // 2}, y < {d['y'] // 4}) on one {d['x']}x{d['y']}x{d['z']} grid: the per-slab scene of the N > 1 runs",
+                       "particles": g1.num_particles, "value": round(args.steps / (ms1 * 1e-3), 3), "unit": "steps/s"}
+        g1.close()
     roof = cpu = None
     if rank == 0 and not args.no_roofline:
         roof = pcg_roofline(local)
@@ -372,6 +391,8 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
         }
+        if scaling_ref is not None:
+            line["scaling_reference"] = scaling_ref
         if sharded is not None:
             line["pcg_sharded"] = sharded
         print(json.dumps(line), flush=True)
