@@ -211,7 +211,8 @@ class HybridFluid {
     void slab_layout(void *window, char *&halo0, size_t &halo_bytes, char *&part0, size_t &part_bytes, unsigned int *&counts) const;
     void slab_barrier();
     void slab_halo_exchange(const SlabHaloItem *items, int n_items);
-    void slab_migrate();
+    MigrateOut slab_migrate_targets();
+    void slab_migrate_finish();
     void set_device_particle_count(uint32_t n);
     bool add_fluid_cube_slab(const uint32_t mn[3], const uint32_t ext[3]);
     uint32_t seeded_global_ = 0;

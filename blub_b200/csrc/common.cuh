@@ -109,6 +109,21 @@ struct SlabComm {
     unsigned int *seq = nullptr;  // device counter of all-reduce rounds done so far (identical on every rank)
 };
 
+// A particle on its way to the neighbouring slab: 64 B.
+struct MigrantRecord {
+    float4 pos, rx, ry, rz;
+};
+// Where the advection kernel of a slab rank puts its results: stayers are compacted into the spare arrays, leavers go
+// straight into the neighbour's receive buffer (P2P stores), z re-based by -+zshift.  counters: [0] stay, [1] down, [2] up,
+// [3] overflow flag.
+struct MigrateOut {
+    float4 *pos, *rx, *ry, *rz;
+    MigrantRecord *peer_down, *peer_up;
+    unsigned int *counters;
+    float z_lo, z_hi, zshift;
+    unsigned int capacity;
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

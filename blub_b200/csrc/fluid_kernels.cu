@@ -342,11 +342,15 @@ __device__ __forceinline__ void trilerp3(const Corners &c, const float ix[3], co
 
 // advect_particles.comp:35-194.  Writes position + the three APIC rows, marks the new cell FLUID (:175-178); the
 // linked-list rebuild of :179-181 has no counterpart (the density pass scatters).
+// MIGRATE (z-slab ranks): instead of writing back in place, the kernel itself sorts its results -- stayers are compacted
+// into the spare arrays, particles that left the slab go straight to the neighbour (see MigrateOut) -- so that migration
+// costs one warp-aggregated atomic per warp instead of an extra pass over all particles.
+template <bool MIGRATE>
 __global__ void __launch_bounds__(PT) advect_kernel(GridDim g, const StepParams *__restrict__ params, float4 *__restrict__ pos,
                                                     float4 *__restrict__ rowx, float4 *__restrict__ rowy, float4 *__restrict__ rowz,
                                                     const float *__restrict__ ux, const float *__restrict__ uy,
                                                     const float *__restrict__ uz, const uint2 *__restrict__ vox,
-                                                    int8_t *__restrict__ marker) {
+                                                    int8_t *__restrict__ marker, MigrateOut mig) {
     const uint32_t i = blockIdx.x * PT + threadIdx.x;
     if (i >= params->num_particles) return;
     const float dt = params->dt;
@@ -456,10 +460,42 @@ __global__ void __launch_bounds__(PT) advect_kernel(GridDim g, const StepParams 
         }
     }
     marker[lin(g, clampi((int)x1[0], 0, g.nx - 1), clampi((int)x1[1], 0, g.ny - 1), clampi((int)x1[2], 0, g.nz - 1))] = (int8_t)CELL_FLUID;
-    pos[i] = make_float4(x1[0], x1[1], x1[2], p4.w);
-    rowx[i] = make_float4(cx[0], cx[1], cx[2], nv[0]); // :184-188 (B4: Jacobian columns stored as the rows)
-    rowy[i] = make_float4(cy[0], cy[1], cy[2], nv[1]);
-    rowz[i] = make_float4(cz[0], cz[1], cz[2], nv[2]);
+    const float4 out_pos = make_float4(x1[0], x1[1], x1[2], p4.w);
+    const float4 out_rx = make_float4(cx[0], cx[1], cx[2], nv[0]); // :184-188 (B4: Jacobian columns stored as the rows)
+    const float4 out_ry = make_float4(cy[0], cy[1], cy[2], nv[1]);
+    const float4 out_rz = make_float4(cz[0], cz[1], cz[2], nv[2]);
+    if (!MIGRATE) {
+        pos[i] = out_pos;
+        rowx[i] = out_rx;
+        rowy[i] = out_ry;
+        rowz[i] = out_rz;
+        return;
+    }
+    const int dest = (x1[2] < mig.z_lo && mig.peer_down) ? 1 : ((x1[2] >= mig.z_hi && mig.peer_up) ? 2 : 0);
+    const unsigned active = __activemask();
+    unsigned slot = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { // one atomic per destination per warp
+        const unsigned m = __ballot_sync(active, dest == d);
+        if (m == 0u) continue;
+        const int leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(mig.counters + d, (unsigned)__popc(m));
+        base = __shfl_sync(active, base, leader);
+        if (dest == d) slot = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+    }
+    if (dest == 0) {
+        mig.pos[slot] = out_pos;
+        mig.rx[slot] = out_rx;
+        mig.ry[slot] = out_ry;
+        mig.rz[slot] = out_rz;
+    } else if (slot < mig.capacity) {
+        MigrantRecord rec = {out_pos, out_rx, out_ry, out_rz};
+        rec.pos.z += dest == 1 ? mig.zshift : -mig.zshift; // re-base into the neighbour's local frame
+        (dest == 1 ? mig.peer_down : mig.peer_up)[slot] = rec; // P2P store over NVLink
+    } else {
+        mig.counters[3] = 1u; // cannot happen with a CFL-limited flow; never overrun the neighbour's buffer
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ density projection
@@ -696,7 +732,13 @@ void launch_clear_marker(cudaStream_t st, const GridDim &g, int8_t *marker) {
 void launch_advect(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos, float4 *const row[3],
                    float *const u[3], const uint2 *vox, int8_t *marker) {
     if (np_upper == 0) return;
-    BLUB_LAUNCH(advect_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2], vox, marker);
+    BLUB_LAUNCH(advect_kernel<false>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2], vox, marker, MigrateOut{});
+}
+
+void launch_advect_migrate(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos, float4 *const row[3],
+                           float *const u[3], const uint2 *vox, int8_t *marker, const MigrateOut &mig) {
+    if (np_upper == 0) return;
+    BLUB_LAUNCH(advect_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2], vox, marker, mig);
 }
 
 void launch_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, const uint2 *vox, const MarkerFlags &flags) {

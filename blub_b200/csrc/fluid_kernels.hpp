@@ -29,6 +29,8 @@ void launch_extrapolate(cudaStream_t st, const GridDim &g, const int8_t *marker,
 void launch_clear_marker(cudaStream_t st, const GridDim &g, int8_t *marker);
 void launch_advect(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos, float4 *const row[3],
                    float *const u[3], const uint2 *vox, int8_t *marker);
+void launch_advect_migrate(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos, float4 *const row[3],
+                           float *const u[3], const uint2 *vox, int8_t *marker, const MigrateOut &mig);
 void launch_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, const uint2 *vox, const MarkerFlags &flags);
 void launch_density_rhs(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos,
                         const int8_t *marker, float *density, float *rhs);

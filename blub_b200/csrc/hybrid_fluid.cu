@@ -391,9 +391,11 @@ void HybridFluid::run_stage(int stage, float dt) {
         launch_clear_marker(stream_, grid_, marker_.ptr);
         break;
     case 7: // advect particles (:917-921)
-        launch_advect(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, voxels_, marker_.ptr);
-        if (shard) {
-            slab_migrate();
+        if (!shard) {
+            launch_advect(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, voxels_, marker_.ptr);
+        } else {
+            launch_advect_migrate(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, voxels_, marker_.ptr, slab_migrate_targets());
+            slab_migrate_finish();
             const SlabHaloItem items[1] = {{marker_.ptr, 1, 1}};
             slab_halo_exchange(items, 1); // X3
         }

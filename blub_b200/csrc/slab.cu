@@ -6,7 +6,8 @@
 //                                  each face (both ranks send their partials of the same 4 global planes and add)
 //   PCG                            boundary planes of r / p pushed from inside the persistent kernel (pcg.cu)
 //   X2  after extrapolation        COPY of the first two owned planes of u into the neighbour's ghost planes
-//   MIG after advection            particles that left the slab move to the neighbour (positions re-based by +-zs)
+//   MIG inside the advection       the advection kernel itself compacts the stayers and writes the leavers into the
+//                                  neighbour's buffer (positions re-based by +-zs); counts + arrivals are appended afterwards
 //   X3  after advection            MAX of the markers
 //   X4  after the density scatter  SUM of the density accumulator
 //   X5  after extrapolation #2     COPY of the displacement field planes
@@ -58,50 +59,6 @@ __global__ void __launch_bounds__(256) halo_add_kernel(float *__restrict__ dst, 
 __global__ void __launch_bounds__(256) halo_max_kernel(int8_t *__restrict__ dst, const int8_t *__restrict__ src, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i < n) dst[i] = max(dst[i], src[i]);
-}
-
-struct MigrantRecord { // what travels: 64 B per particle
-    float4 pos, rx, ry, rz;
-};
-
-// counters: [0] stay, [1] down, [2] up, [3] overflow flag
-__global__ void __launch_bounds__(256) migrate_classify_kernel(const StepParams *__restrict__ params, const float4 *__restrict__ pos,
-                                                               const float4 *__restrict__ rx, const float4 *__restrict__ ry,
-                                                               const float4 *__restrict__ rz, float4 *__restrict__ opos, float4 *__restrict__ orx,
-                                                               float4 *__restrict__ ory, float4 *__restrict__ orz, MigrantRecord *peer_down,
-                                                               MigrantRecord *peer_up, unsigned int *counters, float z_lo, float z_hi, float zshift,
-                                                               unsigned int capacity) {
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= params->num_particles) return;
-    float4 p = pos[i];
-    const int dest = (p.z < z_lo && peer_down) ? 1 : ((p.z >= z_hi && peer_up) ? 2 : 0);
-    // warp-aggregated slot claim: one atomic per destination per warp
-    const unsigned active = __activemask();
-    unsigned slot = 0;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        const unsigned m = __ballot_sync(active, dest == d);
-        if (m == 0u) continue;
-        const int leader = __ffs(m) - 1;
-        unsigned base = 0;
-        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counters + d, (unsigned)__popc(m));
-        base = __shfl_sync(active, base, leader);
-        if (dest == d) slot = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
-    }
-    if (dest == 0) {
-        opos[slot] = p;
-        orx[slot] = rx[i];
-        ory[slot] = ry[i];
-        orz[slot] = rz[i];
-    } else {
-        if (slot >= capacity) { // cannot happen with a CFL-limited flow; never overrun the neighbour's buffer
-            counters[3] = 1u;
-            return;
-        }
-        p.z += dest == 1 ? zshift : -zshift; // re-base into the neighbour's local frame
-        MigrantRecord rec = {p, rx[i], ry[i], rz[i]};
-        (dest == 1 ? peer_down : peer_up)[slot] = rec; // P2P store over NVLink
-    }
 }
 
 // publish how many particles were sent (into the neighbours' windows) and start the new local count
@@ -240,15 +197,42 @@ void HybridFluid::slab_halo_exchange(const SlabHaloItem *items, int n_items) {
     }
 }
 
-// particles that crossed a slab face move to the neighbour; the survivors are compacted into the spare arrays
-void HybridFluid::slab_migrate() {
+// Migration.  The advection kernel of a slab rank already sorted its results (advect_kernel<true>): stayers compacted into
+// the spare arrays, leavers written into the neighbours' receive buffers.  What is left: publish the counts, wait for
+// everybody, append the arrivals, swap the buffers.
+MigrateOut HybridFluid::slab_migrate_targets() {
+    const SlabComm &c = solver_->comm;
+    char *halo0, *part0;
+    size_t hb, pb;
+    unsigned int *counts;
+    slab_layout(window_, halo0, hb, part0, pb, counts);
+    MigrateOut m{};
+    m.pos = pos_[1 - cur_];
+    m.rx = row_alt_[0]; m.ry = row_alt_[1]; m.rz = row_alt_[2];
+    for (int side = 0; side < 2; ++side) {
+        if (!slab_peer_window_[side]) continue;
+        char *ph0, *pp0;
+        size_t phb, ppb;
+        unsigned int *pc;
+        slab_layout(slab_peer_window_[side], ph0, phb, pp0, ppb, pc);
+        MigrantRecord *buf = reinterpret_cast<MigrantRecord *>(pp0 + (size_t)(1 - side) * ppb); // lands in its area for the opposite face
+        if (side == 0) m.peer_down = buf; else m.peer_up = buf;
+    }
+    m.counters = mig_counters_;
+    m.z_lo = (float)SLAB_HALO;
+    m.z_hi = (float)(SLAB_HALO + c.owned_nz);
+    m.zshift = (float)c.owned_nz;
+    m.capacity = slab_migrant_capacity();
+    return m;
+}
+
+void HybridFluid::slab_migrate_finish() {
     const SlabComm &c = solver_->comm;
     if (c.world <= 1) return;
     char *halo0, *part0;
     size_t hb, pb;
     unsigned int *counts;
     slab_layout(window_, halo0, hb, part0, pb, counts);
-    MigrantRecord *peer_buf[2] = {nullptr, nullptr};
     unsigned int *peer_cnt[2] = {nullptr, nullptr};
     for (int side = 0; side < 2; ++side) {
         if (!slab_peer_window_[side]) continue;
@@ -256,15 +240,10 @@ void HybridFluid::slab_migrate() {
         size_t phb, ppb;
         unsigned int *pc;
         slab_layout(slab_peer_window_[side], ph0, phb, pp0, ppb, pc);
-        peer_buf[side] = reinterpret_cast<MigrantRecord *>(pp0 + (size_t)(1 - side) * ppb); // lands in its area for the opposite face
         peer_cnt[side] = pc + (1 - side);
     }
     const uint32_t cap = slab_migrant_capacity();
-    const uint32_t np_upper = max_num_particles_;
     float4 *opos = pos_[1 - cur_];
-    BLUB_LAUNCH(migrate_classify_kernel, blocks_for(np_upper, 256), 256, 0, stream_, params_dev_, pos_[cur_], row_[0], row_[1], row_[2], opos,
-                row_alt_[0], row_alt_[1], row_alt_[2], peer_buf[0], peer_buf[1], mig_counters_, (float)SLAB_HALO, (float)(SLAB_HALO + c.owned_nz),
-                (float)c.owned_nz, cap);
     BLUB_LAUNCH(migrate_publish_kernel, 1, 32, 0, stream_, mig_counters_, peer_cnt[0], peer_cnt[1], cap);
     slab_barrier();
     BLUB_LAUNCH(migrate_append_kernel, blocks_for(2 * (int64_t)cap, 256), 256, 0, stream_, reinterpret_cast<const MigrantRecord *>(part0),

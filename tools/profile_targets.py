@@ -22,6 +22,39 @@ if mode == "step":
         f.step(F.DT_120HZ)
     f.synchronize()
     print("launches", blub_b200.kernel_launch_count())
+elif mode == "stages_sharded":
+    # per-stage times of the sharded step: `world` slabs in one process (peer access), one host thread per slab
+    import threading
+
+    world = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    from oracle.oracle import STAGES
+    n, cap = 256, 33000000
+    for a in range(world):
+        for b in range(world):
+            if a != b:
+                F.enable_peer_access(a, b)
+    slabs = [blub_b200.HybridFluid.create_slab(n, n, n, cap, rank=k, world=world, device=k) for k in range(world)]
+    wins = [s.slab_window()[0] for s in slabs]
+    for s in slabs:
+        s.attach_slab_peers(wins)
+        s.add_fluid_cube([0.0, 0.0, 0.0], [n / 2.0, n / 4.0, float(n * world)])
+        s.set_gravity_grid([0.0, -1962.0, 0.0])
+    for _ in range(3):
+        for s in slabs:
+            s.step(F.DT_120HZ)
+    for s in slabs:
+        s.synchronize()
+    reps, acc = 5, [np.zeros(14) for _ in slabs]
+    for _ in range(reps):
+        def run(k):
+            acc[k] += np.array(slabs[k].step_timed(F.DT_120HZ))
+        th = [threading.Thread(target=run, args=(k,)) for k in range(world)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+    for i, name in enumerate(STAGES):
+        print(f"{name:24s} " + "  ".join(f"{a[i] / reps:8.3f}" for a in acc) + " ms")
+    print(f"{'total':24s} " + "  ".join(f"{a.sum() / reps:8.3f}" for a in acc) + " ms (eager, per rank)")
+    print("errors", [s.slab_error() for s in slabs], "particles", [s.num_particles for s in slabs])
 elif mode == "stages":
     scene = sys.argv[2] if len(sys.argv) > 2 else "dam_256"
     f = blub_b200.HybridFluid.from_scene(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".json"))
