@@ -1,0 +1,42 @@
+"""Generates tests/golden/dam_small_golden.npz from the CPU oracle (the reference itself cannot run here, and ships no vectors).
+
+These are REGRESSION pins, not reference outputs: they freeze what the oracle (and therefore the parity target of the CUDA path)
+produces today for a small dam break, so that a later change to oracle/ cannot silently move the goal posts.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import oracle as O  # noqa: E402
+
+
+def run():
+    f = O.fluid_from_scene(O.load_scene(os.path.join(HERE, "scenes", "dam_small.json")))
+    f.set_rebin_frequency(0)
+    seed = f.particles()[:, :3].copy()
+    f.step_stages(O.DT_120HZ, 0, 2)
+    rhs1 = f.grid(O.ARR_RESIDUAL).copy()
+    marker1 = f.grid(O.ARR_MARKER).copy()
+    f.step_stages(O.DT_120HZ, 2, 14)
+    stats = [f.last_solve(0), f.last_solve(1)]
+    pos1 = f.particles()[:, :3].copy()
+    for _ in range(2):
+        f.step(O.DT_120HZ)
+    pos3 = f.particles()[:, :3].copy()
+    return dict(
+        seed_first=seed[:64], seed_sum=seed.astype(np.float64).sum(0),
+        marker_counts=np.array([(marker1 == v).sum() for v in (-1, 0, 1)]),
+        rhs1_sum=np.float64(rhs1[marker1 == 1].astype(np.float64).sum()), rhs1_absmax=np.float64(np.abs(rhs1[marker1 == 1]).max()),
+        solver_iterations=np.array([stats[0][1], stats[1][1]]), solver_errors=np.array([stats[0][0], stats[1][0]]),
+        pos1_sample=pos1[::16], pos1_sum=pos1.astype(np.float64).sum(0), pos3_sample=pos3[::16], pos3_sum=pos3.astype(np.float64).sum(0),
+    )
+
+
+if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "dam_small_golden.npz"), **run())
+    print("wrote dam_small_golden.npz")
