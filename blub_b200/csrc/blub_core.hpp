@@ -127,6 +127,7 @@ class PressureSolver {
   public:
     bool use_persistent = true;      // one cooperative launch per solve (diag2 preconditioner); false = three kernels per iteration
     bool use_tma = false;            // persistent solver with TMA-staged tiles (nx % 128 == 0); BLUB_PCG=tma or blub_fluid_set_solver_path(f, 2)
+    bool use_dense = false;          // persistent solver without the per-thread sparsity skip (comparison only); set_solver_path(f, 4)
     bool use_tma2 = false;           // double-buffered TMA solver, one 512-thread block per SM; BLUB_PCG=tma2 or set_solver_path(f, 3)
     bool tma_available() const { return tma_blocks_ > 0; }
     bool tma2_available() const { return tma2_blocks_ > 0; }

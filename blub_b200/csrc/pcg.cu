@@ -13,8 +13,9 @@
 //                          preconditioner passes + the BETA / MAX_ERROR reductions)
 //              with two grid barriers per iteration, redundant fixed-order fp64 reductions (deterministic), the diagonal
 //              ("diag2") preconditioner evaluated on the fly so that z is never stored, an immediate stop on convergence
-//              (the reference zeroes its indirect-dispatch arguments instead, pressure_reduce.comp:89-92), and -- for z-slab
-//              sharded fluids -- the halo exchange and the scalar all-reduce INSIDE the kernel (P2P stores, mailboxes).
+//              (the reference zeroes its indirect-dispatch arguments instead, pressure_reduce.comp:89-92), per-thread
+//              skipping of fluid-free quads in sparsely filled tiles, and -- for z-slab sharded fluids -- the halo
+//              exchange and the scalar all-reduce INSIDE the kernel (P2P stores, mailboxes).
 // Alternatives kept and tested: a three-kernel-per-iteration path (dot / update / search with last-block-done reductions;
 // used for precond_mode 1 and when cooperative launch is unavailable) and two TMA-staged forms of the persistent kernel
 // (tensor-map box loads into shared memory; bit-compatible, measured slower -- see DESIGN.md 3.1).
@@ -47,6 +48,7 @@ constexpr float PCG_EPSILON = 1e-10f; // pressure_reduce.comp:33
 // Then "subtract the FLUID neighbours" (pressure.glsl:56-73) is "subtract all six neighbours", so the stencil needs no
 // neighbour masks:  (A x)_i = diag_i x_i - sum_6 x_nbr  on fluid cells.
 constexpr unsigned CODE_FLUID = 8u;
+constexpr int TILE_DENSE_BIT = 1 << 30; // in tile_list_flagged: the tile is at least 3/4 full
 
 // Block = (bx, by) threads, bx * by = 256; thread (lx, ly) owns the quad of 4 x-consecutive cells at
 // x = 4 * (blockIdx.x * bx + lx), y = blockIdx.y * by + ly and marches PCG_TZ planes in z from blockIdx.z * PCG_TZ.
@@ -207,8 +209,11 @@ __device__ __forceinline__ float guarded_div(float num, float den) { // pressure
 __global__ void __launch_bounds__(PCG_THREADS) pcg_prepare_kernel(GridDim g, TileMap t, const int8_t *__restrict__ m, uint8_t *__restrict__ codes,
                                                                   uint8_t *__restrict__ tile_active, float *__restrict__ p, float *__restrict__ r,
                                                                   float *__restrict__ s) {
+    __shared__ int sh_units;
     const TileCtx c = tile_ctx(g, t);
-    int any = 0;
+    if (linear_tid() == 0) sh_units = 0;
+    __syncthreads();
+    int any = 0; // planes of this thread's column whose quad holds a FLUID cell
     if (c.valid) {
         int i = c.i;
 #pragma unroll
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_prepare_kernel(GridDim g, Til
             const char4 cc = *reinterpret_cast<const char4 *>(m + i);
             uchar4 out = make_uchar4(0, 0, 0, 0);
             if (cc.x == CELL_FLUID || cc.y == CELL_FLUID || cc.z == CELL_FLUID || cc.w == CELL_FLUID) {
-                any = 1;
+                any += 1;
                 const char4 ym = *reinterpret_cast<const char4 *>(m + i - g.sy), yp = *reinterpret_cast<const char4 *>(m + i + g.sy);
                 const char4 zm = *reinterpret_cast<const char4 *>(m + i - g.sz), zp = *reinterpret_cast<const char4 *>(m + i + g.sz);
                 const int cx[6] = {m[i - 1], cc.x, cc.y, cc.z, cc.w, m[i + 4]};
@@ -245,8 +250,12 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_prepare_kernel(GridDim g, Til
             st4(s + i, zero4());
         }
     }
-    any = __syncthreads_or(any);
-    if (linear_tid() == 0) tile_active[c.tile] = (uint8_t)(any ? 1 : 0);
+    any = (int)__reduce_add_sync(0xffffffffu, (unsigned)any);
+    if ((linear_tid() & 31) == 0 && any) atomicAdd(&sh_units, any);
+    __syncthreads();
+    // 0 = no fluid, 1 = some, 2 = at least 3/4 of the (thread, plane) quads hold fluid: the persistent solver runs such a tile
+    // with its branch-free body
+    if (linear_tid() == 0) tile_active[c.tile] = (uint8_t)(sh_units == 0 ? 0 : (4 * sh_units >= 3 * PCG_THREADS * PCG_TZ ? 2 : 1));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -528,6 +537,7 @@ struct PcgSolveArgs {
     TileMap t;
     const uint8_t *codes;
     const int *tile_list;   // compacted active tiles
+    const int *tile_list_flagged; // the same with bit 30 set on tiles that are at least 3/4 full (pcg_prepare_kernel)
     const int *num_active;
     float *p, *r, *s0, *s1;
     PcgScalars *scal;
@@ -606,6 +616,173 @@ __device__ __forceinline__ double grid_sum(cooperative_groups::grid_group &grid,
     return v;
 }
 
+// Sparsity (SKIP): the FLUID set of a real scene is a thin, ragged body -- at step 110 of the 256^3 dam break 64 % of the
+// 128x8x4 tiles hold fluid but only 16 % of the 4x1x4 thread columns do (profiles/r01_v12_sparsity.txt).  A thread of a
+// sparse tile therefore reads the six code words of its column first and touches p, r, s only on planes whose quad holds a
+// FLUID cell: under the zero invariant everything it would have loaded, added or stored elsewhere is exactly 0, so the
+// result is bit-identical to the dense form.  Tiles that are at least 3/4 full (flagged by pcg_prepare_kernel, the flag
+// travels with the tile id) run the branch-free body, where no load waits for a code word: an all-fluid grid costs what it
+// cost before (3.72 vs 3.69 ms per 256^3 solve), the dam break's solves drop from 2.87 to 2.17 ms (step 110).
+// SKIP = false (solver path 4) keeps the branch-free body everywhere, for comparison.
+__device__ __forceinline__ unsigned ldcw(const uint8_t *p) { return *reinterpret_cast<const unsigned *>(p); }
+__device__ __forceinline__ uchar4 cw_code(unsigned w) {
+    return make_uchar4((unsigned char)(w & 0xffu), (unsigned char)((w >> 8) & 0xffu), (unsigned char)((w >> 16) & 0xffu), (unsigned char)(w >> 24));
+}
+template <bool SKIP>
+__device__ __forceinline__ float4 snew4w(const float *r, const float *s, int i, float beta, unsigned w) {
+    if (SKIP && w == 0u) return zero4();
+    const float4 r4 = ld4(r + i), s4 = ld4(s + i);
+    const uchar4 c = cw_code(w);
+    return make_float4(precond_diag2(r4.x, c.x) + beta * s4.x, precond_diag2(r4.y, c.y) + beta * s4.y, precond_diag2(r4.z, c.z) + beta * s4.z,
+                       precond_diag2(r4.w, c.w) + beta * s4.w);
+}
+template <bool SKIP>
+__device__ __forceinline__ float4 ld4w(const float *x, int i, unsigned w) {
+    if (SKIP && w == 0u) return zero4();
+    return ld4(x + i);
+}
+
+// What the tile bodies need besides their operands.
+struct TileEnv {
+    GridDim g;
+    const uint8_t *codes;
+    bool sharded;
+    int tz_first, tz_last, push;
+    float *peer_r_lo, *peer_r_hi;
+};
+
+// Code words of the thread's column (planes -1 .. PCG_TZ)
+__device__ __forceinline__ void load_column_codes(const TileEnv &e, const TileCtx &c, unsigned (&w)[PCG_TZ + 2]) {
+#pragma unroll
+    for (int k = 0; k < PCG_TZ + 2; ++k) w[k] = c.valid ? ldcw(e.codes + c.i + (k - 1) * e.g.sz) : 0u;
+}
+
+// r <- b - A p, partial z.r  (pressure_init.comp:45-83)
+template <bool SKIP>
+__device__ __forceinline__ void init_tile(const TileEnv &e, const TileCtx &c, const unsigned (&w)[PCG_TZ + 2], const float *p, float *r, float &acc) {
+    const GridDim &g = e.g;
+    int i = c.i;
+    float4 pm = zero4(), p0 = zero4(), pp = zero4();
+    if (c.valid) { pm = ld4w<SKIP>(p, i - g.sz, w[0]); p0 = ld4w<SKIP>(p, i, w[1]); }
+#pragma unroll
+    for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+        float left = __shfl_up_sync(0xffffffffu, p0.w, 1), right = __shfl_down_sync(0xffffffffu, p0.x, 1);
+        if (c.valid) pp = ld4w<SKIP>(p, i + g.sz, w[k + 2]);
+        if (c.valid && (!SKIP || w[k + 1] != 0u)) {
+            if (c.first) left = p[i - 1];
+            if (c.last) right = p[i + 4];
+            const uchar4 code = cw_code(w[k + 1]);
+            const float4 ym = ld4(p + i - g.sy), yp = ld4(p + i + g.sy);
+            float4 r4 = ld4(r + i);
+            const float4 Ap = stencil_quad(code, p0, left, right, ym, yp, pm, pp);
+            r4.x -= code.x ? Ap.x : 0.0f;
+            r4.y -= code.y ? Ap.y : 0.0f;
+            r4.z -= code.z ? Ap.z : 0.0f;
+            r4.w -= code.w ? Ap.w : 0.0f;
+            st4(r + i, r4);
+            if (e.sharded) { // boundary planes go straight into the neighbour's ghost planes (NVLink P2P stores)
+                if (k == 0 && c.tz == e.tz_first && e.peer_r_lo) st4(e.peer_r_lo + i + e.push, r4);
+                if (k == PCG_TZ - 1 && c.tz == e.tz_last && e.peer_r_hi) st4(e.peer_r_hi + i - e.push, r4);
+            }
+            acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
+                   (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
+        }
+        pm = p0;
+        p0 = pp;
+    }
+}
+
+// phase A: s' = z + beta s (pressure_update_search.comp) fused with s'.A s' (pressure_apply_coeff.comp)
+template <bool SKIP>
+__device__ __forceinline__ void search_tile(const TileEnv &e, const TileCtx &c, const unsigned (&w)[PCG_TZ + 2], const float *r, const float *s_in,
+                                            float *s_out, float beta, float &acc) {
+    const GridDim &g = e.g;
+    const uint8_t *codes = e.codes;
+    int i = c.i;
+    float4 cm = zero4(), c0 = zero4(), cp = zero4();
+    if (c.valid) {
+        cm = snew4w<SKIP>(r, s_in, i - g.sz, beta, w[0]);
+        c0 = snew4w<SKIP>(r, s_in, i, beta, w[1]);
+        // ghost plane below an owned boundary tile: keep the recomputed s' so that phase B and the next
+        // iteration find it locally (bit-identical to what the neighbour computes for its own plane)
+        if (e.sharded && c.tz == e.tz_first && (!SKIP || w[0] != 0u)) st4(s_out + i - g.sz, cm);
+    }
+#pragma unroll
+    for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+        float left = __shfl_up_sync(0xffffffffu, c0.w, 1), right = __shfl_down_sync(0xffffffffu, c0.x, 1);
+        if (c.valid) cp = snew4w<SKIP>(r, s_in, i + g.sz, beta, w[k + 2]);
+        const bool act = c.valid && (!SKIP || w[k + 1] != 0u);
+        float4 ym = zero4(), yp = zero4();
+        if (act) { // operand loads only: short enough to be predicated, so that the planes' loads can overlap
+            ym = snew4(r, s_in, codes, i - g.sy, beta);
+            yp = snew4(r, s_in, codes, i + g.sy, beta);
+        }
+        if (act) {
+            if (c.first) left = snew1(r, s_in, codes, i - 1, beta);
+            if (c.last) right = snew1(r, s_in, codes, i + 4, beta);
+            const float4 As = stencil_quad(cw_code(w[k + 1]), c0, left, right, ym, yp, cm, cp);
+            acc += (c0.x * As.x + c0.y * As.y) + (c0.z * As.z + c0.w * As.w);
+            st4(s_out + i, c0);
+        }
+        if (c.valid && e.sharded && k == PCG_TZ - 1 && c.tz == e.tz_last && (!SKIP || w[k + 2] != 0u)) st4(s_out + i + g.sz, cp);
+        cm = c0;
+        c0 = cp;
+    }
+}
+
+// phase B: p += alpha s', r -= alpha A s' (pressure_update_pressure_and_residual.comp), partial z.r and max|r|
+template <bool SKIP>
+__device__ __forceinline__ void update_tile(const TileEnv &e, const TileCtx &c, const unsigned (&w)[PCG_TZ + 2], const float *s, float *p, float *r,
+                                            float alpha, float &acc, float &err) {
+    const GridDim &g = e.g;
+    int i = c.i;
+    float4 sm = zero4(), s0 = zero4(), sp = zero4();
+    if (c.valid) { sm = ld4w<SKIP>(s, i - g.sz, w[0]); s0 = ld4w<SKIP>(s, i, w[1]); }
+#pragma unroll
+    for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
+        float left = __shfl_up_sync(0xffffffffu, s0.w, 1), right = __shfl_down_sync(0xffffffffu, s0.x, 1);
+        if (c.valid) sp = ld4w<SKIP>(s, i + g.sz, w[k + 2]);
+        const bool act = c.valid && (!SKIP || w[k + 1] != 0u);
+        float4 ym = zero4(), yp = zero4(), p4 = zero4(), r4 = zero4();
+        if (act) {
+            ym = ld4(s + i - g.sy);
+            yp = ld4(s + i + g.sy);
+            p4 = ld4(p + i);
+            r4 = ld4(r + i);
+        }
+        if (act) {
+            if (c.first) left = s[i - 1];
+            if (c.last) right = s[i + 4];
+            const uchar4 code = cw_code(w[k + 1]);
+            const float4 As = stencil_quad(code, s0, left, right, ym, yp, sm, sp);
+            p4.x += alpha * s0.x; p4.y += alpha * s0.y; p4.z += alpha * s0.z; p4.w += alpha * s0.w;
+            r4.x -= alpha * (code.x ? As.x : 0.0f);
+            r4.y -= alpha * (code.y ? As.y : 0.0f);
+            r4.z -= alpha * (code.z ? As.z : 0.0f);
+            r4.w -= alpha * (code.w ? As.w : 0.0f);
+            st4(p + i, p4);
+            st4(r + i, r4);
+            if (e.sharded) {
+                if (k == 0 && c.tz == e.tz_first && e.peer_r_lo) st4(e.peer_r_lo + i + e.push, r4);
+                if (k == PCG_TZ - 1 && c.tz == e.tz_last && e.peer_r_hi) st4(e.peer_r_hi + i - e.push, r4);
+            }
+            acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
+                   (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
+            err = fmaxf(fmaxf(err, fmaxf(fabsf(r4.x), fabsf(r4.y))), fmaxf(fabsf(r4.z), fabsf(r4.w)));
+        }
+        sm = s0;
+        s0 = sp;
+    }
+}
+
+// Tiles are dealt round robin: all blocks sweep the volume as one front, so the z-neighbour planes of a layer of tiles are still
+// in L2 when the next layer needs them.  (Grouping sparse tiles into equal-"work" slots was tried and is slower: a tile pass
+// costs a chain of dependent memory latencies whatever its fill.)  The id of the next tile is fetched one pass ahead.
+#define PCG_FOR_EACH_TILE(tile)                                                                                                      \
+    for (int li_ = blockIdx.x, tile = li_ < nact ? a.tile_list_flagged[li_] : 0, next_ = 0; li_ < nact; li_ += gridDim.x, tile = next_) \
+        if ((next_ = li_ + (int)gridDim.x < nact ? a.tile_list_flagged[li_ + gridDim.x] : 0), true)
+
+template <bool SKIP>
 __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(PcgSolveArgs a) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -615,17 +792,21 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
     __shared__ double sh_csum[SLAB_MAX_WORLD];
     __shared__ float sh_cmax[SLAB_MAX_WORLD];
     __shared__ int sh_dead;
-    const GridDim g = a.g;
     const TileMap t = a.t;
     const SlabComm &cm_ = a.comm;
     const bool sharded = cm_.world > 1;
     const int nact = *a.num_active;
-    const uint8_t *__restrict__ codes = a.codes;
     float *psumA = a.partials, *psumB = a.partials + gridDim.x, *pmax = a.partials + 2 * gridDim.x;
+    TileEnv e;
+    e.g = a.g;
+    e.codes = a.codes;
+    e.sharded = sharded;
     // slab geometry: tiles tz_first..tz_last are owned; the planes just outside are ghost planes fed by the neighbours
-    const int tz_first = cm_.halo / PCG_TZ, tz_last = t.tiles_z - 1 - cm_.halo / PCG_TZ;
-    const int push = cm_.owned_nz * g.sz; // index distance between an owned boundary plane and its image in the neighbour
-    float *const peer_r_lo = cm_.peer_r[0], *const peer_r_hi = cm_.peer_r[1];
+    e.tz_first = cm_.halo / PCG_TZ;
+    e.tz_last = t.tiles_z - 1 - cm_.halo / PCG_TZ;
+    e.push = cm_.owned_nz * a.g.sz; // index distance between an owned boundary plane and its image in the neighbour
+    e.peer_r_lo = cm_.peer_r[0];
+    e.peer_r_hi = cm_.peer_r[1];
     unsigned seq = 0;
     if (linear_tid() == 0) sh_dead = 0;
     if (sharded) seq = *cm_.seq;
@@ -633,36 +814,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
 
     // ---- init: r <- b - A p, sigma <- z.r (pressure_init.comp:45-83, pressure_solver.rs:625-649); s stays 0
     float acc = 0.0f;
-    for (int li = blockIdx.x; li < nact; li += gridDim.x) {
-        const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
-        int i = c.i;
-        float4 pm = zero4(), p0 = zero4(), pp = zero4();
-        if (c.valid) { pm = ld4(a.p + i - g.sz); p0 = ld4(a.p + i); }
-#pragma unroll
-        for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
-            float left, right;
-            x_neighbours(a.p, i, p0, c, left, right);
-            if (c.valid) {
-                pp = ld4(a.p + i + g.sz);
-                const uchar4 code = ldcode(codes + i);
-                const float4 ym = ld4(a.p + i - g.sy), yp = ld4(a.p + i + g.sy);
-                float4 r4 = ld4(a.r + i);
-                const float4 Ap = stencil_quad(code, p0, left, right, ym, yp, pm, pp);
-                r4.x -= code.x ? Ap.x : 0.0f;
-                r4.y -= code.y ? Ap.y : 0.0f;
-                r4.z -= code.z ? Ap.z : 0.0f;
-                r4.w -= code.w ? Ap.w : 0.0f;
-                st4(a.r + i, r4);
-                if (sharded) { // boundary planes go straight into the neighbour's ghost planes (NVLink P2P stores)
-                    if (k == 0 && c.tz == tz_first && peer_r_lo) st4(peer_r_lo + i + push, r4);
-                    if (k == PCG_TZ - 1 && c.tz == tz_last && peer_r_hi) st4(peer_r_hi + i - push, r4);
-                }
-                acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
-                       (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
-            }
-            pm = p0;
-            p0 = pp;
-        }
+    PCG_FOR_EACH_TILE(tile) {
+        const TileCtx c = tile_ctx_id(e.g, t, tile & (TILE_DENSE_BIT - 1));
+        unsigned w[PCG_TZ + 2];
+        load_column_codes(e, c, w);
+        if (!SKIP || (tile & TILE_DENSE_BIT)) init_tile<false>(e, c, w, a.p, a.r, acc);
+        else init_tile<true>(e, c, w, a.p, a.r, acc);
     }
     double tot = grid_sum(grid, psumB, acc, sh, &shd);
     float gmax = 0.0f;
@@ -674,81 +831,27 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
     for (int it = 0;; ++it) {
         const float *s_in = (it & 1) ? a.s1 : a.s0;
         float *s_out = (it & 1) ? a.s0 : a.s1;
-        // ---- phase A: s' = z + beta s (pressure_update_search.comp) fused with s'.A s' (pressure_apply_coeff.comp)
         acc = 0.0f;
-        for (int li = blockIdx.x; li < nact; li += gridDim.x) {
-            const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
-            int i = c.i;
-            float4 cm = zero4(), c0 = zero4(), cp = zero4();
-            uchar4 code0 = make_uchar4(0, 0, 0, 0);
-            if (c.valid) {
-                cm = snew4(a.r, s_in, codes, i - g.sz, beta);
-                c0 = snew4(a.r, s_in, codes, i, beta);
-                code0 = ldcode(codes + i);
-                // ghost plane below an owned boundary tile: keep the recomputed s' so that phase B and the next
-                // iteration find it locally (bit-identical to what the neighbour computes for its own plane)
-                if (sharded && c.tz == tz_first) st4(s_out + i - g.sz, cm);
-            }
-#pragma unroll
-            for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
-                float left = __shfl_up_sync(0xffffffffu, c0.w, 1), right = __shfl_down_sync(0xffffffffu, c0.x, 1);
-                if (c.valid) {
-                    if (c.first) left = snew1(a.r, s_in, codes, i - 1, beta);
-                    if (c.last) right = snew1(a.r, s_in, codes, i + 4, beta);
-                    const uchar4 codep = ldcode(codes + i + g.sz);
-                    cp = snew4(a.r, s_in, codes, i + g.sz, beta);
-                    const float4 ym = snew4(a.r, s_in, codes, i - g.sy, beta), yp = snew4(a.r, s_in, codes, i + g.sy, beta);
-                    const float4 As = stencil_quad(code0, c0, left, right, ym, yp, cm, cp);
-                    acc += (c0.x * As.x + c0.y * As.y) + (c0.z * As.z + c0.w * As.w);
-                    st4(s_out + i, c0);
-                    if (sharded && k == PCG_TZ - 1 && c.tz == tz_last) st4(s_out + i + g.sz, cp);
-                    code0 = codep;
-                }
-                cm = c0;
-                c0 = cp;
-            }
+        PCG_FOR_EACH_TILE(tile) {
+            const TileCtx c = tile_ctx_id(e.g, t, tile & (TILE_DENSE_BIT - 1));
+            unsigned w[PCG_TZ + 2];
+            load_column_codes(e, c, w);
+            if (!SKIP || (tile & TILE_DENSE_BIT)) search_tile<false>(e, c, w, a.r, s_in, s_out, beta, acc);
+            else search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
         }
         tot = grid_sum(grid, psumA, acc, sh, &shd);
         if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
         alpha = guarded_div(sigma, (float)tot); // RESULTMODE_ALPHA, pressure_reduce.comp:73-75
 
-        // ---- phase B: p += alpha s', r -= alpha A s' (pressure_update_pressure_and_residual.comp), z.r, max|r|
         const bool with_err = (a.max_iterations == it) || (it > 0 && it % a.check_frequency == 0); // pressure_solver.rs:676-677
         acc = 0.0f;
         float err = 0.0f;
-        for (int li = blockIdx.x; li < nact; li += gridDim.x) {
-            const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
-            int i = c.i;
-            float4 sm = zero4(), s0 = zero4(), sp = zero4();
-            if (c.valid) { sm = ld4(s_out + i - g.sz); s0 = ld4(s_out + i); }
-#pragma unroll
-            for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
-                float left, right;
-                x_neighbours(s_out, i, s0, c, left, right);
-                if (c.valid) {
-                    sp = ld4(s_out + i + g.sz);
-                    const uchar4 code = ldcode(codes + i);
-                    const float4 ym = ld4(s_out + i - g.sy), yp = ld4(s_out + i + g.sy);
-                    float4 p4 = ld4(a.p + i), r4 = ld4(a.r + i);
-                    const float4 As = stencil_quad(code, s0, left, right, ym, yp, sm, sp);
-                    p4.x += alpha * s0.x; p4.y += alpha * s0.y; p4.z += alpha * s0.z; p4.w += alpha * s0.w;
-                    r4.x -= alpha * (code.x ? As.x : 0.0f);
-                    r4.y -= alpha * (code.y ? As.y : 0.0f);
-                    r4.z -= alpha * (code.z ? As.z : 0.0f);
-                    r4.w -= alpha * (code.w ? As.w : 0.0f);
-                    st4(a.p + i, p4);
-                    st4(a.r + i, r4);
-                    if (sharded) {
-                        if (k == 0 && c.tz == tz_first && peer_r_lo) st4(peer_r_lo + i + push, r4);
-                        if (k == PCG_TZ - 1 && c.tz == tz_last && peer_r_hi) st4(peer_r_hi + i - push, r4);
-                    }
-                    acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
-                           (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
-                    err = fmaxf(fmaxf(err, fmaxf(fabsf(r4.x), fabsf(r4.y))), fmaxf(fabsf(r4.z), fabsf(r4.w)));
-                }
-                sm = s0;
-                s0 = sp;
-            }
+        PCG_FOR_EACH_TILE(tile) {
+            const TileCtx c = tile_ctx_id(e.g, t, tile & (TILE_DENSE_BIT - 1));
+            unsigned w[PCG_TZ + 2];
+            load_column_codes(e, c, w);
+            if (!SKIP || (tile & TILE_DENSE_BIT)) update_tile<false>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
+            else update_tile<true>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
         }
         {
             const float bm = block_max(err, sh);
@@ -756,8 +859,8 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
         }
         tot = grid_sum(grid, psumB, acc, sh, &shd); // the barrier inside also publishes pmax
         {
-            const float e = final_max(pmax, gridDim.x, sh);
-            if (linear_tid() == 0) shf = e;
+            const float em = final_max(pmax, gridDim.x, sh);
+            if (linear_tid() == 0) shf = em;
             __syncthreads();
             gmax = shf;
             __syncthreads();
@@ -780,12 +883,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
         // across the slab face), then one more round so that nobody leaves before its ghost planes are complete
         float *const peer_p_lo = cm_.peer_p[a.which][0], *const peer_p_hi = cm_.peer_p[a.which][1];
         for (int li = blockIdx.x; li < nact; li += gridDim.x) {
-            const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
+            const TileCtx c = tile_ctx_id(e.g, t, a.tile_list[li]);
             if (!c.valid) continue;
-            if (c.tz == tz_first && peer_p_lo) st4(peer_p_lo + c.i + push, ld4(a.p + c.i));
-            if (c.tz == tz_last && peer_p_hi) {
-                const int i = c.i + (PCG_TZ - 1) * g.sz;
-                st4(peer_p_hi + i - push, ld4(a.p + i));
+            if (c.tz == e.tz_first && peer_p_lo) st4(peer_p_lo + c.i + e.push, ld4(a.p + c.i));
+            if (c.tz == e.tz_last && peer_p_hi) {
+                const int i = c.i + (PCG_TZ - 1) * e.g.sz;
+                st4(peer_p_hi + i - e.push, ld4(a.p + i));
             }
         }
         grid.sync();
@@ -803,6 +906,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
         a.scal->done = sh_dead ? -1 : 1;
     }
 }
+#undef PCG_FOR_EACH_TILE
 
 // ---------------------------------------------------------------------------------------------------------------
 // TMA-tiled variant of the persistent solver (grids whose x extent is a multiple of 128 cells).
@@ -1425,7 +1529,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcg_solve_tma2_kernel(const __g
 
 // deterministic compaction of the active tiles (ascending tile id) by one block
 __global__ void __launch_bounds__(1024) pcg_compact_tiles_kernel(const uint8_t *__restrict__ tile_active, int tile_lo, int ntiles,
-                                                                 int *__restrict__ tile_list, int *__restrict__ num_active) {
+                                                                 int *__restrict__ tile_list, int *__restrict__ tile_list_flagged,
+                                                                 int *__restrict__ num_active) {
     __shared__ int sh[1024];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -1442,7 +1547,10 @@ __global__ void __launch_bounds__(1024) pcg_compact_tiles_kernel(const uint8_t *
             __syncthreads();
         }
         const int incl = sh[threadIdx.x];
-        if (v) tile_list[carry + incl - 1] = idx;
+        if (v) {
+            tile_list[carry + incl - 1] = idx;
+            tile_list_flagged[carry + incl - 1] = idx | (tile_active[idx] == 2 ? TILE_DENSE_BIT : 0);
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry += incl;
         __syncthreads();
@@ -1562,14 +1670,14 @@ PressureSolver::PressureSolver(const GridDim &grid, void *external_residual) : g
     BLUB_CUDA_CHECK(cudaMalloc(&partials_, sizeof(float) * (2 * (size_t)num_blocks_ + 8192)));
     BLUB_CUDA_CHECK(cudaMalloc(&tile_active_, (size_t)num_blocks_));
     BLUB_CUDA_CHECK(cudaMemset(tile_active_, 0, (size_t)num_blocks_));
-    BLUB_CUDA_CHECK(cudaMalloc(&tile_list_, sizeof(int) * ((size_t)num_blocks_ + 1)));
+    BLUB_CUDA_CHECK(cudaMalloc(&tile_list_, sizeof(int) * (2 * (size_t)num_blocks_ + 1))); // ids | count | ids with the dense flag
     num_active_ = tile_list_ + num_blocks_;
     // persistent cooperative solver: as many blocks as can be co-resident
     int dev = 0, coop = 0, sms = 0, per_sm = 0;
     BLUB_CUDA_CHECK(cudaGetDevice(&dev));
     BLUB_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     BLUB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_solve_persistent_kernel, PCG_THREADS, 0));
+    BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_solve_persistent_kernel<true>, PCG_THREADS, 0));
     persistent_blocks_ = coop ? sms * per_sm : 0;
     if (persistent_blocks_ > 2048) persistent_blocks_ = 2048;
     const char *env = std::getenv("BLUB_PCG");
@@ -1627,9 +1735,9 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
         // one cooperative launch for the whole solve; s ping-pongs between search_ and aux_ (both zero off the active tiles)
         BLUB_CUDA_CHECK(cudaMemsetAsync(aux_.ptr, 0, (size_t)g.n * sizeof(float), stream));
         const int ghost_tiles = (comm.halo / PCG_TZ) * t.tiles_x * t.tiles_y; // ghost planes are whole tiles (SLAB_HALO == PCG_TZ)
-        BLUB_LAUNCH(pcg_compact_tiles_kernel, 1, 1024, 0, stream, tile_active_, ghost_tiles, t.ntiles - ghost_tiles, tile_list_, num_active_);
+        BLUB_LAUNCH(pcg_compact_tiles_kernel, 1, 1024, 0, stream, tile_active_, ghost_tiles, t.ntiles - ghost_tiles, tile_list_, num_active_ + 1, num_active_);
         PcgSolveArgs args;
-        args.g = g; args.t = t; args.codes = st; args.tile_list = tile_list_; args.num_active = num_active_;
+        args.g = g; args.t = t; args.codes = st; args.tile_list = tile_list_; args.tile_list_flagged = num_active_ + 1; args.num_active = num_active_;
         args.p = p; args.r = r; args.s0 = s; args.s1 = aux_.ptr; args.scal = scal; args.partials = partials_;
         args.params = dparams; args.which = which; args.max_iterations = max_it; args.check_frequency = freq;
         args.comm = comm;
@@ -1649,7 +1757,7 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
         }
         int nblocks = persistent_blocks_ < t.ntiles ? persistent_blocks_ : t.ntiles;
         void *kargs[] = {&args};
-        BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_persistent_kernel, dim3(nblocks), t.block(), kargs, 0, stream));
+        BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel(use_dense ? (const void *)pcg_solve_persistent_kernel<false> : (const void *)pcg_solve_persistent_kernel<true>, dim3(nblocks), t.block(), kargs, 0, stream));
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
         return;
     }

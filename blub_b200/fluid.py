@@ -356,7 +356,10 @@ class HybridFluid:
 
     def set_solver_path(self, persistent):
         """True / 1: persistent cooperative PCG (default); False / 0: three kernels per iteration; 2 or "tma": TMA-staged tiles."""
-        mode = 3 if persistent in (3, "tma2") else (2 if persistent in (2, "tma") else (1 if persistent else 0))
+        if persistent in (4, "dense"):  # persistent kernel without the per-thread sparsity skip
+            mode = 4
+        else:
+            mode = 3 if persistent in (3, "tma2") else (2 if persistent in (2, "tma") else (1 if persistent else 0))
         _check(self.L.blub_fluid_set_solver_path(self.h, mode))
 
     def set_graph_replay(self, enabled):

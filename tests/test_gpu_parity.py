@@ -385,6 +385,39 @@ def test_tma_tiled_pcg_matches_oracle(max_it, freq, tol):
         grid_close(results[True], results["tma2"], "tma2 vs register path", rel=2e-3, abs_=1e-4)
 
 
+@pytest.mark.parametrize("fill", [0.05, 0.5, 0.97])
+def test_sparse_skip_is_bit_identical_to_the_dense_kernel(fill):
+    """The per-thread sparsity skip of the persistent solver only drops work whose result is exactly 0 (zero invariant): the
+    pressure must equal the dense form of the same kernel (solver path 4) bit for bit, on ragged sparse and dense FLUID sets."""
+    nx, ny, nz = 136, 24, 24  # ragged in x: 34 quads, a partial second tile
+    rng = np.random.default_rng(int(fill * 100))
+    m = np.full((nz, ny, nx), O.AIR, dtype=np.int8)
+    m[rng.random((nz, ny, nx)) < fill] = O.FLUID
+    m[rng.random((nz, ny, nx)) < 0.03] = O.SOLID
+    m[:, :, 60:70] = O.AIR  # a gap of empty columns inside the rows
+    m[0], m[-1], m[:, 0], m[:, -1], m[:, :, 0], m[:, :, -1] = 0, 0, 0, 0, 0, 0
+    b = rng.uniform(-1, 1, (nz, ny, nx)).astype(np.float32)
+    orc = O.OracleFluid(nx, ny, nz, 8)
+    orc.set_solver_config(0, 0.0, 24, 4)
+    orc.grid(O.ARR_MARKER)[:] = m
+    orc.grid(O.ARR_RESIDUAL)[:] = b
+    orc.solve(0, DT)
+    out = {}
+    for path in (True, "dense"):
+        gpu = blub_b200.HybridFluid(nx, ny, nz, 8)
+        gpu.set_solver_path(path)
+        gpu.set_solver_config(0, 0.0, 24, 4)
+        gpu.upload_grid(F.TAP_MARKER, m)
+        for rep in range(2):  # second solve: warm start from the first solution
+            gpu.upload_grid(F.TAP_RESIDUAL, b)
+            gpu.solve_only(0, DT)
+            if rep == 0:
+                grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), f"pressure path={path}", rel=3e-3, abs_=1e-4)
+        out[path] = (gpu.download_grid(F.TAP_P_VEL), gpu.last_solve(0))
+    assert out[True][1] == out["dense"][1]
+    assert np.array_equal(out[True][0], out["dense"][0])
+
+
 def test_empty_fluid_steps_without_particles():
     """Edge case: no particles at all (every cell AIR / SOLID): the step must run, the solves report 0 error."""
     gpu = blub_b200.HybridFluid(32, 32, 32, 1000)

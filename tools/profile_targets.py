@@ -1,7 +1,7 @@
 """Short GPU workloads to run under ncu (never a source of bench numbers).
 
     python tools/profile_targets.py step [scene] [steps]   # a few full steps
-    python tools/profile_targets.py pcg [n] [solves]       # the PCG roofline microbench (all-fluid n^3 box)
+    python tools/profile_targets.py pcg [n] [solves] [path] # the PCG roofline microbench (all-fluid n^3 box)
 """
 import os
 import sys
@@ -56,18 +56,27 @@ elif mode == "stages_sharded":
     print(f"{'total':24s} " + "  ".join(f"{a.sum() / reps:8.3f}" for a in acc) + " ms (eager, per rank)")
     print("errors", [s.slab_error() for s in slabs], "particles", [s.num_particles for s in slabs])
 elif mode == "stages":
+    # python tools/profile_targets.py stages [scene] [checkpoint steps ...]: stage times after so many steps (default 3)
     scene = sys.argv[2] if len(sys.argv) > 2 else "dam_256"
+    checkpoints = [int(a) for a in sys.argv[3:]] or [3]
     f = blub_b200.HybridFluid.from_scene(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".json"))
     from oracle.oracle import STAGES
-    for _ in range(3):
-        f.step(F.DT_120HZ)
-    acc = np.zeros(14)
-    reps = 5
-    for _ in range(reps):
-        acc += np.array(f.step_timed(F.DT_120HZ))
-    for name, ms in zip(STAGES, acc / reps):
-        print(f"{name:24s} {ms:8.3f} ms")
-    print(f"{'total':24s} {acc.sum() / reps:8.3f} ms (eager launches, events between stages)")
+    done, cols, reps = 0, [], 3
+    for cp in checkpoints:
+        while done < cp:
+            f.step(F.DT_120HZ)
+            done += 1
+        acc = np.zeros(14)
+        for _ in range(reps):
+            acc += np.array(f.step_timed(F.DT_120HZ))
+            done += 1
+        cols.append(acc / reps)
+    print(f"{'after steps':24s} " + " ".join(f"{c:8d}" for c in checkpoints))
+    for i, name in enumerate(STAGES):
+        print(f"{name:24s} " + " ".join(f"{c[i]:8.3f}" for c in cols) + " ms")
+    print(f"{'total':24s} " + " ".join(f"{c.sum():8.3f}" for c in cols) + " ms (eager launches, events between stages)")
+    f.update_statistics()
+    print("solver stats", f.pressure_solver_stats(0)[-1], f.pressure_solver_stats(1)[-1])
 else:
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     solves = int(sys.argv[3]) if len(sys.argv) > 3 else 2
@@ -79,5 +88,7 @@ else:
     b[m != 1] = 0
     f.upload_grid(F.TAP_MARKER, m)
     f.upload_grid(F.TAP_RESIDUAL, b)
+    if len(sys.argv) > 4:
+        f.set_solver_path(int(sys.argv[4]) if sys.argv[4].isdigit() else sys.argv[4])
     f.set_solver_config(0, 0.0, 32, 4)
     print("ms per solve", f.time_solve(0, F.DT_120HZ, solves))
