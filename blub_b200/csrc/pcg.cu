@@ -592,6 +592,15 @@ __device__ __forceinline__ void comm_allreduce(const SlabComm &c, unsigned seq, 
     mx = m;
 }
 
+// First thing a sharded solve does: one empty all-reduce round.  A rank that has entered its solver kernel has finished its
+// prepare kernel (stream order), which zeroes r and p off-fluid in ALL its planes -- ghost planes included -- with read-modify-
+// write; without the round a fast neighbour's first ghost-plane push could land in the middle of that and be lost.
+__device__ __forceinline__ void slab_start_handshake(const SlabComm &c, unsigned &seq, double *sh_sum, float *sh_max, int *sh_dead) {
+    double none = 0.0;
+    float nomax = 0.0f;
+    comm_allreduce(c, ++seq, none, nomax, sh_sum, sh_max, sh_dead);
+}
+
 // NOTE: r, s, p are written by other blocks between grid barriers: no __restrict__/read-only (LDG.NC) path for them.
 __device__ __forceinline__ float4 snew4(const float *r, const float *s, const uint8_t *__restrict__ codes, int i, float beta) {
     const float4 r4 = ld4(r + i), s4 = ld4(s + i);
@@ -811,6 +820,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
     if (linear_tid() == 0) sh_dead = 0;
     if (sharded) seq = *cm_.seq;
     __syncthreads();
+    if (sharded) slab_start_handshake(cm_, seq, sh_csum, sh_cmax, &sh_dead);
 
     // ---- init: r <- b - A p, sigma <- z.r (pressure_init.comp:45-83, pressure_solver.rs:625-649); s stays 0
     float acc = 0.0f;
@@ -995,6 +1005,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_tma_kernel(const __g
     }
     if (sharded) seq = *cm_.seq;
     __syncthreads();
+    if (sharded) slab_start_handshake(cm_, seq, sh_csum, sh_cmax, &sh_dead);
 
     // ---- init: r <- b - A p, sigma <- z.r (as in the register-marching kernel: runs once, plain loads)
     float acc = 0.0f;
@@ -1295,6 +1306,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcg_solve_tma2_kernel(const __g
     }
     if (sharded) seq = *cm_.seq;
     __syncthreads();
+    if (sharded) slab_start_handshake(cm_, seq, sh_csum, sh_cmax, &sh_dead);
 
     auto tile_origin = [&](int tile, int &x0, int &y0, int &z0, int &tz) {
         const int tx = tile % t.tiles_x, rest = tile / t.tiles_x;
