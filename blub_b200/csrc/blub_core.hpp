@@ -284,7 +284,21 @@ class HybridFluid {
 void voxelize_rigid_solid(void *rgba16f, const uint32_t dim[3], const BlubRigidObject &o, float grid_to_world_scale, const float fluid_world_position[3],
                           double total_time, double delta, int clear_first, cudaStream_t stream, BlubRigidState *state_out);
 
+// shared animation evaluation (solids.cu) and the triangle-mesh hull voxelizer (mesh_voxelizer.cu)
+void rigid_state_at(const BlubRigidObject &o, float grid_to_world_scale, const float fluid_world_position[3], double total_time, double delta,
+                    BlubRigidState &out);
+BlubMesh *mesh_create(const float *positions, uint32_t num_vertices, const uint32_t *indices, uint32_t num_indices, int device);
+void mesh_destroy(BlubMesh *mesh);
+void mesh_info(const BlubMesh &mesh, uint32_t &num_vertices, uint32_t &num_triangles);
+void voxelize_mesh(void *rgba16f, const uint32_t dim[3], BlubMesh &mesh, const BlubRigidObject &o, float grid_to_world_scale, const float fluid_world_position[3],
+                   double total_time, double delta, int clear_first, cudaStream_t stream, BlubRigidState *state_out);
+void read_obj(const std::string &path, std::vector<float> &positions, std::vector<uint32_t> &indices);
+
 // scene JSON (src/scene/mod.rs:19-43)
+struct SceneStaticObject {
+    std::string model;          // path below the reference's `models/` directory (models.rs:253)
+    BlubRigidObject placement;  // pose + animation; shape = 2 (mesh)
+};
 struct SceneBox {
     float min[3], max[3];
 };
@@ -296,6 +310,7 @@ struct SceneConfig {
     uint32_t max_num_particles = 0;
     std::vector<SceneBox> fluid_cubes;
     uint32_t num_static_objects = 0;
+    std::vector<SceneStaticObject> static_objects;
 };
 SceneConfig parse_scene_file(const std::string &path);
 // Scene::create_fluid_from_config, src/scene/mod.rs:109-144

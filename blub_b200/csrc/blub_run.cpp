@@ -9,6 +9,9 @@
 //                  hybrid_fluid.rs:780-973)
 //   --dump FILE    particle positions (float32 x,y,z,pad) for an external viewer -- the renderer hand-off
 //                  (hybrid_fluid.rs:351-369) without wgpu
+//   --models DIR   where the scene's static_objects find their OBJ files (the reference reads `models/<model>`,
+//                  src/scene/models.rs:253).  Every step then runs Scene::step's order (src/scene/mod.rs:192-211): animate the
+//                  models at the already advanced simulation time, voxelize their hulls, step the fluid.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -33,13 +36,13 @@ static void die(const char *what) {
 int main(int argc, char **argv) {
     if (argc < 2) {
         std::fprintf(stderr, "usage: blub_run scene.json [--steps N] [--batch 16] [--hz 120] [--device 0] [--no-graph]\n"
-                             "                [--stats out.json] [--trace out.json] [--dump particles.f32]\n");
+                             "                [--stats out.json] [--trace out.json] [--dump particles.f32] [--models DIR]\n");
         return 2;
     }
     const char *scene = argv[1];
     int steps = 160, batch = 16, device = 0, graph = 1;
     long hz = 120;
-    std::string stats_path, trace_path, dump_path;
+    std::string stats_path, trace_path, dump_path, models_dir = "models";
     for (int i = 2; i < argc; ++i) {
         auto next = [&](const char *flag) -> const char * {
             if (i + 1 >= argc) { std::fprintf(stderr, "blub_run: %s needs a value\n", flag); std::exit(2); }
@@ -53,6 +56,7 @@ int main(int argc, char **argv) {
         else if (!std::strcmp(argv[i], "--stats")) stats_path = next("--stats");
         else if (!std::strcmp(argv[i], "--trace")) trace_path = next("--trace");
         else if (!std::strcmp(argv[i], "--dump")) dump_path = next("--dump");
+        else if (!std::strcmp(argv[i], "--models")) models_dir = next("--models");
         else { std::fprintf(stderr, "blub_run: unknown option %s\n", argv[i]); return 2; }
     }
     if (steps < 1 || batch < 1 || hz < 1) { std::fprintf(stderr, "blub_run: bad --steps/--batch/--hz\n"); return 2; }
@@ -64,15 +68,44 @@ int main(int argc, char **argv) {
     BlubFluid *fluid = nullptr;
     if (blub_scene_load(&fluid, scene, device, nullptr)) die("cannot create fluid");
     blub_fluid_set_graph_replay(fluid, graph);
-    std::printf("scene %s: grid %ux%ux%u, %u particles (max %u), %u static object(s) ignored, dt %.9f s\n", scene, info.grid_dimension[0],
+    std::printf("scene %s: grid %ux%ux%u, %u particles (max %u), %u static object(s), dt %.9f s\n", scene, info.grid_dimension[0],
                 info.grid_dimension[1], info.grid_dimension[2], blub_fluid_num_particles(fluid), info.max_num_particles, info.num_static_objects, dt);
+
+    // SceneModels::from_config (src/scene/models.rs:240-262): one mesh per static object
+    struct Solid { BlubMesh *mesh; BlubRigidObject placement; };
+    std::vector<Solid> solids;
+    void *voxels = nullptr;
+    for (uint32_t k = 0; k < info.num_static_objects; ++k) {
+        Solid s;
+        char model[1024];
+        if (blub_scene_static_object(scene, k, &s.placement, model, sizeof(model))) die("cannot read static object");
+        const std::string path = models_dir + "/" + model;
+        if (blub_mesh_load_obj(&s.mesh, path.c_str(), device)) die("cannot load model"); // the reference fails to load the scene as well
+        uint32_t nv = 0, nt = 0;
+        blub_mesh_info(s.mesh, &nv, &nt);
+        std::printf("static object %u: %s, %u vertices, %u triangles\n", k, path.c_str(), nv, nt);
+        solids.push_back(s);
+    }
+    if (!solids.empty()) {
+        const size_t cells = (size_t)info.grid_dimension[0] * info.grid_dimension[1] * info.grid_dimension[2];
+        if (blub_device_malloc(&voxels, cells * 8, device)) die("cannot allocate the voxel volume");
+        if (blub_fluid_set_solid_voxels(fluid, voxels)) die("set_solid_voxels failed");
+    }
+    double simulated = 0.0; // Timer::total_simulated_time, advanced BEFORE the step it belongs to (src/timer.rs:122-124)
+    auto scene_step = [&]() {
+        simulated += dt;
+        for (size_t k = 0; k < solids.size(); ++k)
+            if (blub_solid_voxelize_mesh(voxels, info.grid_dimension, solids[k].mesh, &solids[k].placement, info.grid_to_world_scale, info.world_position,
+                                         simulated, dt, k == 0, blub_fluid_stream(fluid), nullptr))
+                die("voxelization failed");
+        if (blub_fluid_step(fluid, dt)) die("step failed");
+    };
 
     const auto t0 = std::chrono::steady_clock::now();
     int done = 0;
     while (done < steps) { // MAX_FAST_FORWARD_SIMULATION_BATCH_SIZE = 16, then wait for the GPU
         const int n = steps - done < batch ? steps - done : batch;
-        for (int k = 0; k < n; ++k)
-            if (blub_fluid_step(fluid, dt)) die("step failed");
+        for (int k = 0; k < n; ++k) scene_step();
         if (blub_fluid_synchronize(fluid)) die("synchronize failed");
         blub_fluid_update_statistics(fluid);
         done += n;
@@ -124,5 +157,7 @@ int main(int argc, char **argv) {
                     info.world_position[0], info.world_position[1], info.world_position[2], dump_path.c_str());
     }
     blub_fluid_destroy(fluid);
+    for (Solid &s : solids) blub_mesh_destroy(s.mesh);
+    if (voxels) blub_device_free(voxels);
     return 0;
 }

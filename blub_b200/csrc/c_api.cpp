@@ -1,4 +1,5 @@
 // c_api.cpp -- the extern "C" boundary (include/blub_fluid.h) over blub::HybridFluid.  Nothing throws across it.
+#include <algorithm>
 #include <cstring>
 #include <ios>
 #include <new>
@@ -114,6 +115,95 @@ int blub_solid_voxelize(void *rgba16f, const uint32_t dim[3], const BlubRigidObj
     if (!(scale > 0.0f) || !(delta > 0.0)) return fail(BLUB_ERR_INVALID_ARGUMENT, "scale and delta must be positive");
     return guarded([&] {
         blub::voxelize_rigid_solid(rgba16f, dim, *object, scale, fluid_world_position, total_time, delta, clear_first, static_cast<cudaStream_t>(cuda_stream), state_out);
+        return BLUB_OK;
+    });
+}
+
+void *blub_fluid_stream(const BlubFluid *fluid) { return fluid ? static_cast<void *>(fluid->impl->stream()) : nullptr; }
+
+int blub_device_malloc(void **out, size_t bytes, int device) {
+    if (!out) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    return guarded([&] {
+        BLUB_CUDA_CHECK(cudaSetDevice(device));
+        BLUB_CUDA_CHECK(cudaMalloc(out, bytes ? bytes : 1));
+        BLUB_CUDA_CHECK(cudaMemset(*out, 0, bytes ? bytes : 1));
+        return BLUB_OK;
+    });
+}
+
+int blub_device_free(void *device_ptr) {
+    return guarded([&] {
+        BLUB_CUDA_CHECK(cudaFree(device_ptr));
+        return BLUB_OK;
+    });
+}
+
+int blub_mesh_create(BlubMesh **out, const float *positions, uint32_t num_vertices, const uint32_t *indices, uint32_t num_indices, int device) {
+    if (!out) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    return guarded([&] {
+        *out = blub::mesh_create(positions, num_vertices, indices, num_indices, device);
+        return BLUB_OK;
+    });
+}
+
+int blub_mesh_load_obj(BlubMesh **out, const char *obj_path, int device) {
+    if (!out || !obj_path) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    return guarded([&] {
+        std::vector<float> positions;
+        std::vector<uint32_t> indices;
+        blub::read_obj(obj_path, positions, indices);
+        *out = blub::mesh_create(positions.data(), (uint32_t)(positions.size() / 3), indices.data(), (uint32_t)indices.size(), device);
+        return BLUB_OK;
+    });
+}
+
+void blub_mesh_destroy(BlubMesh *mesh) { blub::mesh_destroy(mesh); }
+
+int blub_mesh_info(const BlubMesh *mesh, uint32_t *num_vertices, uint32_t *num_triangles) {
+    if (!mesh || !num_vertices || !num_triangles) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    blub::mesh_info(*mesh, *num_vertices, *num_triangles);
+    return BLUB_OK;
+}
+
+int blub_obj_read(const char *obj_path, float *positions, uint32_t capacity_vertices, uint32_t *indices, uint32_t capacity_indices, uint32_t counts_out[2]) {
+    if (!obj_path || !counts_out) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        std::vector<float> p;
+        std::vector<uint32_t> idx;
+        blub::read_obj(obj_path, p, idx);
+        counts_out[0] = (uint32_t)(p.size() / 3);
+        counts_out[1] = (uint32_t)idx.size();
+        if (positions) std::memcpy(positions, p.data(), sizeof(float) * 3 * std::min<size_t>(capacity_vertices, p.size() / 3));
+        if (indices) std::memcpy(indices, idx.data(), sizeof(uint32_t) * std::min<size_t>(capacity_indices, idx.size()));
+        return BLUB_OK;
+    });
+}
+
+int blub_solid_voxelize_mesh(void *rgba16f, const uint32_t dim[3], BlubMesh *mesh, const BlubRigidObject *placement, float scale,
+                             const float fluid_world_position[3], double total_time, double delta, int clear_first, void *cuda_stream,
+                             BlubRigidState *state_out) {
+    if (!rgba16f || !dim || !mesh || !placement || !fluid_world_position) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!(scale > 0.0f) || !(delta > 0.0)) return fail(BLUB_ERR_INVALID_ARGUMENT, "scale and delta must be positive");
+    if (dim[0] == 0 || dim[1] == 0 || dim[2] == 0 || (uint64_t)dim[0] * dim[1] * dim[2] >= (1ull << 31)) return fail(BLUB_ERR_INVALID_ARGUMENT, "bad grid dimension");
+    return guarded([&] {
+        blub::voxelize_mesh(rgba16f, dim, *mesh, *placement, scale, fluid_world_position, total_time, delta, clear_first, static_cast<cudaStream_t>(cuda_stream), state_out);
+        return BLUB_OK;
+    });
+}
+
+int blub_scene_static_object(const char *path, uint32_t index, BlubRigidObject *placement_out, char *model_path_out, size_t capacity) {
+    if (!path || !placement_out) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        blub::SceneConfig c = blub::parse_scene_file(path);
+        if (index >= c.static_objects.size()) throw std::invalid_argument("static object index out of range");
+        *placement_out = c.static_objects[index].placement;
+        if (model_path_out && capacity) {
+            std::strncpy(model_path_out, c.static_objects[index].model.c_str(), capacity - 1);
+            model_path_out[capacity - 1] = 0;
+        }
         return BLUB_OK;
     });
 }

@@ -3,6 +3,7 @@
 // Key order is free (scenes/wavegenerator.json orders the fluid block differently from the others).
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <map>
 #include <sstream>
@@ -171,12 +172,37 @@ SceneConfig parse_scene_file(const std::string &path) {
     }
     if (const JsonValue *objs = root.get("static_objects")) { // #[serde(default)]
         if (objs->kind != JsonValue::Array) throw std::runtime_error("scene JSON: `static_objects` is not an array");
-        for (const JsonValue &o : objs->array) { // StaticObjectConfig, src/scene/models.rs:11-19: validate the required fields
-            need(o, "model");
-            float tmp[3];
-            vec3(need(o, "world_position"), "static_objects.world_position", tmp);
-            num_f32(need(o, "scale"), "static_objects.scale");
-            vec3(need(o, "rotation_angles"), "static_objects.rotation_angles", tmp);
+        for (const JsonValue &o : objs->array) { // StaticObjectConfig, src/scene/models.rs:11-19
+            SceneStaticObject so;
+            const JsonValue &model = need(o, "model");
+            if (model.kind != JsonValue::String) throw std::runtime_error("scene JSON: `static_objects.model` is not a string");
+            so.model = model.string;
+            BlubRigidObject &r = so.placement;
+            std::memset(&r, 0, sizeof(r));
+            r.shape = 2; // triangle mesh
+            vec3(need(o, "world_position"), "static_objects.world_position", r.world_position);
+            r.scale = num_f32(need(o, "scale"), "static_objects.scale");
+            vec3(need(o, "rotation_angles"), "static_objects.rotation_angles", r.rotation_angles_deg);
+            const JsonValue *anim = o.get("animation"); // Option<RigidAnimation>, models.rs:41-46
+            if (anim && anim->kind == JsonValue::Object) {
+                const JsonValue *tr = anim->get("translation"); // TranslationAnimation, :28-32
+                if (tr && tr->kind == JsonValue::Object) {
+                    r.has_translation = 1;
+                    vec3(need(*tr, "target"), "animation.translation.target", r.translation_target);
+                    const JsonValue &curve = need(*tr, "curve");
+                    if (curve.kind != JsonValue::String || (curve.string != "Linear" && curve.string != "SmoothStep"))
+                        throw std::runtime_error("scene JSON: `animation.translation.curve` must be \"Linear\" or \"SmoothStep\"");
+                    r.translation_curve = curve.string == "SmoothStep" ? 1 : 0;
+                    r.translation_duration = num_f32(need(*tr, "duration"), "animation.translation.duration");
+                }
+                const JsonValue *rot = anim->get("rotation"); // RotationAnimation, :35-38
+                if (rot && rot->kind == JsonValue::Object) {
+                    r.has_rotation = 1;
+                    vec3(need(*rot, "axis"), "animation.rotation.axis", r.rotation_axis);
+                    r.rotation_deg_per_sec = num_f32(need(*rot, "deg_per_sec"), "animation.rotation.deg_per_sec");
+                }
+            }
+            cfg.static_objects.push_back(so);
         }
         cfg.num_static_objects = (uint32_t)objs->array.size();
     }

@@ -94,9 +94,10 @@ __global__ void __launch_bounds__(256) voxelize_box_kernel(uint2 *__restrict__ v
 
 } // namespace
 
-// evaluates the animation on the host (as StaticMeshData::to_gpu does) and enqueues one kernel
-void voxelize_rigid_solid(void *rgba16f, const uint32_t dim[3], const BlubRigidObject &o, float grid_to_world_scale, const float fluid_world_position[3],
-                          double total_time, double delta, int clear_first, cudaStream_t stream, BlubRigidState *state_out) {
+// StaticMeshData::to_gpu (src/scene/models.rs:186-224) evaluated on the host: where the object is, how it is rotated and how it moves,
+// in voxel space.  Shared by the analytic solids below and the mesh voxelizer (mesh_voxelizer.cu).
+void rigid_state_at(const BlubRigidObject &o, float grid_to_world_scale, const float fluid_world_position[3], double total_time, double delta,
+                    BlubRigidState &out) {
     const float t = (float)total_time, dt = (float)delta;
     float pos[3], prev[3], vel[3] = {0, 0, 0};
     world_position_at_time(o, t, pos);
@@ -112,27 +113,33 @@ void voxelize_rigid_solid(void *rgba16f, const uint32_t dim[3], const BlubRigidO
         const float n = std::sqrt(o.rotation_axis[0] * o.rotation_axis[0] + o.rotation_axis[1] * o.rotation_axis[1] + o.rotation_axis[2] * o.rotation_axis[2]);
         for (int k = 0; k < 3; ++k) axis_scaled[k] = o.rotation_axis[k] / (n > 0.0f ? n : 1.0f) * rad_per_s;
     }
-    BoxParams b;
     // local -> world rotation matrix from the quaternion (columns = rotated basis vectors)
     const float R[9] = {1 - 2 * (q.y * q.y + q.z * q.z), 2 * (q.x * q.y - q.z * q.s),     2 * (q.x * q.z + q.y * q.s),
                         2 * (q.x * q.y + q.z * q.s),     1 - 2 * (q.x * q.x + q.z * q.z), 2 * (q.y * q.z - q.x * q.s),
                         2 * (q.x * q.z - q.y * q.s),     2 * (q.y * q.z + q.x * q.s),     1 - 2 * (q.x * q.x + q.y * q.y)};
-    for (int k = 0; k < 9; ++k) b.rot[k] = R[k];
+    for (int k = 0; k < 9; ++k) out.rotation[k] = R[k];
     for (int k = 0; k < 3; ++k) {
-        b.centre[k] = (pos[k] - fluid_world_position[k]) / grid_to_world_scale; // transform_voxel, models.rs:196-198
+        out.centre_voxel[k] = (pos[k] - fluid_world_position[k]) / grid_to_world_scale; // transform_voxel, models.rs:196-198
+        out.velocity_voxel[k] = vel[k] / grid_to_world_scale;                           // fluid_space_velocity, :206
+        out.axis_scaled[k] = axis_scaled[k];                                            // fluid_space_rotation_axis_scaled, :207-216
+    }
+}
+
+// analytic box / sphere: evaluates the animation and enqueues one kernel
+void voxelize_rigid_solid(void *rgba16f, const uint32_t dim[3], const BlubRigidObject &o, float grid_to_world_scale, const float fluid_world_position[3],
+                          double total_time, double delta, int clear_first, cudaStream_t stream, BlubRigidState *state_out) {
+    BlubRigidState st;
+    rigid_state_at(o, grid_to_world_scale, fluid_world_position, total_time, delta, st);
+    if (state_out) *state_out = st;
+    BoxParams b;
+    for (int k = 0; k < 9; ++k) b.rot[k] = st.rotation[k];
+    for (int k = 0; k < 3; ++k) {
+        b.centre[k] = st.centre_voxel[k];
         b.half[k] = o.half_extent[k] * o.scale / grid_to_world_scale;
-        b.velocity[k] = vel[k] / grid_to_world_scale;                           // fluid_space_velocity, :206
-        b.axis[k] = axis_scaled[k];                                            // fluid_space_rotation_axis_scaled, :207-216
+        b.velocity[k] = st.velocity_voxel[k];
+        b.axis[k] = st.axis_scaled[k];
     }
     b.sphere = o.shape == 1;
-    if (state_out) {
-        for (int k = 0; k < 3; ++k) {
-            state_out->centre_voxel[k] = b.centre[k];
-            state_out->velocity_voxel[k] = b.velocity[k];
-            state_out->axis_scaled[k] = b.axis[k];
-        }
-        for (int k = 0; k < 9; ++k) state_out->rotation[k] = R[k];
-    }
     const int64_t n = (int64_t)dim[0] * dim[1] * dim[2];
     BLUB_LAUNCH(voxelize_box_kernel, (int)((n + 255) / 256), 256, 0, stream, static_cast<uint2 *>(rgba16f), (int)dim[0], (int)dim[1], (int)dim[2], b, clear_first);
 }

@@ -60,8 +60,8 @@ class RigidObject(C.Structure):
         o.world_position[:] = [float(v) for v in obj["world_position"]]
         o.scale = float(obj.get("scale", 1.0))
         o.rotation_angles_deg[:] = [float(v) for v in obj.get("rotation_angles", (0, 0, 0))]
-        o.shape = 1 if obj.get("shape", "box") == "sphere" else 0
-        o.half_extent[:] = [float(v) for v in obj["half_extent"]]
+        o.shape = {"box": 0, "sphere": 1, "mesh": 2}[obj.get("shape", "box")]
+        o.half_extent[:] = [float(v) for v in obj.get("half_extent", (0, 0, 0))]
         tr, rot = obj.get("translation"), obj.get("rotation")
         if tr:
             o.has_translation = 1
@@ -111,6 +111,17 @@ def lib():
         "blub_fluid_slab_error": (C.c_int, [vp]),
         "blub_solid_voxelize": (C.c_int, [vp, C.POINTER(u32), C.POINTER(RigidObject), C.c_float, f3, C.c_double, C.c_double, C.c_int, vp,
                                           C.POINTER(RigidState)]),
+        "blub_fluid_stream": (vp, [vp]),
+        "blub_device_malloc": (C.c_int, [C.POINTER(vp), C.c_size_t, C.c_int]),
+        "blub_device_free": (C.c_int, [vp]),
+        "blub_mesh_create": (C.c_int, [C.POINTER(vp), vp, u32, vp, u32, C.c_int]),
+        "blub_mesh_load_obj": (C.c_int, [C.POINTER(vp), C.c_char_p, C.c_int]),
+        "blub_mesh_destroy": (None, [vp]),
+        "blub_mesh_info": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32)]),
+        "blub_obj_read": (C.c_int, [C.c_char_p, vp, u32, vp, u32, C.POINTER(u32)]),
+        "blub_solid_voxelize_mesh": (C.c_int, [vp, C.POINTER(u32), vp, C.POINTER(RigidObject), C.c_float, f3, C.c_double, C.c_double, C.c_int, vp,
+                                               C.POINTER(RigidState)]),
+        "blub_scene_static_object": (C.c_int, [C.c_char_p, u32, C.POINTER(RigidObject), C.c_char_p, C.c_size_t]),
         "blub_ipc_export": (C.c_int, [vp, C.c_char_p]),
         "blub_ipc_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
         "blub_ipc_close": (C.c_int, [vp]),
@@ -180,6 +191,64 @@ def solid_voxelize(rgba16f_device_ptr, dims, obj, scale, fluid_world_position, t
     _check(lib().blub_solid_voxelize(rgba16f_device_ptr, d, C.byref(RigidObject.from_dict(obj)), float(scale), _f3(fluid_world_position), float(t),
                                      float(dt), 1 if clear_first else 0, cuda_stream, C.byref(st)))
     return st
+
+
+def obj_read(path):
+    """Positions [nv, 3] float32 and triangles [nt, 3] uint32 of a Wavefront OBJ, read by the library's host-side loader."""
+    import numpy as np
+    counts = (C.c_uint32 * 2)()
+    _check(lib().blub_obj_read(os.fsencode(path), None, 0, None, 0, counts))
+    pos = np.zeros((counts[0], 3), dtype=np.float32)
+    idx = np.zeros(counts[1], dtype=np.uint32)
+    _check(lib().blub_obj_read(os.fsencode(path), pos.ctypes.data_as(C.c_void_p), counts[0], idx.ctypes.data_as(C.c_void_p), counts[1], counts))
+    return pos, idx.reshape(-1, 3)
+
+
+class Mesh:
+    """Device-resident triangle mesh for the hull voxelizer (MeshVertices / MeshIndices of the reference's voxelization pass)."""
+
+    def __init__(self, positions=None, triangles=None, obj_path=None, device=0):
+        import numpy as np
+        self.h = C.c_void_p()
+        if obj_path is not None:
+            _check(lib().blub_mesh_load_obj(C.byref(self.h), os.fsencode(obj_path), device))
+        else:
+            pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+            idx = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1)
+            _check(lib().blub_mesh_create(C.byref(self.h), pos.ctypes.data_as(C.c_void_p), pos.shape[0], idx.ctypes.data_as(C.c_void_p), idx.shape[0], device))
+
+    def info(self):
+        nv, nt = C.c_uint32(), C.c_uint32()
+        _check(lib().blub_mesh_info(self.h, C.byref(nv), C.byref(nt)))
+        return int(nv.value), int(nt.value)
+
+    def voxelize(self, rgba16f_device_ptr, dims, placement, scale, fluid_world_position, t, dt, clear_first=True, cuda_stream=None):
+        """One draw of the reference's voxelization pass for this mesh (placement: dict as for RigidObject.from_dict, shape ignored)."""
+        d = (C.c_uint32 * 3)(*[int(v) for v in dims])
+        st = RigidState()
+        obj = placement if isinstance(placement, RigidObject) else RigidObject.from_dict(dict(placement, shape="mesh"))
+        _check(lib().blub_solid_voxelize_mesh(rgba16f_device_ptr, d, self.h, C.byref(obj), float(scale), _f3(fluid_world_position), float(t), float(dt),
+                                              1 if clear_first else 0, cuda_stream, C.byref(st)))
+        return st
+
+    def close(self):
+        if self.h:
+            lib().blub_mesh_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def scene_static_object(path, index):
+    """(model path, RigidObject placement) of static_objects[index] of a scene file."""
+    obj = RigidObject()
+    buf = C.create_string_buffer(1024)
+    _check(lib().blub_scene_static_object(os.fsencode(path), index, C.byref(obj), buf, len(buf)))
+    return buf.value.decode(), obj
 
 
 def kernel_launch_count(reset=False) -> int:
@@ -361,6 +430,10 @@ class HybridFluid:
         else:
             mode = 3 if persistent in (3, "tma2") else (2 if persistent in (2, "tma") else (1 if persistent else 0))
         _check(self.L.blub_fluid_set_solver_path(self.h, mode))
+
+    def stream(self):
+        """The CUDA stream (as an integer handle) the fluid's work is enqueued on."""
+        return self.L.blub_fluid_stream(self.h)
 
     def set_graph_replay(self, enabled):
         _check(self.L.blub_fluid_set_graph_replay(self.h, 1 if enabled else 0))

@@ -128,7 +128,7 @@ const char *blub_version(void);
 
 /* ---- scene JSON surface (src/scene/mod.rs:19-43,109-144; src/scene/models.rs:11-46) ------------------------- */
 /* Scene::new + create_fluid_from_config: parses an unchanged blub scene file, creates the fluid, seeds every
- * fluid cube (world / grid_to_world_scale) and sets gravity.  static_objects are parsed and counted but their
+ * fluid cube (world / grid_to_world_scale) and sets gravity.  static_objects are parsed (blub_scene_static_object) but their
  * meshes (git-LFS stubs in the reference checkout) are not voxelized. */
 int blub_scene_load(BlubFluid **out, const char *scene_json_path, int device, void *cuda_stream);
 /* Scene description without creating a fluid: fills dims, max_num_particles, scale, gravity(world), #cubes, #static objects. */
@@ -150,7 +150,7 @@ typedef struct {
     float world_position[3];
     float scale;
     float rotation_angles_deg[3];   /* static Euler angles (cgmath Euler<Deg>) */
-    int32_t shape;                  /* 0 = box with half_extent (model space), 1 = sphere of radius half_extent[0] */
+    int32_t shape;                  /* 0 = box with half_extent (model space), 1 = sphere of radius half_extent[0], 2 = triangle mesh */
     float half_extent[3];
     int32_t has_translation;        /* TranslationAnimation: ping-pong between world_position and target */
     float translation_target[3];
@@ -168,6 +168,39 @@ typedef struct {                    /* what the animation evaluated to (for test
 int blub_solid_voxelize(void *rgba16f_device_ptr, const uint32_t grid_dimension[3], const BlubRigidObject *object, float grid_to_world_scale,
                         const float fluid_world_position[3], double total_simulated_time, double simulation_delta, int clear_first,
                         void *cuda_stream, BlubRigidState *state_out);
+
+/* ---- small device helpers for hosts without CUDA bindings of their own (e.g. the Rust shim of INTEGRATION.md) ----------------- */
+/* the stream the fluid's work is enqueued on (the one given to blub_fluid_create, or the fluid's own): enqueue the voxelization of a
+ * step there and it is ordered before the step without any host synchronisation */
+void *blub_fluid_stream(const BlubFluid *fluid);
+int blub_device_malloc(void **out, size_t bytes, int device);  /* zero-initialised */
+int blub_device_free(void *device_ptr);
+
+/* ---- triangle meshes: the conservative hull voxelizer (src/scene/voxelization.rs:118-157, shader/voxelize/conservative_hull.*) ----
+ * A BlubMesh is the geometry the voxelization pass reads: model-space positions + triangle indices (MeshVertices / MeshIndices,
+ * conservative_hull.vert:16-20) resident on one device.  blub_mesh_load_obj reads a Wavefront OBJ the way the reference does
+ * (tobj::load_obj with triangulate / ignore_points / ignore_lines, src/scene/models.rs:252-262; only `v` and `f` matter here). */
+typedef struct BlubMesh BlubMesh;
+int blub_mesh_create(BlubMesh **out, const float *positions_xyz, uint32_t num_vertices, const uint32_t *indices, uint32_t num_indices,
+                     int device);
+int blub_mesh_load_obj(BlubMesh **out, const char *obj_path, int device);
+void blub_mesh_destroy(BlubMesh *mesh);
+int blub_mesh_info(const BlubMesh *mesh, uint32_t *num_vertices, uint32_t *num_triangles);
+/* Host-only OBJ reader behind blub_mesh_load_obj (no device needed).  Writes at most the given capacities and always reports the full
+ * counts in counts_out = {vertices, indices}: call once with capacities 0 to size the arrays. */
+int blub_obj_read(const char *obj_path, float *positions_xyz, uint32_t capacity_vertices, uint32_t *indices, uint32_t capacity_indices,
+                  uint32_t counts_out[2]);
+/* One draw of SceneVoxelization::update for `mesh` placed and animated by `placement` (its `shape` / `half_extent` are ignored): every
+ * triangle is rasterised conservatively along its dominant axis and marks its hull voxels (+-1 in depth where the depth slope asks
+ * for it) with w = 1 and xyz = ComputeVoxelSpeed.  clear_first != 0 = the clear_texture in front of the first mesh of a step; later
+ * meshes overwrite earlier ones where they overlap, like consecutive draws.  Stream-ordered, deterministic. */
+int blub_solid_voxelize_mesh(void *rgba16f_device_ptr, const uint32_t grid_dimension[3], BlubMesh *mesh, const BlubRigidObject *placement,
+                             float grid_to_world_scale, const float fluid_world_position[3], double total_simulated_time,
+                             double simulation_delta, int clear_first, void *cuda_stream, BlubRigidState *state_out);
+/* static_objects[index] of a scene file: the model path as written (relative to the reference's `models/` directory) and its
+ * placement + animation (shape = 2: mesh).  Returns BLUB_ERR_INVALID_ARGUMENT past the end. */
+int blub_scene_static_object(const char *scene_json_path, uint32_t index, BlubRigidObject *placement_out, char *model_path_out,
+                             size_t model_path_capacity);
 
 /* ---- multi-GPU: z-slab sharding of the pressure solve (the reference is single-GPU) ---------------
  * Rank `rank` of `world` (<= 8) owns nz_owned planes of a global nx x ny x (world * nz_owned) grid; its local grid has 4
