@@ -30,10 +30,57 @@ def scene_path(name):
     return os.path.join(SCENES, name + ".json")
 
 
+# Workloads that carry a moving solid: the scene's fluid + an analytic box written into the solid-voxel
+# volume before every step, as Scene::step does with its meshes (src/scene/mod.rs:192-211).  Box of 24x40x24 cells travelling +-20 cells
+# about the middle of the basin, SmoothStep over 2 s (animation parameters of scenes/#double_dam_wgpulogo_rotating.json:61-79).
+SOLID_WORKLOADS = {
+    "double_dam_box": {"scene": "double_dam",
+                       "solid": {"world_position": [0.44, 0.20, 0.32], "scale": 1.0, "rotation_angles": [0.0, 0.0, 0.0], "shape": "box",
+                                 "half_extent": [0.12, 0.20, 0.12], "translation": {"target": [0.84, 0.20, 0.32], "curve": "SmoothStep", "duration": 2.0}}},
+}
+
+
+def workload_scene(name):
+    return SOLID_WORKLOADS[name]["scene"] if name in SOLID_WORKLOADS else name
+
+
 def workload_desc(name):
-    sc = json.load(open(scene_path(name)))
+    sc = json.load(open(scene_path(workload_scene(name))))
     d = sc["fluid"]["grid_dimension"]
-    return sc, f"{name}: {d['x']}x{d['y']}x{d['z']} grid"
+    extra = " + moving solid box (voxelized every step)" if name in SOLID_WORKLOADS else ""
+    return sc, f"{name}: {d['x']}x{d['y']}x{d['z']} grid{extra}"
+
+
+class SolidStepper:
+    """Scene::step for a workload with a solid: advance the clock, voxelize on the fluid's stream, step the fluid."""
+
+    def __init__(self, fluid, sc, solid, device):
+        import torch
+        d = sc["fluid"]["grid_dimension"]
+        self.fluid, self.solid, self.dims = fluid, solid, (d["x"], d["y"], d["z"])
+        self.scale = sc["fluid"]["grid_to_world_scale"]
+        self.origin = [sc["fluid"]["world_position"][c] for c in "xyz"]
+        self.vol = torch.zeros((d["z"], d["y"], d["x"], 4), dtype=torch.float16, device=f"cuda:{device}")
+        torch.cuda.synchronize()
+        fluid.set_solid_voxels(self.vol.data_ptr())
+        self.stream = torch.cuda.ExternalStream(fluid.stream(), device=f"cuda:{device}")
+        self.t = 0.0
+
+    def step(self, dt):
+        from blub_b200 import fluid as F
+        self.t += dt
+        F.solid_voxelize(self.vol.data_ptr(), self.dims, self.solid, self.scale, self.origin, self.t, dt, cuda_stream=self.fluid.stream())
+        self.fluid.step(dt)
+
+    def time_steps(self, dt, steps):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            self.step(dt)
+        e1.record(self.stream)
+        e1.synchronize()
+        return float(e0.elapsed_time(e1))
 
 
 class ClockSampler:
@@ -166,15 +213,37 @@ def torch_max(x):
     return float(t.item())
 
 
+def oracle_stepper(f, sc, workload):
+    """One Scene::step on the oracle: with a solid workload the box is re-voxelized (NumPy restatement) before every fluid step."""
+    from oracle import oracle as O
+
+    if workload not in SOLID_WORKLOADS:
+        return lambda: f.step(O.DT_120HZ)
+    from oracle import solids as S
+
+    d = sc["fluid"]["grid_dimension"]
+    state = {"t": 0.0}
+
+    def step():
+        state["t"] += O.DT_120HZ
+        vol, _ = S.voxelize(SOLID_WORKLOADS[workload]["solid"], (d["x"], d["y"], d["z"]), sc["fluid"]["grid_to_world_scale"],
+                            [sc["fluid"]["world_position"][c] for c in "xyz"], state["t"], O.DT_120HZ)
+        f.set_voxels(vol)
+        f.step(O.DT_120HZ)
+    return step
+
+
 def cpu_baseline_sample(workload, steps):
     """Oracle (CPU port of the reference's algorithm) timed on this box's host cores on `steps` steps of the workload."""
     from oracle import oracle as O
 
-    f = O.fluid_from_scene(O.load_scene(scene_path(workload)))
-    f.step(O.DT_120HZ)  # first step pays page faults / first-touch; not timed
+    sc = O.load_scene(scene_path(workload_scene(workload)))
+    f = O.fluid_from_scene(sc)
+    step = oracle_stepper(f, sc, workload)
+    step()  # first step pays page faults / first-touch; not timed
     t0 = time.perf_counter()
     for _ in range(steps):
-        f.step(O.DT_120HZ)
+        step()
     t = time.perf_counter() - t0
     cores = os.cpu_count() or 1
     return {"value": round(steps / t, 5), "unit": "steps/s", "cores": cores, "kind": "port",
@@ -190,7 +259,7 @@ def run_reference(args):
     sc, desc = workload_desc(args.workload)
     n = max(1, args.gpus)
     if n == 1:
-        f = O.fluid_from_scene(O.load_scene(scene_path(args.workload)))
+        f = O.fluid_from_scene(O.load_scene(scene_path(workload_scene(args.workload))))
     else:  # the same stacked scene the sharded arm simulates on n GPUs (value = n * steps/s, i.e. slab-steps/s)
         import numpy as np
 
@@ -202,12 +271,13 @@ def run_reference(args):
     # bounded sample: one CPU step of the 256^3 workload takes seconds, so time as many of the K requested steps as fit
     # into the budget (at least one) after at most one untimed step
     budget = float(os.environ.get("BLUB_REF_BUDGET_S", "150"))
+    step = oracle_stepper(f, sc, args.workload) if n == 1 else (lambda: f.step(O.DT_120HZ))
     for _ in range(min(args.warmup, 1)):
-        f.step(O.DT_120HZ)
+        step()
     t0 = time.perf_counter()
     timed = 0
     while timed < args.steps:
-        f.step(O.DT_120HZ)
+        step()
         timed += 1
         if time.perf_counter() - t0 > budget:
             break
@@ -267,9 +337,12 @@ def main():
 
     sc, desc = workload_desc(args.workload)
     dt = F.DT_120HZ
+    has_solid = args.workload in SOLID_WORKLOADS
+    if has_solid and world > 1:
+        args.multi = "replicas"  # the moving-solid workload is not sharded: N independent replicas
     sharded_step = world > 1 and args.multi in ("sharded", "stacked")
     if not sharded_step:
-        fluid = blub_b200.HybridFluid.from_scene(scene_path(args.workload), device=local)
+        fluid = blub_b200.HybridFluid.from_scene(scene_path(workload_scene(args.workload)), device=local)
         npart = fluid.num_particles
         parallelism = "single GPU" if world == 1 else f"{world} independent replicas (one scene per GPU, no exchange)"
     else:
@@ -307,8 +380,10 @@ def main():
         else:
             desc = f"{world} x ({desc}) stacked along z = {d['x']}x{d['y']}x{d['z'] * world} grid"
         parallelism = f"one simulation on {world} z-slabs (P2P halo exchange + particle migration, in-kernel PCG exchange)"
+    stepper = SolidStepper(fluid, sc, SOLID_WORKLOADS[args.workload]["solid"], local) if has_solid else None
+    step = stepper.step if stepper else fluid.step
     for _ in range(max(args.warmup, 3)):
-        fluid.step(dt)
+        step(dt)
     fluid.synchronize()
 
     # ---- device-timed region: K steps between CUDA events on the fluid's stream, barrier + sync on both sides --------
@@ -317,7 +392,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = blub_b200.kernel_launch_count()
-    ms = fluid.time_steps(dt, args.steps)
+    ms = stepper.time_steps(dt, args.steps) if stepper else fluid.time_steps(dt, args.steps)
     launches = blub_b200.kernel_launch_count() - launches0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -330,7 +405,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fluid.step(dt)
+        step(dt)
         fluid.synchronize()
         fluid.update_statistics()
     fluid.synchronize()

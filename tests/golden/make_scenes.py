@@ -40,6 +40,8 @@ SCENES = {
     "dam_256": scene((256, 256, 256), 0.005, 16500000, [((0.0, 0.0, 0.0), (0.64, 0.64, 0.64))]),
     # synthetic C4: 512^3 basin, 510 x 31 x 510 cells -> 64,504,800 particles
     "basin_512": scene((512, 512, 512), 0.01, 65000000, [((0.0, 0.0, 0.0), (5.12, 0.32, 5.12))]),
+    # scenes/double_dam_wgpulogo.json:13-40 without its static object -- 128x64x64, two dams, 1,199,328 particles (config C5's fluid)
+    "double_dam": scene((128, 64, 64), 0.01, 2000000, [((0.0, 0.0, 0.0), (0.32, 0.4, 0.64)), ((0.96, 0.0, 0.0), (1.28, 0.4, 0.64))]),
     # small dam break for per-stage parity (not a reference scene)
     "dam_small": scene((32, 32, 32), 0.01, 40000, [((0.0, 0.0, 0.0), (0.16, 0.2, 0.32))]),
 }

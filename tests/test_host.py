@@ -103,6 +103,9 @@ def test_fixtures_match_reference_scenes():
         ref = json.load(open(f"/root/reference/scenes/{name}.json"))
         mine = json.load(open(util.scene_path(name)))
         assert ref["fluid"] == mine["fluid"] and ref["gravity"] == mine["gravity"], name
+    ref = json.load(open("/root/reference/scenes/double_dam_wgpulogo.json"))  # config C5's fluid, without the LFS-stub mesh
+    mine = json.load(open(util.scene_path("double_dam")))
+    assert ref["fluid"] == mine["fluid"] and ref["gravity"] == mine["gravity"]
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/scenes"), reason="reference checkout not present")
