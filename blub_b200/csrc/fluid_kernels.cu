@@ -401,22 +401,23 @@ __global__ void __launch_bounds__(PT) advect_kernel(GridDim g, const StepParams 
         cy[k] = mixf(vx10, vx11, iz[k]) - mixf(vx00, vx01, iz[k]);
         cz[k] = vxy1 - vxy0;
     }
-    // RK4 confined to the sampled cell, :116-126 (step.{x,y,z} is added to the {X,Y,Z} interpolants of every component)
+    // RK4 confined to the sampled cell, :116-126.  As written (quirk B17): the shader adds the step VECTOR element-wise to vec3s that are
+    // indexed by the velocity component, so component k is re-sampled with all three of its interpolants advanced by step[k].
     float k2[3], k3[3], k4[3], ax[3], ay[3], az[3], st[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) st[k] = dt * 0.5f * nv[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { ax[k] = saturatef(ix[k] + st[0]); ay[k] = saturatef(iy[k] + st[1]); az[k] = saturatef(iz[k] + st[2]); }
+    for (int k = 0; k < 3; ++k) { ax[k] = saturatef(ix[k] + st[k]); ay[k] = saturatef(iy[k] + st[k]); az[k] = saturatef(iz[k] + st[k]); }
     trilerp3(cn, ax, ay, az, k2);
 #pragma unroll
     for (int k = 0; k < 3; ++k) st[k] = dt * 0.5f * k2[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { ax[k] = saturatef(ix[k] + st[0]); ay[k] = saturatef(iy[k] + st[1]); az[k] = saturatef(iz[k] + st[2]); }
+    for (int k = 0; k < 3; ++k) { ax[k] = saturatef(ix[k] + st[k]); ay[k] = saturatef(iy[k] + st[k]); az[k] = saturatef(iz[k] + st[k]); }
     trilerp3(cn, ax, ay, az, k3);
 #pragma unroll
     for (int k = 0; k < 3; ++k) st[k] = dt * k3[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { ax[k] = saturatef(ix[k] + st[0]); ay[k] = saturatef(iy[k] + st[1]); az[k] = saturatef(iz[k] + st[2]); }
+    for (int k = 0; k < 3; ++k) { ax[k] = saturatef(ix[k] + st[k]); ay[k] = saturatef(iy[k] + st[k]); az[k] = saturatef(iz[k] + st[k]); }
     trilerp3(cn, ax, ay, az, k4);
     float mv[3], x1[3];
 #pragma unroll

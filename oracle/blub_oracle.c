@@ -9,7 +9,7 @@
  * environment (no cargo/rustc/Vulkan/shaderc, 258 un-vendored crates, windowed app) and it
  * ships no tests, golden vectors or known-answer fixtures for this path.  This file follows
  * the reference's shaders and host code line by line (citations below, relative to
- * /root/reference) and is pinned only by analytic known-answer tests (tests/test_oracle_kat.py).
+ * /root/reference) and is pinned only by analytic known-answer tests (tests/test_oracle_kat.py, tests/test_transfer_kat.py).
  *
  * Conventions (shader/simulation/hybrid_fluid.glsl:20-23):
  *   marker: SOLID = 0, FLUID = 1, AIR = -1; any out-of-domain texel/image read returns 0.
@@ -31,6 +31,8 @@
  *                      ceil(N / 16384) groups wrote one (pressure_init.comp:27-30), so the last group's partial is dropped
  *                      whenever N is not a multiple of 16384.  Every shipped scene has N % 16384 == 0, where both modes
  *                      coincide (B16).
+ * Followed as written without a switch: the in-cell RK4 of advect_particles.comp:116-125 advances component k's three interpolants by
+ * step[k] (element-wise vec3 addition on component-indexed vectors, B17).
  */
 #include <math.h>
 #include <stdint.h>
@@ -790,16 +792,18 @@ void orc_advect_particles(OrcFluid *f, float dt) {
             cy[k] = mixf(vx10[k], vx11[k], iz[k]) - mixf(vx00[k], vx01[k], iz[k]);
             cz[k] = vxy1[k] - vxy0[k];
         }
-        /* RK4 inside the cell, :116-126.  step.{x,y,z} is added to the {X,Y,Z} interpolant of every component. */
+        /* RK4 inside the cell, :116-126.  AS WRITTEN (found in review): interpolantsX/Y/Z are vec3s indexed by the velocity
+         * COMPONENT and the shader adds the step vector to each of them element-wise (`saturate(interpolantsX + stepK2)`), so component k
+         * is re-sampled at its own interpolants advanced by step[k] along x, y AND z -- not at the point moved by (step.x, step.y, step.z). */
         float k1[3] = {nv[0], nv[1], nv[2]}, k2[3], k3[3], k4[3], ax[3], ay[3], az[3], st[3];
         for (int k = 0; k < 3; ++k) st[k] = dt * 0.5f * k1[k];
-        for (int k = 0; k < 3; ++k) { ax[k] = satf(ix[k] + st[0]); ay[k] = satf(iy[k] + st[1]); az[k] = satf(iz[k] + st[2]); }
+        for (int k = 0; k < 3; ++k) { ax[k] = satf(ix[k] + st[k]); ay[k] = satf(iy[k] + st[k]); az[k] = satf(iz[k] + st[k]); }
         trilerp3(v, ax, ay, az, k2);
         for (int k = 0; k < 3; ++k) st[k] = dt * 0.5f * k2[k];
-        for (int k = 0; k < 3; ++k) { ax[k] = satf(ix[k] + st[0]); ay[k] = satf(iy[k] + st[1]); az[k] = satf(iz[k] + st[2]); }
+        for (int k = 0; k < 3; ++k) { ax[k] = satf(ix[k] + st[k]); ay[k] = satf(iy[k] + st[k]); az[k] = satf(iz[k] + st[k]); }
         trilerp3(v, ax, ay, az, k3);
         for (int k = 0; k < 3; ++k) st[k] = dt * k3[k];
-        for (int k = 0; k < 3; ++k) { ax[k] = satf(ix[k] + st[0]); ay[k] = satf(iy[k] + st[1]); az[k] = satf(iz[k] + st[2]); }
+        for (int k = 0; k < 3; ++k) { ax[k] = satf(ix[k] + st[k]); ay[k] = satf(iy[k] + st[k]); az[k] = satf(iz[k] + st[k]); }
         trilerp3(v, ax, ay, az, k4);
         float mv[3], x1[3];
         for (int k = 0; k < 3; ++k) {
