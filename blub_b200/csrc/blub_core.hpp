@@ -263,6 +263,7 @@ class HybridFluid {
     GridArray<float2> numw_[3];        // P2G accumulators: (sum w*value, sum w) per face
     uint8_t *seg_fluid_ = nullptr, *row_fluid_ = nullptr, *row_near_ = nullptr; // coarse occupancy maps of the marker volume
     int seg_shift_ = 5;
+    uint8_t *face_valid_ = nullptr;  // experimental extrapolation variant (BLUB_EXTRAPOLATE=bytes), else unused
     GridArray<int8_t> marker_;
     uint32_t *cell_count_ = nullptr; // binning: per-cell counters / offsets
     uint32_t *block_sums_ = nullptr;

@@ -12,6 +12,8 @@ struct MarkerFlags {
     uint8_t *row_fluid; // ny * nz entries
     uint8_t *row_near;  // ny * nz entries: row_fluid dilated by [-1, +2] in y and z
     int seg_shift;      // 5 (32-cell segments) or 3 when nx is not a multiple of 32
+    uint8_t *face_valid; // EXPERIMENTAL (BLUB_EXTRAPOLATE=bytes), else null: per cell, bit c = "face c carries a valid velocity"
+                         // (the cell or its +c neighbour is FLUID, extrapolate_velocity.comp:5-10), bit 3 = the cell is FLUID
 };
 
 void launch_p2g(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float4 *const row[3],

@@ -58,6 +58,12 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
     BLUB_CUDA_CHECK(cudaMemset(row_near_, 0, (size_t)ny * nz));
     BLUB_CUDA_CHECK(cudaMemset(seg_fluid_, 0, (size_t)(grid_.n >> seg_shift_)));
     BLUB_CUDA_CHECK(cudaMemset(row_fluid_, 0, (size_t)ny * nz));
+    if (const char *ex = std::getenv("BLUB_EXTRAPOLATE")) {
+        if (std::string(ex) == "bytes") { // opt-in experiment, see extrapolate_bytes_kernel
+            BLUB_CUDA_CHECK(cudaMalloc(&face_valid_, (size_t)grid_.n));
+            BLUB_CUDA_CHECK(cudaMemset(face_valid_, 0, (size_t)grid_.n));
+        }
+    }
     BLUB_CUDA_CHECK(cudaMalloc(&cell_count_, (size_t)grid_.n * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMalloc(&block_sums_, (size_t)(binning_scan_blocks(grid_) + 1024) * sizeof(uint32_t)));
     SolverConfig cfg; // defaults .1 / 32 / 4, hybrid_fluid.rs:253-257
@@ -124,6 +130,7 @@ HybridFluid::~HybridFluid() {
     cudaFree(seg_fluid_);
     cudaFree(row_fluid_);
     cudaFree(row_near_);
+    if (face_valid_) cudaFree(face_valid_);
     cudaFree(block_sums_);
     if (solver_ && solver_->comm.seq) cudaFree(solver_->comm.seq);
     solver_.reset();
@@ -350,7 +357,7 @@ void HybridFluid::upload_step_params(float dt) {
 void HybridFluid::run_stage(int stage, float dt) {
     float *u[3] = {u_[0].ptr, u_[1].ptr, u_[2].ptr};
     float2 *nw[3] = {numw_[0].ptr, numw_[1].ptr, numw_[2].ptr};
-    const MarkerFlags flags = {seg_fluid_, row_fluid_, row_near_, seg_shift_};
+    const MarkerFlags flags = {seg_fluid_, row_fluid_, row_near_, seg_shift_, face_valid_};
     const bool shard = slab_world_ > 1 && solver_->comm.world > 1;
     const uint32_t np = slab_world_ > 1 ? max_num_particles_ : num_particles_; // sharded: the device-side count guards the kernels
     switch (stage) {
