@@ -86,6 +86,7 @@ void rigid_state_at(const BlubRigidObject &o, float grid_to_world_scale, const f
 
 void voxelize_mesh(void *rgba16f, const uint32_t dim[3], BlubMesh &mesh, const BlubRigidObject &o, float grid_to_world_scale, const float fluid_world_position[3],
                    double total_time, double delta, int clear_first, cudaStream_t stream, BlubRigidState *state_out) {
+    BLUB_CUDA_CHECK(cudaSetDevice(mesh.device)); // the volume and the stream must live on the mesh's device
     BlubRigidState st;
     rigid_state_at(o, grid_to_world_scale, fluid_world_position, total_time, delta, st);
     if (state_out) *state_out = st;
