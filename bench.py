@@ -247,7 +247,7 @@ def cpu_baseline_sample(workload, steps):
     t = time.perf_counter() - t0
     cores = os.cpu_count() or 1
     return {"value": round(steps / t, 5), "unit": "steps/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} step(s) of {workload} after 1 untimed step, OpenMP over {cores} host threads (advection and list build serial)"}
+            "sample": f"{steps} step(s) of {workload} after 1 untimed step, OpenMP over {cores} host threads (linked-list builds serial)"}
 
 
 def run_reference(args):

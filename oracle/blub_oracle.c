@@ -745,7 +745,9 @@ static int wall_hit(const OrcFluid *f, const float np_[3], int use_marker) {
 
 void orc_advect_particles(OrcFluid *f, float dt) {
     const int S[3] = {f->nx, f->ny, f->nz};
-    /* sequential: the linked-list rebuild (:175-181) is order dependent */
+    /* Every particle is independent up to the marker / linked-list writes of :175-181, whose result depends on the particle order:
+     * those run in a second, sequential pass over the new positions (identical outcome, the first pass can use all cores). */
+#pragma omp parallel for schedule(static)
     for (uint32_t i = 0; i < f->num_particles; ++i) {
         float x0[3] = {f->pos[4 * (size_t)i], f->pos[4 * (size_t)i + 1], f->pos[4 * (size_t)i + 2]};
         { /* :45-64 "eaten" by a moving wall */
@@ -836,24 +838,25 @@ void orc_advect_particles(OrcFluid *f, float dt) {
                 nv[k] = (dir[k] * maxstep) / dt;
             }
         }
-        { /* :175-181 marker + linked list for the density pass */
-            int x = (int)x1[0], y = (int)x1[1], z = (int)x1[2];
-            if (inb(f, x, y, z)) f->marker[lin(f, x, y, z)] = CELL_FLUID;
-            int dx = (int)(x1[0] - 0.5f), dy = (int)(x1[1] - 0.5f), dz = (int)(x1[2] - 0.5f);
-            uint32_t prev = 0;
-            if (inb(f, dx, dy, dz)) {
-                size_t d = lin(f, dx, dy, dz);
-                prev = f->ll[d];
-                f->ll[d] = i + 1;
-            }
-            *pnext(f, i) = prev - 1u;
-        }
         float *P = &f->pos[4 * (size_t)i];
         P[0] = x1[0]; P[1] = x1[1]; P[2] = x1[2];
         float *rx = &f->row[0][4 * (size_t)i], *ry = &f->row[1][4 * (size_t)i], *rz = &f->row[2][4 * (size_t)i];
         rx[0] = cx[0]; rx[1] = cx[1]; rx[2] = cx[2]; rx[3] = nv[0]; /* :184-188 (B4: Jacobian columns stored as rows) */
         ry[0] = cy[0]; ry[1] = cy[1]; ry[2] = cy[2]; ry[3] = nv[1];
         rz[0] = cz[0]; rz[1] = cz[1]; rz[2] = cz[2]; rz[3] = nv[2];
+    }
+    for (uint32_t i = 0; i < f->num_particles; ++i) { /* :175-181 marker + linked list for the density pass, in particle order */
+        const float *x1 = &f->pos[4 * (size_t)i];
+        int x = (int)x1[0], y = (int)x1[1], z = (int)x1[2];
+        if (inb(f, x, y, z)) f->marker[lin(f, x, y, z)] = CELL_FLUID;
+        int dx = (int)(x1[0] - 0.5f), dy = (int)(x1[1] - 0.5f), dz = (int)(x1[2] - 0.5f);
+        uint32_t prev = 0;
+        if (inb(f, dx, dy, dz)) {
+            size_t d = lin(f, dx, dy, dz);
+            prev = f->ll[d];
+            f->ll[d] = i + 1;
+        }
+        *pnext(f, i) = prev - 1u;
     }
 }
 
