@@ -9,6 +9,9 @@
 // 729-thread groups in lock-step rounds (capped at 12 / 32 entries).  Here particle->grid transfers are scatters
 // (RED.ADD.F32 into num/weight volumes, then one normalisation pass), which needs no lists, has no cap and touches each
 // particle once; binning is a counting sort with a work-efficient scan and ping-pong buffers (no copy-back).
+#include <cstdlib>
+#include <cstring>
+
 #include "fluid_kernels.hpp"
 
 namespace blub {
@@ -82,6 +85,100 @@ __global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepPa
                     // 16.4 M particles): the L2 atomic units are bound by sectors touched, not by instructions.
                     atomicAdd(nw[c] + f, make_float2(w * v, w));
                 }
+    }
+}
+
+// EXPERIMENTAL alternatives (BLUB_SCATTER=aggregate; not the default, not yet measured).  After a re-sort the particles of one cell
+// sit in adjacent lanes and hit the SAME eight faces: the reductions of a warp then serialise in the L2 atomic units.  Here every run
+// of adjacent lanes with the same dual cell first adds its contributions up with shuffles (segmented reduction, log2 steps) and only
+// the first lane of the run issues reductions.  Same pairs, same weights; only the summation order differs.
+template <int NV>
+__device__ __forceinline__ bool segmented_run_sum(int key, float (&v)[NV]) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int prev = __shfl_up_sync(full, key, 1);
+    const bool head = lane == 0 || prev != key;
+    const unsigned heads = __ballot_sync(full, head);
+    const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u)); // run heads in the lanes above this one
+    const int end = above ? __ffs(above) - 1 : 32;                            // first lane that is not part of this lane's run
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool take = lane + o < end;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const float t = __shfl_down_sync(full, v[k], o);
+            if (take) v[k] += t;
+        }
+    }
+    return head;
+}
+
+template <bool MARK>
+__global__ void __launch_bounds__(PT) p2g_scatter_aggregate_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
+                                                                   const float4 *__restrict__ rowx, const float4 *__restrict__ rowy,
+                                                                   const float4 *__restrict__ rowz, float2 *__restrict__ nwx, float2 *__restrict__ nwy,
+                                                                   float2 *__restrict__ nwz, int8_t *__restrict__ marker) {
+    const uint32_t i = blockIdx.x * PT + threadIdx.x;
+    const bool valid = i < params->num_particles; // no early return: every lane takes part in the shuffles
+    float4 p = valid ? pos[i] : make_float4(1.5f, 1.5f, 1.5f, 0.0f);
+    p.x = fminf(fmaxf(p.x, 1.0f), (float)g.nx - 1.0f);
+    p.y = fminf(fmaxf(p.y, 1.0f), (float)g.ny - 1.0f);
+    p.z = fminf(fmaxf(p.z, 1.0f), (float)g.nz - 1.0f);
+    if (MARK && valid) marker[lin(g, min((int)p.x, g.nx - 1), min((int)p.y, g.ny - 1), min((int)p.z, g.nz - 1))] = (int8_t)CELL_FLUID;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 rows[3] = {valid ? rowx[i] : zero, valid ? rowy[i] : zero, valid ? rowz[i] : zero};
+    float2 *const nw[3] = {nwx, nwy, nwz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float ox = c == 0 ? 1.0f : 0.5f, oy = c == 1 ? 1.0f : 0.5f, oz = c == 2 ? 1.0f : 0.5f;
+        const int dx = (int)(p.x - ox), dy = (int)(p.y - oy), dz = (int)(p.z - oz);
+        const float qx = (float)dx + ox, qy = (float)dy + oy, qz = (float)dz + oz;
+        const float4 r = rows[c];
+        const float tx[2] = {qx - p.x, qx + 1.0f - p.x}, ty[2] = {qy - p.y, qy + 1.0f - p.y}, tz[2] = {qz - p.z, qz + 1.0f - p.z};
+        const float wxs[2] = {saturatef(1.0f - fabsf(tx[0])), saturatef(1.0f - fabsf(tx[1]))};
+        const float wys[2] = {saturatef(1.0f - fabsf(ty[0])), saturatef(1.0f - fabsf(ty[1]))};
+        const float wzs[2] = {saturatef(1.0f - fabsf(tz[0])), saturatef(1.0f - fabsf(tz[1]))};
+        const int base = lin(g, dx, dy, dz);
+        float acc[16]; // (sum w * value, sum w) of the eight faces
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int ox_ = k & 1, oy_ = (k >> 1) & 1, oz_ = k >> 2;
+            const float w = valid ? wxs[ox_] * wys[oy_] * wzs[oz_] : 0.0f;
+            const float v = r.x * tx[ox_] + r.y * ty[oy_] + r.z * tz[oz_] + r.w;
+            acc[2 * k] = w > 0.0f ? w * v : 0.0f;
+            acc[2 * k + 1] = w > 0.0f ? w : 0.0f;
+        }
+        const bool head = segmented_run_sum<16>(valid ? base : -1 - (int)(threadIdx.x & 31), acc);
+        if (head && valid) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (acc[2 * k + 1] > 0.0f) atomicAdd(nw[c] + base + (k & 1) + ((k >> 1) & 1) * g.sy + (k >> 2) * g.sz, make_float2(acc[2 * k], acc[2 * k + 1]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PT) density_scatter_aggregate_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
+                                                                       float *__restrict__ density) {
+    const uint32_t i = blockIdx.x * PT + threadIdx.x;
+    const bool valid = i < params->num_particles;
+    float4 p = valid ? pos[i] : make_float4(1.5f, 1.5f, 1.5f, 0.0f);
+    p.x = fminf(fmaxf(p.x, 0.5f), (float)g.nx - 1.0f);
+    p.y = fminf(fmaxf(p.y, 0.5f), (float)g.ny - 1.0f);
+    p.z = fminf(fmaxf(p.z, 0.5f), (float)g.nz - 1.0f);
+    const int dx = (int)(p.x - 0.5f), dy = (int)(p.y - 0.5f), dz = (int)(p.z - 0.5f);
+    const float qx = (float)dx + 0.5f, qy = (float)dy + 0.5f, qz = (float)dz + 0.5f;
+    const float wx[2] = {saturatef(1.0f - fabsf(qx - p.x)), saturatef(1.0f - fabsf(qx + 1.0f - p.x))};
+    const float wy[2] = {saturatef(1.0f - fabsf(qy - p.y)), saturatef(1.0f - fabsf(qy + 1.0f - p.y))};
+    const float wz[2] = {saturatef(1.0f - fabsf(qz - p.z)), saturatef(1.0f - fabsf(qz + 1.0f - p.z))};
+    const int base = lin(g, dx, dy, dz);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = valid ? wx[k & 1] * wy[(k >> 1) & 1] * wz[k >> 2] : 0.0f;
+    const bool head = segmented_run_sum<8>(valid ? base : -1 - (int)(threadIdx.x & 31), acc);
+    if (head && valid) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (acc[k] > 0.0f) atomicAdd(density + base + (k & 1) + ((k >> 1) & 1) * g.sy + (k >> 2) * g.sz, acc[k]);
     }
 }
 
@@ -732,6 +829,13 @@ inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 
 } // namespace
 
 // ------------------------------------------------------------------------------------------------ launchers
+// opt-in experiment (see p2g_scatter_aggregate_kernel); read when a launch is issued (a captured step graph keeps the choice it was
+// captured with)
+static bool scatter_aggregate() {
+    const char *e = std::getenv("BLUB_SCATTER");
+    return e && std::strcmp(e, "aggregate") == 0;
+}
+
 static void run_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, const uint2 *vox, const MarkerFlags &flags) {
     BLUB_CUDA_CHECK(cudaMemsetAsync(flags.row_fluid, 0, (size_t)g.ny * g.nz, st));
     BLUB_LAUNCH(boundary_marker_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, vox, flags.seg_fluid, flags.row_fluid, 1 << flags.seg_shift);
@@ -744,7 +848,10 @@ void launch_p2g_scatter(cudaStream_t st, const GridDim &g, const StepParams *par
     // transfer_clear.comp: marker <- AIR; the (num, weight) volumes replace the linked-list head volume
     BLUB_CUDA_CHECK(cudaMemsetAsync(marker, 0xFF, (size_t)g.n, st));
     for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(nw[c], 0, (size_t)g.n * sizeof(float2), st));
-    if (np_upper > 0)
+    if (np_upper == 0) return;
+    if (scatter_aggregate())
+        BLUB_LAUNCH(p2g_scatter_aggregate_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
+    else
         BLUB_LAUNCH(p2g_scatter_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
 }
 
@@ -798,7 +905,9 @@ void launch_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, c
 
 void launch_density_scatter(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float *density) {
     BLUB_CUDA_CHECK(cudaMemsetAsync(density, 0, (size_t)g.n * sizeof(float), st));
-    if (np_upper > 0) BLUB_LAUNCH(density_scatter_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, density);
+    if (np_upper == 0) return;
+    if (scatter_aggregate()) BLUB_LAUNCH(density_scatter_aggregate_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, density);
+    else BLUB_LAUNCH(density_scatter_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, density);
 }
 
 void launch_density_finish(cudaStream_t st, const GridDim &g, const StepParams *params, const int8_t *marker, const float *density, float *rhs) {

@@ -44,3 +44,42 @@ def test_byte_mask_extrapolation_is_bit_identical():
         assert np.array_equal(out["default"][c], out["bytes"][c])
         changed += int((out["default"][c] != u[c]).sum())
     assert changed > 1000
+
+
+def test_warp_aggregated_scatters_match_the_default():
+    """BLUB_SCATTER=aggregate: same (face, particle) pairs and weights, summed per run of equal dual cells before the reductions."""
+    import blub_b200
+    from blub_b200 import fluid as F
+    from tests import util
+    from tests.util import grid_close
+
+    results = {}
+    rng = np.random.default_rng(11)
+    rows = None
+    for mode in ("default", "aggregate"):
+        os.environ.pop("BLUB_SCATTER", None)
+        f = blub_b200.HybridFluid.from_scene(util.scene_path("dam_small"))
+        f.set_rebin_frequency(0)
+        f.set_graph_replay(False)
+        pos = f.download_particles().copy()
+        if rows is None:
+            rows = [rng.normal(0, 3.0, pos.shape).astype(np.float32) for _ in range(3)]
+            extra = pos.copy()  # an unsorted tail: the same particles again, shuffled
+            rng.shuffle(extra)
+        f.set_particles(pos, *rows)
+        if mode == "aggregate":
+            os.environ["BLUB_SCATTER"] = "aggregate"
+        try:
+            f.step_stages(DT, 0, 1)
+            u = [f.download_grid(t) for t in (F.TAP_UX, F.TAP_UY, F.TAP_UZ)]
+            m = f.download_grid(F.TAP_MARKER)
+            f.step_stages(DT, 9, 10)
+            rhs = f.download_grid(F.TAP_RESIDUAL)
+        finally:
+            os.environ.pop("BLUB_SCATTER", None)
+        results[mode] = (u, m, rhs)
+    assert np.array_equal(results["default"][1], results["aggregate"][1])
+    fl = results["default"][1] == O.FLUID
+    for c in range(3):
+        grid_close(results["default"][0][c], results["aggregate"][0][c], f"P2G u[{c}]", rel=1e-5, abs_=1e-5, mask=util.fluid_adjacent_faces(results["default"][1], c))
+    grid_close(results["default"][2], results["aggregate"][2], "density rhs", rel=1e-5, abs_=1e-3, mask=fl)
