@@ -64,8 +64,6 @@ def test_warp_aggregated_scatters_match_the_default():
         pos = f.download_particles().copy()
         if rows is None:
             rows = [rng.normal(0, 3.0, pos.shape).astype(np.float32) for _ in range(3)]
-            extra = pos.copy()  # an unsorted tail: the same particles again, shuffled
-            rng.shuffle(extra)
         f.set_particles(pos, *rows)
         if mode == "aggregate":
             os.environ["BLUB_SCATTER"] = "aggregate"
