@@ -16,6 +16,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # Duration::from_nanos(1e9 / 120).as_secs_f32() (simulation_controller.rs:33-39)
 DT_120HZ = float(np.float32(8333333e-9))
 
+# the 14 stages of one step, in the order of HybridFluid::step (hybrid_fluid.rs:770-977); indices for step_stages / step_timed
+STAGES = [
+    "p2g", "divergence_compute", "solve_velocity", "binning", "divergence_remove", "extrapolate",
+    "transfer_clear", "advect", "set_boundary_marker", "density_gather_error", "solve_density",
+    "position_change", "extrapolate2", "correct_particles",
+]
 TAP_POS, TAP_VX, TAP_VY, TAP_VZ, TAP_UX, TAP_UY, TAP_UZ, TAP_MARKER, TAP_P_VEL, TAP_P_DEN, TAP_RESIDUAL = range(11)
 
 BLUB_OK = 0

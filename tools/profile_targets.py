@@ -27,7 +27,7 @@ elif mode == "stages_sharded":
     import threading
 
     world = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-    from oracle.oracle import STAGES
+    STAGES = F.STAGES
     n, cap = 256, 33000000
     for a in range(world):
         for b in range(world):
@@ -60,7 +60,7 @@ elif mode == "stages":
     scene = sys.argv[2] if len(sys.argv) > 2 else "dam_256"
     checkpoints = [int(a) for a in sys.argv[3:]] or [3]
     f = blub_b200.HybridFluid.from_scene(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".json"))
-    from oracle.oracle import STAGES
+    STAGES = F.STAGES
     done, cols, reps = 0, [], 3
     for cp in checkpoints:
         while done < cp:
