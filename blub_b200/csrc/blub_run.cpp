@@ -9,6 +9,9 @@
 //                  hybrid_fluid.rs:780-973)
 //   --dump FILE    particle positions (float32 x,y,z,pad) for an external viewer -- the renderer hand-off
 //                  (hybrid_fluid.rs:351-369) without wgpu
+//   --record FPS PREFIX   the controller's "recording with fixed frame length" (simulation_controller.rs:80-82,174-176): the render
+//                  clock advances by 1 / FPS per frame, the simulation runs the steps that belong to the frame (Timer::simulation_frame_loop),
+//                  and instead of a screenshot the particle positions are written to PREFIX00000.f32, PREFIX00001.f32, ...
 //   --models DIR   where the scene's static_objects find their OBJ files (the reference reads `models/<model>`,
 //                  src/scene/models.rs:253).  Every step then runs Scene::step's order (src/scene/mod.rs:192-211): animate the
 //                  models at the already advanced simulation time, voxelize their hulls, step the fluid.
@@ -36,13 +39,14 @@ static void die(const char *what) {
 int main(int argc, char **argv) {
     if (argc < 2) {
         std::fprintf(stderr, "usage: blub_run scene.json [--steps N] [--batch 16] [--hz 120] [--device 0] [--no-graph]\n"
-                             "                [--stats out.json] [--trace out.json] [--dump particles.f32] [--models DIR]\n");
+                             "                [--stats out.json] [--trace out.json] [--dump particles.f32] [--models DIR] [--record FPS PREFIX]\n");
         return 2;
     }
     const char *scene = argv[1];
     int steps = 160, batch = 16, device = 0, graph = 1;
     long hz = 120;
-    std::string stats_path, trace_path, dump_path, models_dir = "models";
+    std::string stats_path, trace_path, dump_path, models_dir = "models", record_prefix;
+    double record_fps = 0.0;
     for (int i = 2; i < argc; ++i) {
         auto next = [&](const char *flag) -> const char * {
             if (i + 1 >= argc) { std::fprintf(stderr, "blub_run: %s needs a value\n", flag); std::exit(2); }
@@ -57,11 +61,14 @@ int main(int argc, char **argv) {
         else if (!std::strcmp(argv[i], "--trace")) trace_path = next("--trace");
         else if (!std::strcmp(argv[i], "--dump")) dump_path = next("--dump");
         else if (!std::strcmp(argv[i], "--models")) models_dir = next("--models");
+        else if (!std::strcmp(argv[i], "--record")) { record_fps = std::atof(next("--record")); record_prefix = next("--record"); }
         else { std::fprintf(stderr, "blub_run: unknown option %s\n", argv[i]); return 2; }
     }
     if (steps < 1 || batch < 1 || hz < 1) { std::fprintf(stderr, "blub_run: bad --steps/--batch/--hz\n"); return 2; }
     // delta_from_steps_per_second: Duration::from_nanos(1e9 / hz), then as_secs_f32 (simulation_controller.rs:33-35)
-    const double dt = (double)(float)((double)(1000000000L / hz) * 1e-9);
+    const uint64_t dt_ns = blub_simulation_delta_ns((uint64_t)hz);
+    const double dt = (double)blub_duration_as_secs_f32(dt_ns);
+    if (!record_prefix.empty() && !(record_fps > 0.0)) { std::fprintf(stderr, "blub_run: bad --record FPS\n"); return 2; }
 
     BlubSceneInfo info;
     if (blub_scene_info(scene, &info)) die("cannot read scene");
@@ -91,9 +98,10 @@ int main(int argc, char **argv) {
         if (blub_device_malloc(&voxels, cells * 8, device)) die("cannot allocate the voxel volume");
         if (blub_fluid_set_solid_voxels(fluid, voxels)) die("set_solid_voxels failed");
     }
-    double simulated = 0.0; // Timer::total_simulated_time, advanced BEFORE the step it belongs to (src/timer.rs:122-124)
+    uint64_t simulated_ns = 0, rendered_ns = 0; // Timer::total_simulated_time / total_rendered_time
     auto scene_step = [&]() {
-        simulated += dt;
+        simulated_ns += dt_ns; // advanced BEFORE the step it belongs to (src/timer.rs:122-124)
+        const double simulated = (double)blub_duration_as_secs_f32(simulated_ns);
         for (size_t k = 0; k < solids.size(); ++k)
             if (blub_solid_voxelize_mesh(voxels, info.grid_dimension, solids[k].mesh, &solids[k].placement, info.grid_to_world_scale, info.world_position,
                                          simulated, dt, k == 0, blub_fluid_stream(fluid), nullptr))
@@ -101,8 +109,35 @@ int main(int argc, char **argv) {
         if (blub_fluid_step(fluid, dt)) die("step failed");
     };
 
+    auto write_particles = [&](const std::string &path) {
+        const uint32_t n = blub_fluid_num_particles(fluid);
+        std::vector<float> pos((size_t)n * 4);
+        if (n && blub_fluid_download(fluid, BLUB_TAP_PARTICLE_POS, pos.data(), pos.size() * sizeof(float))) die("download failed");
+        FILE *f = std::fopen(path.c_str(), "wb");
+        if (!f) { std::perror("blub_run: cannot write particles"); std::exit(1); }
+        std::fwrite(pos.data(), sizeof(float), pos.size(), f);
+        std::fclose(f);
+        return n;
+    };
+
     const auto t0 = std::chrono::steady_clock::now();
     int done = 0;
+    if (!record_prefix.empty()) { // RecordingWithFixedFrameLength: one frame = 1 / FPS on the render clock
+        const uint64_t frame_ns = (uint64_t)(1e9 / record_fps); // Duration::from_secs_f64(1.0 / fps), truncated to nanoseconds
+        uint64_t clock_ns = 0; // the Timer's own simulation clock; scene_step keeps the same count in simulated_ns
+        for (int frame = 0; done < steps; ++frame) {
+            uint32_t n = blub_timer_steps_in_frame(&rendered_ns, &clock_ns, frame_ns, dt_ns);
+            if ((int)n > steps - done) n = (uint32_t)(steps - done);
+            for (uint32_t k = 0; k < n; ++k) scene_step();
+            if (blub_fluid_synchronize(fluid)) die("synchronize failed");
+            blub_fluid_update_statistics(fluid);
+            done += (int)n;
+            char name[32];
+            std::snprintf(name, sizeof(name), "%05d.f32", frame);
+            write_particles(record_prefix + name);
+            std::printf("frame %d: %u step(s), simulated %.6f s\n", frame, n, (double)blub_duration_as_secs_f32(simulated_ns));
+        }
+    }
     while (done < steps) { // MAX_FAST_FORWARD_SIMULATION_BATCH_SIZE = 16, then wait for the GPU
         const int n = steps - done < batch ? steps - done : batch;
         for (int k = 0; k < n; ++k) scene_step();
@@ -146,13 +181,7 @@ int main(int argc, char **argv) {
         std::fclose(f);
     }
     if (!dump_path.empty()) {
-        const uint32_t n = blub_fluid_num_particles(fluid);
-        std::vector<float> pos((size_t)n * 4);
-        if (n && blub_fluid_download(fluid, BLUB_TAP_PARTICLE_POS, pos.data(), pos.size() * sizeof(float))) die("download failed");
-        FILE *f = std::fopen(dump_path.c_str(), "wb");
-        if (!f) { std::perror("blub_run: --dump"); return 1; }
-        std::fwrite(pos.data(), sizeof(float), pos.size(), f);
-        std::fclose(f);
+        const uint32_t n = write_particles(dump_path);
         std::printf("wrote %u particles (float32 x y z pad, grid units; world = grid * %g + (%g, %g, %g)) to %s\n", n, info.grid_to_world_scale,
                     info.world_position[0], info.world_position[1], info.world_position[2], dump_path.c_str());
     }

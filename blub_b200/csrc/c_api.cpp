@@ -119,6 +119,24 @@ int blub_solid_voxelize(void *rgba16f, const uint32_t dim[3], const BlubRigidObj
     });
 }
 
+uint64_t blub_simulation_delta_ns(uint64_t steps_per_second) { return steps_per_second ? 1000ull * 1000ull * 1000ull / steps_per_second : 0; }
+
+float blub_duration_as_secs_f32(uint64_t ns) { // core::time::Duration::as_secs_f32
+    return (float)(ns / 1000000000ull) + (float)(uint32_t)(ns % 1000000000ull) / 1000000000.0f;
+}
+
+uint32_t blub_timer_steps_in_frame(uint64_t *total_rendered_ns, uint64_t *total_simulated_ns, uint64_t frame_delta_ns, uint64_t simulation_delta_ns) {
+    if (!total_rendered_ns || !total_simulated_ns || simulation_delta_ns == 0) return 0;
+    *total_rendered_ns += frame_delta_ns; // force_frame_delta on a fresh frame, timer.rs:70-74
+    uint32_t steps = 0;
+    // simulation_frame_loop, timer.rs:94-126: "simulation time shouldn't advance faster than render time"
+    while (*total_rendered_ns >= *total_simulated_ns && *total_rendered_ns - *total_simulated_ns >= simulation_delta_ns) {
+        *total_simulated_ns += simulation_delta_ns;
+        ++steps;
+    }
+    return steps;
+}
+
 void *blub_fluid_stream(const BlubFluid *fluid) { return fluid ? static_cast<void *>(fluid->impl->stream()) : nullptr; }
 
 int blub_device_malloc(void **out, size_t bytes, int device) {

@@ -117,6 +117,9 @@ def lib():
         "blub_fluid_slab_error": (C.c_int, [vp]),
         "blub_solid_voxelize": (C.c_int, [vp, C.POINTER(u32), C.POINTER(RigidObject), C.c_float, f3, C.c_double, C.c_double, C.c_int, vp,
                                           C.POINTER(RigidState)]),
+        "blub_simulation_delta_ns": (C.c_uint64, [C.c_uint64]),
+        "blub_duration_as_secs_f32": (C.c_float, [C.c_uint64]),
+        "blub_timer_steps_in_frame": (u32, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64]),
         "blub_fluid_stream": (vp, [vp]),
         "blub_device_malloc": (C.c_int, [C.POINTER(vp), C.c_size_t, C.c_int]),
         "blub_device_free": (C.c_int, [vp]),

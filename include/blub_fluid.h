@@ -169,6 +169,16 @@ int blub_solid_voxelize(void *rgba16f_device_ptr, const uint32_t grid_dimension[
                         const float fluid_world_position[3], double total_simulated_time, double simulation_delta, int clear_first,
                         void *cuda_stream, BlubRigidState *state_out);
 
+/* ---- simulation clock (src/timer.rs:18-36,94-126, src/simulation_controller.rs:33-35): integer nanoseconds, host only ------------- */
+/* Duration::from_nanos(1e9 / steps_per_second): the simulation delta of the controller (120 Hz -> 8,333,333 ns) */
+uint64_t blub_simulation_delta_ns(uint64_t steps_per_second);
+/* Duration::as_secs_f32: what the shaders / the model animation receive as time */
+float blub_duration_as_secs_f32(uint64_t nanoseconds);
+/* One render frame of `frame_delta_ns` on the render clock (Timer::force_frame_delta as used by recording and fast forward), then
+ * Timer::simulation_frame_loop until the simulation has caught up: returns how many simulation steps belong to this frame and
+ * advances both clocks.  (The realtime mode's step dropping needs wall-clock frame times and is not part of a headless run.) */
+uint32_t blub_timer_steps_in_frame(uint64_t *total_rendered_ns, uint64_t *total_simulated_ns, uint64_t frame_delta_ns, uint64_t simulation_delta_ns);
+
 /* ---- small device helpers for hosts without CUDA bindings of their own (e.g. the Rust shim of INTEGRATION.md) ----------------- */
 /* the stream the fluid's work is enqueued on (the one given to blub_fluid_create, or the fluid's own): enqueue the voxelization of a
  * step there and it is ordered before the step without any host synchronisation */

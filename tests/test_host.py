@@ -126,3 +126,23 @@ def test_oracle_scene_seeding_counts():
     f = util.oracle_from_scene("single_cell_debug")
     assert f.num_particles == 8
     assert (np.floor(f.particles()[:, :3]) == [31, 31, 63]).all()
+
+
+def test_simulation_clock_matches_the_timer_arithmetic():
+    """src/timer.rs:94-126 + simulation_controller.rs:33-35 in integer nanoseconds (host-only helpers of the C ABI)."""
+    import ctypes as C
+    from blub_b200 import fluid as F
+
+    L = F.lib()
+    dt_ns = L.blub_simulation_delta_ns(120)
+    assert dt_ns == 8333333
+    assert L.blub_duration_as_secs_f32(dt_ns) == np.float32(F.DT_120HZ)  # the dt every step is given (SURVEY B14)
+    assert L.blub_duration_as_secs_f32(3 * 10 ** 9 + 500_000_000) == np.float32(3.5)
+    rendered, simulated = C.c_uint64(0), C.c_uint64(0)
+    frame = int(1e9 / 60)  # Duration::from_secs_f64(1 / 60)
+    per_frame = [L.blub_timer_steps_in_frame(C.byref(rendered), C.byref(simulated), frame, dt_ns) for _ in range(60)]
+    assert per_frame == [2] * 60 and simulated.value == 120 * dt_ns <= rendered.value
+    rendered, simulated = C.c_uint64(0), C.c_uint64(0)
+    per_frame = [L.blub_timer_steps_in_frame(C.byref(rendered), C.byref(simulated), 20_000_000, dt_ns) for _ in range(50)]  # 50 fps
+    assert set(per_frame) == {2, 3} and sum(per_frame) == 120 and per_frame[:5] == [2, 2, 3, 2, 3]
+    assert rendered.value - simulated.value < dt_ns  # never ahead of the render clock, never a full step behind
