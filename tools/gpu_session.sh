@@ -1,0 +1,43 @@
+#!/bin/bash
+# One gpurun call, many answers: every call costs 1.5-3 minutes of box time before the command even starts, so measurements are
+# batched.  Usage (from the repository root, on the GPU box):
+#     bash tools/gpu_session.sh [tests] [experimental] [timeline] [bench] [launches] [ncu] [blubrun]
+# Everything lands in gpurun_out/session_*.{txt,json,csv}; nothing here is a bench number unless it comes from bench.py outside ncu.
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+want() { [[ " $ARGS " == *" $1 "* ]]; }
+ARGS="${*:-tests timeline bench}"
+
+if want tests; then
+    timeout 300 python -m pytest tests -m gpu -q --tb=short 2>&1 | grep -v "^$" | tail -25 > $OUT/session_tests.txt
+    tail -3 $OUT/session_tests.txt
+fi
+if want experimental; then  # the opt-in variants must first reproduce the default kernels
+    BLUB_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_zz_experimental.py -m gpu -q --tb=short 2>&1 | grep -v "^$" | tail -25 > $OUT/session_experimental.txt
+    tail -3 $OUT/session_experimental.txt
+fi
+if want timeline; then      # stage times over a dam break: default, then each opt-in variant
+    python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_default.txt 2>&1
+    BLUB_EXTRAPOLATE=bytes python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_extrapolate_bytes.txt 2>&1
+    BLUB_SCATTER=aggregate python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_scatter_aggregate.txt 2>&1
+    for f in default extrapolate_bytes scatter_aggregate; do echo "== $f"; grep -E "after|p2g|extrapolate |density_gather|total" $OUT/session_timeline_$f.txt; done
+fi
+if want bench; then
+    timeout 400 python bench.py --steps 100 --warmup 10 > $OUT/session_bench.json 2> $OUT/session_bench.err
+    head -c 400 $OUT/session_bench.json; echo
+fi
+if want launches; then      # the launch list of the bench command itself (shares only: ncu serialises and runs cold)
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/session_launches.csv \
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-roofline --no-scaling-reference > $OUT/session_launches.log 2>&1
+    python tools/summarize_ncu.py launches $OUT/session_launches.csv > $OUT/session_launches.md 2>&1; head -30 $OUT/session_launches.md
+fi
+if want ncu; then           # one full capture of the PCG kernel on the roofline microbench
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:pcg_solve_persistent -c 1 -o $OUT/session_pcg \
+        python tools/profile_targets.py pcg 256 1 > $OUT/session_ncu.log 2>&1
+    ls -la $OUT/session_pcg.ncu-rep
+fi
+if want blubrun; then
+    ./blub_b200/blub_run tests/golden/scenes/dam_halfhalf.json --steps 320 --stats $OUT/session_run_stats.json --trace $OUT/session_run_trace.json > $OUT/session_run.txt 2>&1
+    tail -2 $OUT/session_run.txt
+fi
