@@ -503,6 +503,7 @@ int blub_fluid_set_solver_path(BlubFluid *fluid, int persistent) {
     fluid->impl->solver().use_tma = persistent == 2;
     fluid->impl->solver().use_tma2 = persistent == 3;
     fluid->impl->solver().use_dense = persistent == 4;
+    fluid->impl->solver().use_brick = persistent == 5;
     if (persistent == 3 && !fluid->impl->solver().tma2_available()) return fail(BLUB_ERR_INVALID_ARGUMENT, "double-buffered TMA solver needs nx % 128 == 0 and cooperative launch");
     fluid->impl->invalidate_graphs();
     if (persistent == 2 && !fluid->impl->solver().tma_available()) return fail(BLUB_ERR_INVALID_ARGUMENT, "TMA solver needs nx % 128 == 0 and cooperative launch");

@@ -532,6 +532,17 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_search_kernel(GridDim g, Tile
 // stop at once instead of running out a recorded launch list.  Blocks walk the compacted list of active tiles with a
 // fixed stride, so a tile is processed by the same SM in every phase.  24 B/cell/iteration of DRAM traffic at most
 // (A: r, s, code in + s' out = 13; B: p, r, s', code in + p, r out = 21 ... minus what stays in the 126 MB L2).
+struct BrickMap {
+    int bricks_x, bricks_y, bricks_z, nbricks;
+};
+BrickMap make_brickmap(const GridDim &g) {
+    BrickMap b;
+    b.bricks_x = g.nx / 32;
+    b.bricks_y = g.ny / 4;
+    b.bricks_z = g.nz / PCG_TZ;
+    b.nbricks = b.bricks_x * b.bricks_y * b.bricks_z;
+    return b;
+}
 struct PcgSolveArgs {
     GridDim g;
     TileMap t;
@@ -539,6 +550,9 @@ struct PcgSolveArgs {
     const int *tile_list;   // compacted active tiles
     const int *tile_list_flagged; // the same with bit 30 set on tiles that are at least 3/4 full (pcg_prepare_kernel)
     const int *num_active;
+    const int *brick_list_flagged; // experimental brick solver: compacted 32x4x4 bricks (bit 30 = dense), see pcg_solve_brick_kernel
+    const int *num_active_bricks;
+    BrickMap bricks;
     float *p, *r, *s0, *s1;
     PcgScalars *scal;
     float *partials;        // 3 x gridDim.x
@@ -917,6 +931,170 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
     }
 }
 #undef PCG_FOR_EACH_TILE
+
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (solver path 5, BLUB_PCG=brick; not the default, not yet run on a GPU): the persistent solver with a finer work unit.
+// Same phases, barriers, reductions, tile bodies and multi-GPU protocol as pcg_solve_persistent_kernel; what changes is who works on
+// what: one WARP takes a brick of 32 x 4 x 4 cells (lane = 8 quads x 4 rows, marching 4 planes) from a compacted brick list.  A dam
+// break fills 35-50 % of such bricks where it touches 64-88 % of the 128 x 8 x 4 tiles, and thousands of bricks spread over 4736 warps
+// without the pass quantisation of hundreds of tiles over 592 blocks (profiles/r01_v12_work_units_oracle_256x128x128.txt).  The tile
+// bodies only assume that lane - 1 / lane + 1 hold the x-adjacent quads unless the lane is `first` / `last`: true inside each 8-lane
+// row of a brick.  Needs nx % 32 == 0.
+__device__ __forceinline__ TileCtx brick_ctx_id(const GridDim &g, const BrickMap &b, int brick) {
+    const int bx = brick % b.bricks_x, rest = brick / b.bricks_x, by = rest % b.bricks_y, bz = rest / b.bricks_y;
+    const int lane = linear_tid() & 31, lx = lane & 7, ly = lane >> 3;
+    TileCtx c;
+    c.tile = brick;
+    c.tz = bz;
+    c.valid = true; // nx % 32 == 0, ny % 4 == 0, nz % 4 == 0: bricks are never ragged
+    c.first = lx == 0;
+    c.last = lx == 7;
+    c.i = ((bz * PCG_TZ) * g.ny + by * 4 + ly) * g.nx + bx * 32 + 4 * lx;
+    return c;
+}
+// per brick: 0 = no fluid, 1 = some, 2 = at least 3/4 of its (thread, plane) units hold fluid (runs the branch-free body).  One warp per brick.
+__global__ void __launch_bounds__(PCG_THREADS) pcg_brick_flags_kernel(GridDim g, BrickMap b, const uint8_t *__restrict__ codes, uint8_t *__restrict__ brick_active) {
+    const int brick = blockIdx.x * (PCG_THREADS / 32) + (linear_tid() >> 5);
+    if (brick >= b.nbricks) return;
+    const TileCtx c = brick_ctx_id(g, b, brick);
+    int units = 0;
+#pragma unroll
+    for (int k = 0; k < PCG_TZ; ++k) units += ldcw(codes + c.i + k * g.sz) != 0u ? 1 : 0;
+    units = (int)__reduce_add_sync(0xffffffffu, (unsigned)units);
+    if ((linear_tid() & 31) == 0) brick_active[brick] = (uint8_t)(units == 0 ? 0 : (4 * units >= 3 * 32 * PCG_TZ ? 2 : 1));
+}
+
+#define PCG_FOR_EACH_BRICK(tile)                                                                                                         \
+    for (int li_ = warp_id, tile = li_ < nact ? a.brick_list_flagged[li_] : 0, next_ = 0; li_ < nact; li_ += num_warps, tile = next_)  \
+        if ((next_ = li_ + num_warps < nact ? a.brick_list_flagged[li_ + num_warps] : 0), true)
+
+__global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_brick_kernel(PcgSolveArgs a) {
+    constexpr bool SKIP = true;
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float sh[PCG_THREADS / 32];
+    __shared__ double shd;
+    __shared__ float shf;
+    __shared__ double sh_csum[SLAB_MAX_WORLD];
+    __shared__ float sh_cmax[SLAB_MAX_WORLD];
+    __shared__ int sh_dead;
+    const TileMap t = a.t;
+    const SlabComm &cm_ = a.comm;
+    const bool sharded = cm_.world > 1;
+    const int nact = *a.num_active_bricks;
+    const int warp_id = blockIdx.x * (PCG_THREADS / 32) + (linear_tid() >> 5), num_warps = gridDim.x * (PCG_THREADS / 32);
+    float *psumA = a.partials, *psumB = a.partials + gridDim.x, *pmax = a.partials + 2 * gridDim.x;
+    TileEnv e;
+    e.g = a.g;
+    e.codes = a.codes;
+    e.sharded = sharded;
+    // slab geometry: tiles tz_first..tz_last are owned; the planes just outside are ghost planes fed by the neighbours
+    e.tz_first = cm_.halo / PCG_TZ;
+    e.tz_last = t.tiles_z - 1 - cm_.halo / PCG_TZ;
+    e.push = cm_.owned_nz * a.g.sz; // index distance between an owned boundary plane and its image in the neighbour
+    e.peer_r_lo = cm_.peer_r[0];
+    e.peer_r_hi = cm_.peer_r[1];
+    unsigned seq = 0;
+    if (linear_tid() == 0) sh_dead = 0;
+    if (sharded) seq = *cm_.seq;
+    __syncthreads();
+    if (sharded) slab_start_handshake(cm_, seq, sh_csum, sh_cmax, &sh_dead);
+
+    // ---- init: r <- b - A p, sigma <- z.r (pressure_init.comp:45-83, pressure_solver.rs:625-649); s stays 0
+    float acc = 0.0f;
+    PCG_FOR_EACH_BRICK(tile) {
+        const TileCtx c = brick_ctx_id(e.g, a.bricks, tile & (TILE_DENSE_BIT - 1));
+        unsigned w[PCG_TZ + 2];
+        load_column_codes(e, c, w);
+        if (!SKIP || (tile & TILE_DENSE_BIT)) init_tile<false>(e, c, w, a.p, a.r, acc);
+        else init_tile<true>(e, c, w, a.p, a.r, acc);
+    }
+    double tot = grid_sum(grid, psumB, acc, sh, &shd);
+    float gmax = 0.0f;
+    if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+    float sigma = (float)tot;
+    float alpha = 0.0f, beta = 0.0f, max_error = 0.0f;
+    int num_iterations = 0;
+
+    for (int it = 0;; ++it) {
+        const float *s_in = (it & 1) ? a.s1 : a.s0;
+        float *s_out = (it & 1) ? a.s0 : a.s1;
+        acc = 0.0f;
+        PCG_FOR_EACH_BRICK(tile) {
+            const TileCtx c = brick_ctx_id(e.g, a.bricks, tile & (TILE_DENSE_BIT - 1));
+            unsigned w[PCG_TZ + 2];
+            load_column_codes(e, c, w);
+            if (!SKIP || (tile & TILE_DENSE_BIT)) search_tile<false>(e, c, w, a.r, s_in, s_out, beta, acc);
+            else search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
+        }
+        tot = grid_sum(grid, psumA, acc, sh, &shd);
+        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+        alpha = guarded_div(sigma, (float)tot); // RESULTMODE_ALPHA, pressure_reduce.comp:73-75
+
+        const bool with_err = (a.max_iterations == it) || (it > 0 && it % a.check_frequency == 0); // pressure_solver.rs:676-677
+        acc = 0.0f;
+        float err = 0.0f;
+        PCG_FOR_EACH_BRICK(tile) {
+            const TileCtx c = brick_ctx_id(e.g, a.bricks, tile & (TILE_DENSE_BIT - 1));
+            unsigned w[PCG_TZ + 2];
+            load_column_codes(e, c, w);
+            if (!SKIP || (tile & TILE_DENSE_BIT)) update_tile<false>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
+            else update_tile<true>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
+        }
+        {
+            const float bm = block_max(err, sh);
+            if (linear_tid() == 0) pmax[blockIdx.x] = bm;
+        }
+        tot = grid_sum(grid, psumB, acc, sh, &shd); // the barrier inside also publishes pmax
+        {
+            const float em = final_max(pmax, gridDim.x, sh);
+            if (linear_tid() == 0) shf = em;
+            __syncthreads();
+            gmax = shf;
+            __syncthreads();
+        }
+        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+        const float zr = (float)tot;
+        if (with_err) {
+            const float tol = a.params->tolerance[a.which];
+            if (a.max_iterations == it || gmax < tol) { // pressure_reduce.comp:82-94: statistics + stop everything
+                max_error = gmax;
+                num_iterations = it;
+                break;
+            }
+        }
+        beta = guarded_div(zr, sigma); // RESULTMODE_BETA, pressure_reduce.comp:77-80
+        sigma = zr;
+    }
+    if (sharded) {
+        // hand the boundary planes of the solution to the neighbours (warm start of their next init, pressure gradient
+        // across the slab face), then one more round so that nobody leaves before its ghost planes are complete
+        float *const peer_p_lo = cm_.peer_p[a.which][0], *const peer_p_hi = cm_.peer_p[a.which][1];
+        for (int li = warp_id; li < nact; li += num_warps) {
+            const TileCtx c = brick_ctx_id(e.g, a.bricks, a.brick_list_flagged[li] & (TILE_DENSE_BIT - 1));
+            if (!c.valid) continue;
+            if (c.tz == e.tz_first && peer_p_lo) st4(peer_p_lo + c.i + e.push, ld4(a.p + c.i));
+            if (c.tz == e.tz_last && peer_p_hi) {
+                const int i = c.i + (PCG_TZ - 1) * e.g.sz;
+                st4(peer_p_hi + i - e.push, ld4(a.p + i));
+            }
+        }
+        grid.sync();
+        double dummy = 0.0;
+        float dmax = 0.0f;
+        comm_allreduce(cm_, ++seq, dummy, dmax, sh_csum, sh_cmax, &sh_dead);
+        if (blockIdx.x == 0 && linear_tid() == 0) *cm_.seq = seq;
+    }
+    if (blockIdx.x == 0 && linear_tid() == 0) {
+        a.scal->alpha = alpha;
+        a.scal->beta = beta;
+        a.scal->sigma = sigma;
+        a.scal->max_error = max_error;
+        a.scal->num_iterations = num_iterations;
+        a.scal->done = sh_dead ? -1 : 1;
+    }
+}
+#undef PCG_FOR_EACH_BRICK
 
 // ---------------------------------------------------------------------------------------------------------------
 // TMA-tiled variant of the persistent solver (grids whose x extent is a multiple of 128 cells).
@@ -1710,6 +1888,20 @@ PressureSolver::PressureSolver(const GridDim &grid, void *external_residual) : g
     }
     use_tma = tma_blocks_ > 0 && env && std::string(env) == "tma";
     use_tma2 = tma2_blocks_ > 0 && env && std::string(env) == "tma2";
+    // experimental brick-granular solver (path 5): needs whole 32-cell bricks along x
+    brick_blocks_ = 0;
+    if (persistent_blocks_ > 0 && grid.nx % 32 == 0) {
+        const BrickMap b = make_brickmap(grid);
+        BLUB_CUDA_CHECK(cudaMalloc(&brick_active_, (size_t)b.nbricks));
+        BLUB_CUDA_CHECK(cudaMemset(brick_active_, 0, (size_t)b.nbricks));
+        BLUB_CUDA_CHECK(cudaMalloc(&brick_list_, sizeof(int) * (2 * (size_t)b.nbricks + 1))); // ids | count | ids with the dense flag
+        BLUB_CUDA_CHECK(cudaMemset(brick_list_, 0, sizeof(int) * (2 * (size_t)b.nbricks + 1)));
+        int per = 0;
+        BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_brick_kernel, PCG_THREADS, 0));
+        brick_blocks_ = sms * per;
+        if (brick_blocks_ > 2048) brick_blocks_ = 2048;
+    }
+    use_brick = brick_blocks_ > 0 && env && std::string(env) == "brick";
 }
 
 PressureSolver::~PressureSolver() {
@@ -1717,6 +1909,8 @@ PressureSolver::~PressureSolver() {
     if (partials_) cudaFree(partials_);
     if (tile_active_) cudaFree(tile_active_);
     if (tile_list_) cudaFree(tile_list_);
+    if (brick_active_) cudaFree(brick_active_);
+    if (brick_list_) cudaFree(brick_list_);
     delete static_cast<PcgTmaMaps *>(tma_maps_);
 }
 
@@ -1753,6 +1947,20 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
         args.p = p; args.r = r; args.s0 = s; args.s1 = aux_.ptr; args.scal = scal; args.partials = partials_;
         args.params = dparams; args.which = which; args.max_iterations = max_it; args.check_frequency = freq;
         args.comm = comm;
+        args.bricks = BrickMap{0, 0, 0, 0}; args.brick_list_flagged = nullptr; args.num_active_bricks = nullptr;
+        if (use_brick && brick_blocks_ > 0) { // experimental: one warp per 32x4x4 brick
+            const BrickMap b = make_brickmap(g);
+            int *brick_count = brick_list_ + b.nbricks;
+            const int ghost_bricks = (comm.halo / PCG_TZ) * b.bricks_x * b.bricks_y;
+            BLUB_LAUNCH(pcg_brick_flags_kernel, (b.nbricks + PCG_THREADS / 32 - 1) / (PCG_THREADS / 32), PCG_THREADS, 0, stream, g, b, st, brick_active_);
+            BLUB_LAUNCH(pcg_compact_tiles_kernel, 1, 1024, 0, stream, brick_active_, ghost_bricks, b.nbricks - ghost_bricks, brick_list_, brick_count + 1, brick_count);
+            args.bricks = b; args.brick_list_flagged = brick_count + 1; args.num_active_bricks = brick_count;
+            int nblocks = brick_blocks_;
+            void *kargs[] = {&args};
+            BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_brick_kernel, dim3(nblocks), dim3(PCG_THREADS, 1, 1), kargs, 0, stream));
+            g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+            return;
+        }
         if (use_tma2 && tma2_blocks_ > 0) {
             int nblocks = tma2_blocks_ < t.ntiles ? tma2_blocks_ : t.ntiles;
             void *kargs[] = {&args, tma_maps_};

@@ -436,6 +436,8 @@ class HybridFluid:
         """True / 1: persistent cooperative PCG (default); False / 0: three kernels per iteration; 2 or "tma": TMA-staged tiles."""
         if persistent in (4, "dense"):  # persistent kernel without the per-thread sparsity skip
             mode = 4
+        elif persistent in (5, "brick"):  # experimental: one warp per 32x4x4 brick
+            mode = 5
         else:
             mode = 3 if persistent in (3, "tma2") else (2 if persistent in (2, "tma") else (1 if persistent else 0))
         _check(self.L.blub_fluid_set_solver_path(self.h, mode))

@@ -81,3 +81,33 @@ def test_warp_aggregated_scatters_match_the_default():
     for c in range(3):
         grid_close(results["default"][0][c], results["aggregate"][0][c], f"P2G u[{c}]", rel=1e-5, abs_=1e-5, mask=util.fluid_adjacent_faces(results["default"][1], c))
     grid_close(results["default"][2], results["aggregate"][2], "density rhs", rel=1e-5, abs_=1e-3, mask=fl)
+
+
+@pytest.mark.parametrize("nx,fill", [(64, 0.5), (128, 0.9), (96, 0.05)])
+def test_brick_granular_pcg_matches_the_tile_kernel(nx, fill):
+    """Solver path 5 (one warp per 32x4x4 brick): same bodies, same barriers; only the work unit and with it the grouping of the
+    per-block partial sums differ, so the iterates agree to rounding."""
+    import blub_b200
+    from blub_b200 import fluid as F
+    from tests.util import grid_close
+
+    ny, nz = 40, 24
+    rng = np.random.default_rng(nx)
+    m = np.full((nz, ny, nx), O.AIR, dtype=np.int8)
+    m[rng.random((nz, ny, nx)) < fill] = O.FLUID
+    m[rng.random((nz, ny, nx)) < 0.03] = O.SOLID
+    m[0], m[-1], m[:, 0], m[:, -1], m[:, :, 0], m[:, :, -1] = 0, 0, 0, 0, 0, 0
+    b = rng.uniform(-1, 1, (nz, ny, nx)).astype(np.float32)
+    out = {}
+    for path in (True, "brick"):
+        f = blub_b200.HybridFluid(nx, ny, nz, 8)
+        f.set_solver_path(path)
+        f.set_solver_config(0, 0.0, 24, 4)
+        f.upload_grid(F.TAP_MARKER, m)
+        for rep in range(2):  # second solve: warm start
+            f.upload_grid(F.TAP_RESIDUAL, b)
+            f.solve_only(0, DT)
+        out[path] = (f.download_grid(F.TAP_P_VEL), f.last_solve(0))
+    assert out[True][1][1] == out["brick"][1][1] == 24
+    grid_close(out[True][0], out["brick"][0], "pressure brick vs tile", rel=2e-3, abs_=1e-4)
+    assert (out["brick"][0][m != O.FLUID] == 0).all()
