@@ -21,7 +21,13 @@ if want timeline; then      # stage times over a dam break: default, then each o
     python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_default.txt 2>&1
     BLUB_EXTRAPOLATE=bytes python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_extrapolate_bytes.txt 2>&1
     BLUB_SCATTER=aggregate python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_scatter_aggregate.txt 2>&1
-    for f in default extrapolate_bytes scatter_aggregate; do echo "== $f"; grep -E "after|p2g|extrapolate |density_gather|total" $OUT/session_timeline_$f.txt; done
+    BLUB_PCG=brick python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_brick.txt 2>&1
+    BLUB_PCG=brick python tools/profile_targets.py stages dam_halfhalf_highres 3 56 110 > $OUT/session_timeline_pcg_brick_c3.txt 2>&1
+    python tools/profile_targets.py stages dam_halfhalf_highres 3 56 110 > $OUT/session_timeline_default_c3.txt 2>&1
+    python tools/profile_targets.py pcg 256 6 brick > $OUT/session_pcg_dense_brick.txt 2>&1
+    python tools/profile_targets.py pcg 256 6 > $OUT/session_pcg_dense_default.txt 2>&1
+    for f in default extrapolate_bytes scatter_aggregate pcg_brick default_c3 pcg_brick_c3; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total" $OUT/session_timeline_$f.txt; done
+    cat $OUT/session_pcg_dense_brick.txt $OUT/session_pcg_dense_default.txt
 fi
 if want bench; then
     timeout 400 python bench.py --steps 100 --warmup 10 > $OUT/session_bench.json 2> $OUT/session_bench.err
