@@ -138,6 +138,7 @@ class PressureSolver {
     int tma_blocks_ = 0, tma2_blocks_ = 0, brick_blocks_ = 0;
     uint8_t *brick_active_ = nullptr; // experimental brick solver: per-brick activity, compacted list (ids | count | flagged ids)
     int *brick_list_ = nullptr;
+    bool brick_three_ = false;        // BLUB_PCG_BRICK_BLOCKS=3: the 80-register build of the brick kernel
 
   public:
 };

@@ -968,7 +968,8 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_brick_flags_kernel(GridDim g,
     for (int li_ = warp_id, tile = li_ < nact ? a.brick_list_flagged[li_] : 0, next_ = 0; li_ < nact; li_ += num_warps, tile = next_)  \
         if ((next_ = li_ + num_warps < nact ? a.brick_list_flagged[li_ + num_warps] : 0), true)
 
-__global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_brick_kernel(PcgSolveArgs a) {
+template <int BLOCKS_PER_SM> // 4: 64 registers (some spills), 32 warps per SM; 3: 80 registers, no spills, 24 warps per SM -- to be measured
+__global__ void __launch_bounds__(PCG_THREADS, BLOCKS_PER_SM) pcg_solve_brick_kernel(PcgSolveArgs a) {
     constexpr bool SKIP = true;
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -1897,7 +1898,10 @@ PressureSolver::PressureSolver(const GridDim &grid, void *external_residual) : g
         BLUB_CUDA_CHECK(cudaMalloc(&brick_list_, sizeof(int) * (2 * (size_t)b.nbricks + 1))); // ids | count | ids with the dense flag
         BLUB_CUDA_CHECK(cudaMemset(brick_list_, 0, sizeof(int) * (2 * (size_t)b.nbricks + 1)));
         int per = 0;
-        BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_brick_kernel, PCG_THREADS, 0));
+        const char *bps = std::getenv("BLUB_PCG_BRICK_BLOCKS");
+        brick_three_ = bps && std::string(bps) == "3";
+        if (brick_three_) BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_brick_kernel<3>, PCG_THREADS, 0));
+        else BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_brick_kernel<4>, PCG_THREADS, 0));
         brick_blocks_ = sms * per;
         if (brick_blocks_ > 2048) brick_blocks_ = 2048;
     }
@@ -1957,7 +1961,8 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
             args.bricks = b; args.brick_list_flagged = brick_count + 1; args.num_active_bricks = brick_count;
             int nblocks = brick_blocks_;
             void *kargs[] = {&args};
-            BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_brick_kernel, dim3(nblocks), dim3(PCG_THREADS, 1, 1), kargs, 0, stream));
+            BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel(brick_three_ ? (const void *)pcg_solve_brick_kernel<3> : (const void *)pcg_solve_brick_kernel<4>, dim3(nblocks), dim3(PCG_THREADS, 1, 1), kargs, 0,
+                                                        stream));
             g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
             return;
         }

@@ -23,10 +23,11 @@ if want timeline; then      # stage times over a dam break: default, then each o
     BLUB_SCATTER=aggregate python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_scatter_aggregate.txt 2>&1
     BLUB_PCG=brick python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_brick.txt 2>&1
     BLUB_PCG=brick python tools/profile_targets.py stages dam_halfhalf_highres 3 56 110 > $OUT/session_timeline_pcg_brick_c3.txt 2>&1
+    BLUB_PCG=brick BLUB_PCG_BRICK_BLOCKS=3 python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_brick3.txt 2>&1
     python tools/profile_targets.py stages dam_halfhalf_highres 3 56 110 > $OUT/session_timeline_default_c3.txt 2>&1
     python tools/profile_targets.py pcg 256 6 brick > $OUT/session_pcg_dense_brick.txt 2>&1
     python tools/profile_targets.py pcg 256 6 > $OUT/session_pcg_dense_default.txt 2>&1
-    for f in default extrapolate_bytes scatter_aggregate pcg_brick default_c3 pcg_brick_c3; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total" $OUT/session_timeline_$f.txt; done
+    for f in default extrapolate_bytes scatter_aggregate pcg_brick pcg_brick3 default_c3 pcg_brick_c3; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total" $OUT/session_timeline_$f.txt; done
     cat $OUT/session_pcg_dense_brick.txt $OUT/session_pcg_dense_default.txt
 fi
 if want bench; then
