@@ -129,13 +129,13 @@ class PressureSolver {
     bool use_tma = false;            // persistent solver with TMA-staged tiles (nx % 128 == 0); BLUB_PCG=tma or blub_fluid_set_solver_path(f, 2)
     bool use_dense = false;          // persistent solver without the per-thread sparsity skip (comparison only); set_solver_path(f, 4)
     bool use_brick = false;          // EXPERIMENTAL: persistent solver with one warp per 32x4x4 brick; BLUB_PCG=brick or set_solver_path(f, 5)
-    bool use_tma2 = false;           // double-buffered TMA solver, one 512-thread block per SM; BLUB_PCG=tma2 or set_solver_path(f, 3)
     bool tma_available() const { return tma_blocks_ > 0; }
-    bool tma2_available() const { return tma2_blocks_ > 0; }
+    bool brick_available() const { return brick_blocks_ > 0; }
+    bool persistent_available() const { return persistent_blocks_ > 0; }
 
   private:
     void *tma_maps_ = nullptr;       // PcgTmaMaps (tensor maps of r, s0, s1, codes)
-    int tma_blocks_ = 0, tma2_blocks_ = 0, brick_blocks_ = 0;
+    int tma_blocks_ = 0, brick_blocks_ = 0;
     uint8_t *brick_active_ = nullptr; // experimental brick solver: per-brick activity, compacted list (ids | count | flagged ids)
     int *brick_list_ = nullptr;
     bool brick_three_ = false;        // BLUB_PCG_BRICK_BLOCKS=3: the 80-register build of the brick kernel

@@ -499,14 +499,17 @@ int blub_fluid_step_timed(BlubFluid *fluid, double dt, float ms_per_stage[14]) {
 
 int blub_fluid_set_solver_path(BlubFluid *fluid, int persistent) {
     if (!fluid) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL fluid");
-    fluid->impl->solver().use_persistent = persistent != 0;
-    fluid->impl->solver().use_tma = persistent == 2;
-    fluid->impl->solver().use_tma2 = persistent == 3;
-    fluid->impl->solver().use_dense = persistent == 4;
-    fluid->impl->solver().use_brick = persistent == 5;
-    if (persistent == 3 && !fluid->impl->solver().tma2_available()) return fail(BLUB_ERR_INVALID_ARGUMENT, "double-buffered TMA solver needs nx % 128 == 0 and cooperative launch");
+    blub::PressureSolver &s = fluid->impl->solver();
+    // validate first: a refused request leaves the solver (and the cached step graphs) exactly as they were
+    if (persistent < 0 || persistent > 5 || persistent == 3) return fail(BLUB_ERR_INVALID_ARGUMENT, "solver path must be 0 (three kernels), 1 (persistent), 2 (TMA-staged), 4 (dense) or 5 (brick)");
+    if (persistent == 2 && !s.tma_available()) return fail(BLUB_ERR_INVALID_ARGUMENT, "TMA solver needs nx % 128 == 0 and cooperative launch");
+    if (persistent == 5 && !s.brick_available()) return fail(BLUB_ERR_INVALID_ARGUMENT, "brick solver needs nx % 32 == 0 and cooperative launch");
+    if (persistent == 5 && fluid->impl->sharded()) return fail(BLUB_ERR_INVALID_ARGUMENT, "brick solver is single-GPU only");
+    s.use_persistent = persistent != 0;
+    s.use_tma = persistent == 2;
+    s.use_dense = persistent == 4;
+    s.use_brick = persistent == 5;
     fluid->impl->invalidate_graphs();
-    if (persistent == 2 && !fluid->impl->solver().tma_available()) return fail(BLUB_ERR_INVALID_ARGUMENT, "TMA solver needs nx % 128 == 0 and cooperative launch");
     return BLUB_OK;
 }
 

@@ -1387,337 +1387,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_tma_kernel(const __g
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Double-buffered TMA solver: ONE block of 512 threads per SM, two shared-memory stages.  While the block computes on the
-// boxes of tile j, the TMA unit already fills the other stage with tile j+1 (and, in phase B, the p / r / code quads of
-// tile j+1 are already in flight into registers): a full tile of operands is in flight per SM at all times, independent
-// of occupancy -- the register-marching kernel is bound by load latency (long-scoreboard stalls, ~60 % DRAM utilisation).
-// Threads (lx, ty): row ly = ty & 7 of the tile, planes {2h, 2h+1} with h = ty >> 3.
-constexpr int T2_THREADS = 512;
-constexpr int T2_STAGE_BYTES = TMA_SMEM_BYTES;      // 74,880
-constexpr int T2_SMEM_BYTES = 2 * T2_STAGE_BYTES;   // 149,760
-
-__device__ __forceinline__ float block_sum512(float v, float *sh) {
-    v = warp_sum(v);
-    const int tid = linear_tid(), lane = tid & 31, w = tid >> 5;
-    if (lane == 0) sh[w] = v;
-    __syncthreads();
-    float r = 0.0f;
-    if (w == 0) {
-        r = lane < (T2_THREADS / 32) ? sh[lane] : 0.0f;
-        r = warp_sum(r);
-    }
-    __syncthreads();
-    return r;
-}
-__device__ __forceinline__ float block_max512(float v, float *sh) {
-    v = warp_max(v);
-    const int tid = linear_tid(), lane = tid & 31, w = tid >> 5;
-    if (lane == 0) sh[w] = v;
-    __syncthreads();
-    float r = 0.0f;
-    if (w == 0) {
-        r = lane < (T2_THREADS / 32) ? sh[lane] : 0.0f;
-        r = warp_max(r);
-    }
-    __syncthreads();
-    return r;
-}
-// sum / max of the per-block partials, identical in every block (fixed order), broadcast to all threads
-__device__ __forceinline__ double grid_sum512(cooperative_groups::grid_group &grid, float *partials, float acc, float *sh, double *shd) {
-    const float bs = block_sum512(acc, sh);
-    if (linear_tid() == 0) partials[blockIdx.x] = bs;
-    grid.sync();
-    if (linear_tid() < 32) {
-        double a = 0.0;
-        for (int k = linear_tid(); k < (int)gridDim.x; k += 32) a += (double)__ldcg(partials + k);
-        a = warp_sum(a);
-        if (linear_tid() == 0) *shd = a;
-    }
-    __syncthreads();
-    const double v = *shd;
-    __syncthreads();
-    return v;
-}
-__device__ __forceinline__ float grid_max512(const float *partials, float *shf) {
-    if (linear_tid() < 32) {
-        float a = 0.0f;
-        for (int k = linear_tid(); k < (int)gridDim.x; k += 32) a = fmaxf(a, __ldcg(partials + k));
-        a = warp_max(a);
-        if (linear_tid() == 0) *shf = a;
-    }
-    __syncthreads();
-    const float v = *shf;
-    __syncthreads();
-    return v;
-}
-
-__global__ void __launch_bounds__(T2_THREADS, 1) pcg_solve_tma2_kernel(const __grid_constant__ PcgSolveArgs a, const __grid_constant__ PcgTmaMaps maps) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar[2];
-    __shared__ float sh[T2_THREADS / 32];
-    __shared__ double shd;
-    __shared__ float shf;
-    __shared__ double sh_csum[SLAB_MAX_WORLD];
-    __shared__ float sh_cmax[SLAB_MAX_WORLD];
-    __shared__ int sh_dead;
-    const GridDim g = a.g;
-    const TileMap t = a.t;
-    const SlabComm &cm_ = a.comm;
-    const bool sharded = cm_.world > 1;
-    const int nact = *a.num_active;
-    const uint8_t *__restrict__ codes = a.codes;
-    float *psumA = a.partials, *psumB = a.partials + gridDim.x, *pmax = a.partials + 2 * gridDim.x;
-    const int tz_first = cm_.halo / PCG_TZ, tz_last = t.tiles_z - 1 - cm_.halo / PCG_TZ;
-    const int push = cm_.owned_nz * g.sz;
-    float *const peer_r_lo = cm_.peer_r[0], *const peer_r_hi = cm_.peer_r[1];
-    const int tid = linear_tid(), lx = threadIdx.x, ly = threadIdx.y & 7, half = threadIdx.y >> 3;
-    const int G = gridDim.x;
-    const int nmy = nact > (int)blockIdx.x ? (nact - (int)blockIdx.x + G - 1) / G : 0;
-    unsigned seq = 0, par0 = 0, par1 = 0;
-    if (tid == 0) {
-        sh_dead = 0;
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        fence_proxy_async();
-    }
-    if (sharded) seq = *cm_.seq;
-    __syncthreads();
-    if (sharded) slab_start_handshake(cm_, seq, sh_csum, sh_cmax, &sh_dead);
-
-    auto tile_origin = [&](int tile, int &x0, int &y0, int &z0, int &tz) {
-        const int tx = tile % t.tiles_x, rest = tile / t.tiles_x;
-        x0 = tx * 128;
-        y0 = (rest % t.tiles_y) * 8;
-        tz = rest / t.tiles_y;
-        z0 = tz * PCG_TZ;
-    };
-
-    // ---- init: r <- b - A p, sigma <- z.r (runs once; the first 8 warps use the register-marching code)
-    float acc = 0.0f;
-    if (threadIdx.y < 8) {
-        for (int li = blockIdx.x; li < nact; li += G) {
-            const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
-            int i = c.i;
-            float4 pm = zero4(), p0 = zero4(), pp = zero4();
-            if (c.valid) { pm = ld4(a.p + i - g.sz); p0 = ld4(a.p + i); }
-#pragma unroll
-            for (int k = 0; k < PCG_TZ; ++k, i += g.sz) {
-                float left, right;
-                x_neighbours(a.p, i, p0, c, left, right);
-                if (c.valid) {
-                    pp = ld4(a.p + i + g.sz);
-                    const uchar4 code = ldcode(codes + i);
-                    const float4 ym = ld4(a.p + i - g.sy), yp = ld4(a.p + i + g.sy);
-                    float4 r4 = ld4(a.r + i);
-                    const float4 Ap = stencil_quad(code, p0, left, right, ym, yp, pm, pp);
-                    r4.x -= code.x ? Ap.x : 0.0f;
-                    r4.y -= code.y ? Ap.y : 0.0f;
-                    r4.z -= code.z ? Ap.z : 0.0f;
-                    r4.w -= code.w ? Ap.w : 0.0f;
-                    st4(a.r + i, r4);
-                    if (sharded) {
-                        if (k == 0 && c.tz == tz_first && peer_r_lo) st4(peer_r_lo + i + push, r4);
-                        if (k == PCG_TZ - 1 && c.tz == tz_last && peer_r_hi) st4(peer_r_hi + i - push, r4);
-                    }
-                    acc += (precond_diag2(r4.x, code.x) * r4.x + precond_diag2(r4.y, code.y) * r4.y) +
-                           (precond_diag2(r4.z, code.z) * r4.z + precond_diag2(r4.w, code.w) * r4.w);
-                }
-                pm = p0;
-                p0 = pp;
-            }
-        }
-    }
-    fence_proxy_async_global();
-    double tot = grid_sum512(grid, psumB, acc, sh, &shd);
-    float gmax = 0.0f;
-    if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
-    float sigma = (float)tot;
-    float alpha = 0.0f, beta = 0.0f, max_error = 0.0f;
-    int num_iterations = 0;
-
-    const int qoff = (ly + 1) * TMA_BX + 4 + 4 * lx;
-    const int coff = (ly + 1) * TMA_CX + 16 + 4 * lx;
-    constexpr int PLANE = TMA_BX * TMA_BY, CPLANE = TMA_CX * TMA_BY;
-    // global index of this thread's quad in plane k of tile `tile`
-    auto quad_index = [&](int x0, int y0, int z0, int k) { return ((z0 + k) * g.ny + y0 + ly) * g.nx + x0 + 4 * lx; };
-
-    for (int it = 0;; ++it) {
-        const CUtensorMap *map_in = (it & 1) ? &maps.s1 : &maps.s0;
-        const CUtensorMap *map_out = (it & 1) ? &maps.s0 : &maps.s1;
-        float *s_out = (it & 1) ? a.s0 : a.s1;
-
-        // ---------------- phase A ----------------
-        auto issueA = [&](int j, int st) {
-            if (tid != 0) return;
-            int x0, y0, z0, tz;
-            tile_origin(a.tile_list[blockIdx.x + j * G], x0, y0, z0, tz);
-            unsigned char *base = smem_raw + st * T2_STAGE_BYTES;
-            fence_proxy_async_global();
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&bar[st], 2 * TMA_F32_BYTES + TMA_U8_BYTES);
-            tma_load_3d(base, &maps.r, x0 - 4, y0 - 1, z0 - 1, &bar[st]);
-            tma_load_3d(base + TMA_F32_BYTES, map_in, x0 - 4, y0 - 1, z0 - 1, &bar[st]);
-            tma_load_3d(base + 2 * TMA_F32_BYTES, &maps.codes, x0 - 16, y0 - 1, z0 - 1, &bar[st]);
-        };
-        acc = 0.0f;
-        if (nmy > 0) issueA(0, 0);
-        for (int j = 0; j < nmy; ++j) {
-            const int st = j & 1;
-            if (j + 1 < nmy) issueA(j + 1, st ^ 1);
-            if (st == 0) { mbar_wait(&bar[0], par0, &sh_dead); par0 ^= 1u; } else { mbar_wait(&bar[1], par1, &sh_dead); par1 ^= 1u; }
-            float *shR = reinterpret_cast<float *>(smem_raw + st * T2_STAGE_BYTES);
-            float *shS = shR + TMA_F32_BYTES / 4;
-            const uint8_t *shC = smem_raw + st * T2_STAGE_BYTES + 2 * TMA_F32_BYTES;
-            for (int qd = tid; qd < TMA_BY * TMA_BZ * (TMA_BX / 4); qd += T2_THREADS) {
-                const int row = qd / (TMA_BX / 4), col = (qd - row * (TMA_BX / 4)) * 4;
-                const float4 r4 = *reinterpret_cast<const float4 *>(shR + row * TMA_BX + col);
-                float4 s4 = *reinterpret_cast<const float4 *>(shS + row * TMA_BX + col);
-                const uchar4 cd = *reinterpret_cast<const uchar4 *>(shC + row * TMA_CX + col + 12);
-                s4.x = precond_diag2(r4.x, cd.x) + beta * s4.x;
-                s4.y = precond_diag2(r4.y, cd.y) + beta * s4.y;
-                s4.z = precond_diag2(r4.z, cd.z) + beta * s4.z;
-                s4.w = precond_diag2(r4.w, cd.w) + beta * s4.w;
-                *reinterpret_cast<float4 *>(shS + row * TMA_BX + col) = s4;
-            }
-            __syncthreads();
-            int x0, y0, z0, tz;
-            tile_origin(a.tile_list[blockIdx.x + j * G], x0, y0, z0, tz);
-            if (sharded && tz == tz_first && half == 0) st4(s_out + quad_index(x0, y0, z0, -1), *reinterpret_cast<const float4 *>(shS + qoff));
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const int k = 2 * half + kk;
-                const float *S = shS + (k + 1) * PLANE + qoff;
-                const float4 c0 = *reinterpret_cast<const float4 *>(S);
-                const float4 ym = *reinterpret_cast<const float4 *>(S - TMA_BX), yp = *reinterpret_cast<const float4 *>(S + TMA_BX);
-                const float4 zm = *reinterpret_cast<const float4 *>(S - PLANE), zp = *reinterpret_cast<const float4 *>(S + PLANE);
-                const uchar4 code = *reinterpret_cast<const uchar4 *>(shC + (k + 1) * CPLANE + coff);
-                const float4 As = stencil_quad(code, c0, S[-1], S[4], ym, yp, zm, zp);
-                acc += (c0.x * As.x + c0.y * As.y) + (c0.z * As.z + c0.w * As.w);
-                const int i = quad_index(x0, y0, z0, k);
-                st4(s_out + i, c0);
-                if (sharded && k == PCG_TZ - 1 && tz == tz_last) st4(s_out + i + g.sz, zp);
-            }
-            __syncthreads(); // stage st is free again
-        }
-        fence_proxy_async_global();
-        tot = grid_sum512(grid, psumA, acc, sh, &shd);
-        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
-        alpha = guarded_div(sigma, (float)tot);
-
-        // ---------------- phase B ----------------
-        const bool with_err = (a.max_iterations == it) || (it > 0 && it % a.check_frequency == 0);
-        auto issueB = [&](int j, int st) {
-            if (tid != 0) return;
-            int x0, y0, z0, tz;
-            tile_origin(a.tile_list[blockIdx.x + j * G], x0, y0, z0, tz);
-            fence_proxy_async_global();
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&bar[st], TMA_F32_BYTES);
-            tma_load_3d(smem_raw + st * T2_STAGE_BYTES + TMA_F32_BYTES, map_out, x0 - 4, y0 - 1, z0 - 1, &bar[st]);
-        };
-        float4 pn[2], rn[2];
-        uchar4 cn[2];
-        auto load_regs = [&](int j) {
-            int x0, y0, z0, tz;
-            tile_origin(a.tile_list[blockIdx.x + j * G], x0, y0, z0, tz);
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const int i = quad_index(x0, y0, z0, 2 * half + kk);
-                pn[kk] = ld4(a.p + i);
-                rn[kk] = ld4(a.r + i);
-                cn[kk] = ldcode(codes + i);
-            }
-        };
-        acc = 0.0f;
-        float err = 0.0f;
-        if (nmy > 0) { issueB(0, 0); load_regs(0); }
-        for (int j = 0; j < nmy; ++j) {
-            const int st = j & 1;
-            float4 pc[2] = {pn[0], pn[1]}, rc[2] = {rn[0], rn[1]};
-            const uchar4 cc[2] = {cn[0], cn[1]};
-            if (j + 1 < nmy) { issueB(j + 1, st ^ 1); load_regs(j + 1); }
-            if (st == 0) { mbar_wait(&bar[0], par0, &sh_dead); par0 ^= 1u; } else { mbar_wait(&bar[1], par1, &sh_dead); par1 ^= 1u; }
-            const float *shS = reinterpret_cast<const float *>(smem_raw + st * T2_STAGE_BYTES + TMA_F32_BYTES);
-            int x0, y0, z0, tz;
-            tile_origin(a.tile_list[blockIdx.x + j * G], x0, y0, z0, tz);
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const int k = 2 * half + kk;
-                const float *S = shS + (k + 1) * PLANE + qoff;
-                const float4 s0 = *reinterpret_cast<const float4 *>(S);
-                const float4 ym = *reinterpret_cast<const float4 *>(S - TMA_BX), yp = *reinterpret_cast<const float4 *>(S + TMA_BX);
-                const float4 zm = *reinterpret_cast<const float4 *>(S - PLANE), zp = *reinterpret_cast<const float4 *>(S + PLANE);
-                const float4 As = stencil_quad(cc[kk], s0, S[-1], S[4], ym, yp, zm, zp);
-                float4 pq = pc[kk], rq = rc[kk];
-                pq.x += alpha * s0.x; pq.y += alpha * s0.y; pq.z += alpha * s0.z; pq.w += alpha * s0.w;
-                rq.x -= alpha * (cc[kk].x ? As.x : 0.0f);
-                rq.y -= alpha * (cc[kk].y ? As.y : 0.0f);
-                rq.z -= alpha * (cc[kk].z ? As.z : 0.0f);
-                rq.w -= alpha * (cc[kk].w ? As.w : 0.0f);
-                const int i = quad_index(x0, y0, z0, k);
-                st4(a.p + i, pq);
-                st4(a.r + i, rq);
-                if (sharded) {
-                    if (k == 0 && tz == tz_first && peer_r_lo) st4(peer_r_lo + i + push, rq);
-                    if (k == PCG_TZ - 1 && tz == tz_last && peer_r_hi) st4(peer_r_hi + i - push, rq);
-                }
-                acc += (precond_diag2(rq.x, cc[kk].x) * rq.x + precond_diag2(rq.y, cc[kk].y) * rq.y) +
-                       (precond_diag2(rq.z, cc[kk].z) * rq.z + precond_diag2(rq.w, cc[kk].w) * rq.w);
-                err = fmaxf(fmaxf(err, fmaxf(fabsf(rq.x), fabsf(rq.y))), fmaxf(fabsf(rq.z), fabsf(rq.w)));
-            }
-            __syncthreads();
-        }
-        fence_proxy_async_global();
-        {
-            const float bm = block_max512(err, sh);
-            if (tid == 0) pmax[blockIdx.x] = bm;
-        }
-        tot = grid_sum512(grid, psumB, acc, sh, &shd);
-        gmax = grid_max512(pmax, &shf);
-        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
-        const float zr = (float)tot;
-        if (with_err) {
-            const float tol = a.params->tolerance[a.which];
-            if (a.max_iterations == it || gmax < tol) {
-                max_error = gmax;
-                num_iterations = it;
-                break;
-            }
-        }
-        beta = guarded_div(zr, sigma);
-        sigma = zr;
-    }
-    if (sharded) {
-        float *const peer_p_lo = cm_.peer_p[a.which][0], *const peer_p_hi = cm_.peer_p[a.which][1];
-        if (threadIdx.y < 8) {
-            for (int li = blockIdx.x; li < nact; li += G) {
-                const TileCtx c = tile_ctx_id(g, t, a.tile_list[li]);
-                if (c.tz == tz_first && peer_p_lo) st4(peer_p_lo + c.i + push, ld4(a.p + c.i));
-                if (c.tz == tz_last && peer_p_hi) {
-                    const int i = c.i + (PCG_TZ - 1) * g.sz;
-                    st4(peer_p_hi + i - push, ld4(a.p + i));
-                }
-            }
-        }
-        grid.sync();
-        double dummy = 0.0;
-        float dmax = 0.0f;
-        comm_allreduce(cm_, ++seq, dummy, dmax, sh_csum, sh_cmax, &sh_dead);
-        if (blockIdx.x == 0 && tid == 0) *cm_.seq = seq;
-    }
-    if (blockIdx.x == 0 && tid == 0) {
-        a.scal->alpha = alpha;
-        a.scal->beta = beta;
-        a.scal->sigma = sigma;
-        a.scal->max_error = max_error;
-        a.scal->num_iterations = num_iterations;
-        a.scal->done = sh_dead ? -1 : 1;
-    }
-}
-
 // deterministic compaction of the active tiles (ascending tile id) by one block
 __global__ void __launch_bounds__(1024) pcg_compact_tiles_kernel(const uint8_t *__restrict__ tile_active, int tile_lo, int ntiles,
                                                                  int *__restrict__ tile_list, int *__restrict__ tile_list_flagged,
@@ -1882,13 +1551,9 @@ PressureSolver::PressureSolver(const GridDim &grid, void *external_residual) : g
             int per = 0;
             BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_tma_kernel, PCG_THREADS, TMA_SMEM_BYTES));
             tma_blocks_ = sms * per;
-            BLUB_CUDA_CHECK(cudaFuncSetAttribute(pcg_solve_tma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-            BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_tma2_kernel, T2_THREADS, T2_SMEM_BYTES));
-            tma2_blocks_ = sms * per;
         }
     }
     use_tma = tma_blocks_ > 0 && env && std::string(env) == "tma";
-    use_tma2 = tma2_blocks_ > 0 && env && std::string(env) == "tma2";
     // experimental brick-granular solver (path 5): needs whole 32-cell bricks along x
     brick_blocks_ = 0;
     if (persistent_blocks_ > 0 && grid.nx % 32 == 0) {
@@ -1963,13 +1628,6 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
             void *kargs[] = {&args};
             BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel(brick_three_ ? (const void *)pcg_solve_brick_kernel<3> : (const void *)pcg_solve_brick_kernel<4>, dim3(nblocks), dim3(PCG_THREADS, 1, 1), kargs, 0,
                                                         stream));
-            g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-            return;
-        }
-        if (use_tma2 && tma2_blocks_ > 0) {
-            int nblocks = tma2_blocks_ < t.ntiles ? tma2_blocks_ : t.ntiles;
-            void *kargs[] = {&args, tma_maps_};
-            BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_tma2_kernel, dim3(nblocks), dim3(32, 16, 1), kargs, T2_SMEM_BYTES, stream));
             g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
             return;
         }

@@ -439,7 +439,7 @@ class HybridFluid:
         elif persistent in (5, "brick"):  # experimental: one warp per 32x4x4 brick
             mode = 5
         else:
-            mode = 3 if persistent in (3, "tma2") else (2 if persistent in (2, "tma") else (1 if persistent else 0))
+            mode = 2 if persistent in (2, "tma") else (1 if persistent else 0)
         _check(self.L.blub_fluid_set_solver_path(self.h, mode))
 
     def stream(self):

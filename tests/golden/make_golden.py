@@ -3,6 +3,12 @@
 These are REGRESSION pins, not reference outputs: they freeze what the oracle (and therefore the parity target of the CUDA path)
 produces today for a small dam break, so that a later change to oracle/ cannot silently move the goal posts.
 
+Protocol: everything that is compared as a TRAJECTORY runs both pressure solves at tolerance 1e-4 / max 128
+iterations, so that the iterate is converged and the comparison is well conditioned.  With the reference's default solver (0.1 / 32 / 4)
+the solve stops at a discontinuous `max|r| < tol` test on an unconverged iterate: the oracle compared with ITSELF after a 1e-6-cell
+perturbation of the seed then moves by 1e-3..4e-3 cells in one step (round-1 VERDICT), which is a property of the test, not of an
+implementation.  The default solver is covered stage by stage (tests/test_gpu_parity.py::test_stagewise_parity_one_step).
+
     python tests/golden/make_golden.py
 """
 import os
@@ -14,10 +20,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import oracle as O  # noqa: E402
 
+TIGHT = dict(error_tolerance=1e-4, max_num_iterations=128, error_check_frequency=4)
+STEPS = 3
+
 
 def run():
     f = O.fluid_from_scene(O.load_scene(os.path.join(HERE, "scenes", "dam_small.json")))
     f.set_rebin_frequency(0)
+    for which in (0, 1):
+        f.set_solver_config(which, **TIGHT)
     seed = f.particles()[:, :3].copy()
     f.step_stages(O.DT_120HZ, 0, 2)
     rhs1 = f.grid(O.ARR_RESIDUAL).copy()
@@ -25,7 +36,7 @@ def run():
     f.step_stages(O.DT_120HZ, 2, 14)
     stats = [f.last_solve(0), f.last_solve(1)]
     pos1 = f.particles()[:, :3].copy()
-    for _ in range(2):
+    for _ in range(STEPS - 1):
         f.step(O.DT_120HZ)
     pos3 = f.particles()[:, :3].copy()
     return dict(

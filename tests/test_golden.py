@@ -30,11 +30,21 @@ def test_oracle_reproduces_the_golden_vectors():
 
 @pytest.mark.gpu
 def test_cuda_path_matches_the_golden_vectors():
+    """SURVEY 8(c) protocol: trajectories are compared with both solves converged (1e-4 / 128), see make_golden.py.  Measured
+    conditioning of this check (oracle against itself, seed perturbed by 1e-6 / 1e-5 cells): 4e-6 / 3e-5 cells after one step,
+    4e-5 / 5e-5 after three -- two orders of magnitude below the tolerances used here."""
+    import importlib.util
+
     import blub_b200
     from blub_b200 import fluid as F
 
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(util.HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
     gpu = blub_b200.HybridFluid.from_scene(util.scene_path("dam_small"))
     gpu.set_rebin_frequency(0)
+    for which in (0, 1):
+        gpu.set_solver_config(which, **mg.TIGHT)
     seed = gpu.download_particles()[:, :3]
     assert np.array_equal(seed[:64], GOLD["seed_first"]) and np.allclose(seed.astype(np.float64).sum(0), GOLD["seed_sum"], rtol=0, atol=1e-6)
     gpu.step_stages(DT, 0, 2)
@@ -44,11 +54,13 @@ def test_cuda_path_matches_the_golden_vectors():
     assert abs(np.abs(rhs[m == 1]).max() - GOLD["rhs1_absmax"]) <= 1e-4 * GOLD["rhs1_absmax"] + 1e-5
     gpu.step_stages(DT, 2, 14)
     its = [gpu.last_solve(0)[1], gpu.last_solve(1)[1]]
-    assert its == list(GOLD["solver_iterations"])
+    # converged solves stop at a check iteration (every 4th); the last bits of max|r| decide between neighbouring checks
+    assert all(abs(a - b) <= 4 and a % 4 == 0 for a, b in zip(its, GOLD["solver_iterations"])), (its, GOLD["solver_iterations"])
     p1 = gpu.download_particles()[:, :3]
-    assert np.abs(p1[::16] - GOLD["pos1_sample"]).max() <= 2e-3  # one step: 2e-4 cells typical, fp32 CG iterate differences bound it
-    for _ in range(2):
+    d1 = np.abs(p1[::16] - GOLD["pos1_sample"]).max(axis=1)
+    assert d1.max() <= 2e-4, d1.max()  # positions <= 2e-4 cells after one step
+    for _ in range(mg.STEPS - 1):
         gpu.step(DT)
     p3 = gpu.download_particles()[:, :3]
     d = np.abs(p3[::16] - GOLD["pos3_sample"]).max(axis=1)
-    assert np.quantile(d, 0.999) <= 1e-2, (np.quantile(d, 0.999), d.max())
+    assert np.quantile(d, 0.999) <= 2e-3 and d.max() <= 1e-2, (np.quantile(d, 0.999), d.max())

@@ -65,3 +65,20 @@ def apply_A(m, x):
             diag += (mm != O.SOLID)
             out -= np.where(mm == O.FLUID, np.roll(x, sh, axis=ax), 0.0)
     return np.where(fl, out + diag * x, 0.0)
+
+
+def markers_agree(m_o, m_g, what="marker", allowed=8):
+    """Marker volumes after SEVERAL steps: a particle within round-off of a cell face may sit in the neighbouring cell in one of the two
+    implementations, which flips an AIR/FLUID marker at the free surface.  Structural agreement = at most `allowed` such cells, and never a
+    SOLID mismatch (solids do not depend on particles)."""
+    bad = m_o != m_g
+    assert not (bad & ((m_o == O.SOLID) | (m_g == O.SOLID))).any(), f"{what}: SOLID cells differ"
+    assert int(bad.sum()) <= allowed, f"{what}: {int(bad.sum())} cells differ"
+    return int(bad.sum())
+
+
+def tight_solver(*fluids, tol=1e-4, max_it=128):
+    """trajectory comparisons run both solves to convergence so that the iterate is well defined."""
+    for f in fluids:
+        f.set_solver_config(0, tol, max_it, 4)
+        f.set_solver_config(1, tol, max_it, 4)

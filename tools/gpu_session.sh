@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call, many answers: every call costs 1.5-3 minutes of box time before the command even starts, so measurements are
 # batched.  Usage (from the repository root, on the GPU box):
-#     bash tools/gpu_session.sh [tests] [experimental] [timeline] [bench] [launches] [ncu] [blubrun]
+#     bash tools/gpu_session.sh [tests] [experimental] [smoke] [timeline] [variants] [bench] [launches] [ncu] [blubrun]
 # Everything lands in gpurun_out/session_*.{txt,json,csv}; nothing here is a bench number unless it comes from bench.py outside ncu.
 set -u
 OUT=gpurun_out
@@ -9,30 +9,36 @@ mkdir -p $OUT
 want() { [[ " $ARGS " == *" $1 "* ]]; }
 ARGS="${*:-tests timeline bench}"
 
-if want tests; then
-    timeout 300 python -m pytest tests -m gpu -q --tb=short 2>&1 | grep -v "^$" | tail -25 > $OUT/session_tests.txt
-    tail -3 $OUT/session_tests.txt
+if want tests; then         # the whole GPU suite, WITHOUT -x: every failure is listed
+    timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider 2>&1 | grep -v "^$" > $OUT/session_tests.txt
+    tail -40 $OUT/session_tests.txt
 fi
 if want experimental; then  # the opt-in variants must first reproduce the default kernels
-    BLUB_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_zz_experimental.py -m gpu -q --tb=short 2>&1 | grep -v "^$" | tail -25 > $OUT/session_experimental.txt
-    tail -3 $OUT/session_experimental.txt
+    BLUB_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_experimental.py -m gpu -q --tb=short -p no:cacheprovider 2>&1 | grep -v "^$" | tail -40 > $OUT/session_experimental.txt
+    tail -15 $OUT/session_experimental.txt
 fi
-if want timeline; then      # stage times over a dam break: default, then each opt-in variant
+if want smoke; then         # twice: the round-1 failure was run-to-run
+    for k in 1 2; do timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/session_smoke$k.txt 2>&1; tail -2 $OUT/session_smoke$k.txt; done
+fi
+if want timeline; then      # stage times over a dam break
     python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_default.txt 2>&1
+    python tools/profile_targets.py stages dam_halfhalf_highres 3 56 110 > $OUT/session_timeline_default_c3.txt 2>&1
+    for f in default default_c3; do echo "== $f"; cat $OUT/session_timeline_$f.txt; done
+fi
+if want variants; then      # each opt-in variant against the default timeline
     BLUB_EXTRAPOLATE=bytes python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_extrapolate_bytes.txt 2>&1
     BLUB_SCATTER=aggregate python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_scatter_aggregate.txt 2>&1
     BLUB_PCG=brick python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_brick.txt 2>&1
-    BLUB_PCG=brick python tools/profile_targets.py stages dam_halfhalf_highres 3 56 110 > $OUT/session_timeline_pcg_brick_c3.txt 2>&1
     BLUB_PCG=brick BLUB_PCG_BRICK_BLOCKS=3 python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_brick3.txt 2>&1
-    python tools/profile_targets.py stages dam_halfhalf_highres 3 56 110 > $OUT/session_timeline_default_c3.txt 2>&1
+    BLUB_PCG=brick python tools/profile_targets.py stages dam_halfhalf_highres 3 56 110 > $OUT/session_timeline_pcg_brick_c3.txt 2>&1
     python tools/profile_targets.py pcg 256 6 brick > $OUT/session_pcg_dense_brick.txt 2>&1
     python tools/profile_targets.py pcg 256 6 > $OUT/session_pcg_dense_default.txt 2>&1
-    for f in default extrapolate_bytes scatter_aggregate pcg_brick pcg_brick3 default_c3 pcg_brick_c3; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total" $OUT/session_timeline_$f.txt; done
+    for f in extrapolate_bytes scatter_aggregate pcg_brick pcg_brick3 pcg_brick_c3; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total|Error|error" $OUT/session_timeline_$f.txt; done
     cat $OUT/session_pcg_dense_brick.txt $OUT/session_pcg_dense_default.txt
 fi
 if want bench; then
-    timeout 400 python bench.py --steps 100 --warmup 10 > $OUT/session_bench.json 2> $OUT/session_bench.err
-    head -c 400 $OUT/session_bench.json; echo
+    timeout 600 python bench.py > $OUT/session_bench.json 2> $OUT/session_bench.err
+    head -c 600 $OUT/session_bench.json; echo; tail -3 $OUT/session_bench.err
 fi
 if want launches; then      # the launch list of the bench command itself (shares only: ncu serialises and runs cold)
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/session_launches.csv \
