@@ -10,6 +10,7 @@
 
 #include "../../include/blub_fluid.h"
 #include "common.cuh"
+#include "fluid_kernels.hpp"
 
 namespace blub {
 
@@ -185,6 +186,8 @@ class HybridFluid {
     // 0 = fine; 1 = a peer timed out in a barrier; 2 = particle capacity exceeded; 3 = migration buffer overflow (synchronises)
     int slab_error();
     void invalidate_graphs() { destroy_graphs(); }
+    void set_transfer_path(int scatter);
+    void marker_written_externally() { fluid_bits_stale_ = true; }
 
     Quirks quirks;
 
@@ -203,6 +206,7 @@ class HybridFluid {
   private:
     void upload_step_params(float dt);
     void run_stage(int stage, float dt);
+    void refresh_fluid_bits();
     void destroy_graphs();
 
     // ---- z-slab sharding of the whole step (slab.cu) ----
@@ -264,13 +268,12 @@ class HybridFluid {
     int cur_ = 0;
     float4 *row_[3] = {nullptr, nullptr, nullptr};
     GridArray<float> u_[3], density_;
-    GridArray<float2> numw_[3];        // P2G accumulators: (sum w*value, sum w) per face
-    uint8_t *seg_fluid_ = nullptr, *row_fluid_ = nullptr, *row_near_ = nullptr; // coarse occupancy maps of the marker volume
-    int seg_shift_ = 5;
-    uint8_t *face_valid_ = nullptr;  // experimental extrapolation variant (BLUB_EXTRAPOLATE=bytes), else unused
+    GridArray<float2> numw_[3];        // scatter-form P2G accumulators: (sum w*value, sum w) per face (sharded step / comparison path only)
+    FluidBits fluid_bits_ = {nullptr, 0}; // 1 bit per cell "FLUID", rebuilt with every finished marker volume
+    bool fluid_bits_stale_ = false;       // the marker volume was written through a tap since
     GridArray<int8_t> marker_;
-    uint32_t *cell_count_ = nullptr; // binning: per-cell counters / offsets
-    uint32_t *block_sums_ = nullptr;
+    CellLists lists_ = {nullptr, nullptr, nullptr, nullptr}; // per-step cell lists (P2G gather, binning)
+    bool use_scatter_ = false;            // scatter form of P2G on a single GPU (comparison path; the sharded step always scatters)
     const uint2 *voxels_ = nullptr;
 
     std::unique_ptr<PressureSolver> solver_;

@@ -409,6 +409,7 @@ int blub_fluid_upload(BlubFluid *fluid, int tap, const void *host_src, size_t by
         BLUB_CUDA_CHECK(cudaSetDevice(fluid->impl->device()));
         BLUB_CUDA_CHECK(cudaMemcpyAsync(t.ptr, host_src, bytes, cudaMemcpyHostToDevice, fluid->impl->stream()));
         BLUB_CUDA_CHECK(cudaStreamSynchronize(fluid->impl->stream()));
+        if (tap == BLUB_TAP_MARKER) fluid->impl->marker_written_externally();
         return BLUB_OK;
     });
 }
@@ -511,6 +512,13 @@ int blub_fluid_set_solver_path(BlubFluid *fluid, int persistent) {
     s.use_brick = persistent == 5;
     fluid->impl->invalidate_graphs();
     return BLUB_OK;
+}
+
+int blub_fluid_set_transfer_path(BlubFluid *fluid, int scatter) {
+    if (!fluid) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL fluid");
+    if (scatter != 0 && scatter != 1) return fail(BLUB_ERR_INVALID_ARGUMENT, "transfer path must be 0 (gather) or 1 (scatter)");
+    if (fluid->impl->sharded() && scatter == 0) return fail(BLUB_ERR_INVALID_ARGUMENT, "a z-slab rank always uses the scatter form (halo sums of the accumulators)");
+    return guarded([&] { fluid->impl->set_transfer_path(scatter); return BLUB_OK; });
 }
 
 int blub_fluid_set_graph_replay(BlubFluid *fluid, int enabled) {

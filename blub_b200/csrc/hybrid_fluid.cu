@@ -47,25 +47,22 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
         BLUB_CUDA_CHECK(cudaMalloc(&row_[c], pbytes));
         BLUB_CUDA_CHECK(cudaMemset(row_[c], 0, pbytes));
         u_[c].alloc(grid_);
-        numw_[c].alloc(grid_);
+        if (slab_world_ > 1) numw_[c].alloc(grid_); // accumulators of the scatter form (sharded step); single GPU: on demand
     }
     density_.alloc(grid_);
     marker_.alloc(grid_);
-    seg_shift_ = (nx % 32 == 0) ? 5 : 3;
-    BLUB_CUDA_CHECK(cudaMalloc(&seg_fluid_, (size_t)(grid_.n >> seg_shift_)));
-    BLUB_CUDA_CHECK(cudaMalloc(&row_fluid_, (size_t)ny * nz));
-    BLUB_CUDA_CHECK(cudaMalloc(&row_near_, (size_t)ny * nz));
-    BLUB_CUDA_CHECK(cudaMemset(row_near_, 0, (size_t)ny * nz));
-    BLUB_CUDA_CHECK(cudaMemset(seg_fluid_, 0, (size_t)(grid_.n >> seg_shift_)));
-    BLUB_CUDA_CHECK(cudaMemset(row_fluid_, 0, (size_t)ny * nz));
-    if (const char *ex = std::getenv("BLUB_EXTRAPOLATE")) {
-        if (std::string(ex) == "bytes") { // opt-in experiment, see extrapolate_bytes_kernel
-            BLUB_CUDA_CHECK(cudaMalloc(&face_valid_, (size_t)grid_.n));
-            BLUB_CUDA_CHECK(cudaMemset(face_valid_, 0, (size_t)grid_.n));
-        }
+    fluid_bits_.wpr = ((int)nx + 31) / 32;
+    BLUB_CUDA_CHECK(cudaMalloc(&fluid_bits_.words, (size_t)fluid_bits_.wpr * ny * nz * sizeof(uint32_t)));
+    BLUB_CUDA_CHECK(cudaMemset(fluid_bits_.words, 0, (size_t)fluid_bits_.wpr * ny * nz * sizeof(uint32_t)));
+    BLUB_CUDA_CHECK(cudaMalloc(&lists_.cell_start, (size_t)(grid_.n + 1 + 8) * sizeof(uint32_t)));
+    BLUB_CUDA_CHECK(cudaMemset(lists_.cell_start, 0, (size_t)(grid_.n + 1 + 8) * sizeof(uint32_t)));
+    BLUB_CUDA_CHECK(cudaMalloc(&lists_.order, ((size_t)max_num_particles + 64) * sizeof(uint32_t)));
+    BLUB_CUDA_CHECK(cudaMalloc(&lists_.cell_slot, ((size_t)max_num_particles + 64) * sizeof(uint2)));
+    BLUB_CUDA_CHECK(cudaMalloc(&lists_.block_sums, (size_t)(binning_scan_blocks(grid_) + 1024) * sizeof(uint32_t)));
+    configure_transfer_kernels();
+    if (const char *tp = std::getenv("BLUB_P2G")) {
+        if (std::string(tp) == "scatter") set_transfer_path(1);
     }
-    BLUB_CUDA_CHECK(cudaMalloc(&cell_count_, (size_t)grid_.n * sizeof(uint32_t)));
-    BLUB_CUDA_CHECK(cudaMalloc(&block_sums_, (size_t)(binning_scan_blocks(grid_) + 1024) * sizeof(uint32_t)));
     SolverConfig cfg; // defaults .1 / 32 / 4, hybrid_fluid.rs:253-257
     if (slab_world_ > 1) {
         // peer-visible window: [mailbox 4 KiB | residual | pressure (velocity) | pressure (density)], one cudaMalloc so that
@@ -126,12 +123,11 @@ HybridFluid::~HybridFluid() {
     }
     density_.release();
     marker_.release();
-    cudaFree(cell_count_);
-    cudaFree(seg_fluid_);
-    cudaFree(row_fluid_);
-    cudaFree(row_near_);
-    if (face_valid_) cudaFree(face_valid_);
-    cudaFree(block_sums_);
+    cudaFree(fluid_bits_.words);
+    cudaFree(lists_.cell_start);
+    cudaFree(lists_.order);
+    cudaFree(lists_.cell_slot);
+    cudaFree(lists_.block_sums);
     if (solver_ && solver_->comm.seq) cudaFree(solver_->comm.seq);
     solver_.reset();
     field_velocity_.reset();
@@ -353,22 +349,49 @@ void HybridFluid::upload_step_params(float dt) {
     BLUB_CUDA_CHECK(cudaEventRecord(param_events_[slot], stream_));
 }
 
+// The extrapolation works on the FLUID bit mask, which every marker-finishing pass of a step rebuilds.  A marker volume written
+// from outside (test taps) makes it stale: rebuild it from the marker volume as it is.
+void HybridFluid::refresh_fluid_bits() {
+    if (!fluid_bits_stale_) return;
+    launch_fluid_bits(stream_, grid_, marker_.ptr, fluid_bits_);
+    fluid_bits_stale_ = false;
+}
+
+// 0: gather form of P2G (default), 1: scatter form (RED.ADD.F32x2 into accumulator volumes; what the sharded step uses)
+void HybridFluid::set_transfer_path(int scatter) {
+    BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    if (scatter && !numw_[0].ptr)
+        for (int c = 0; c < 3; ++c) numw_[c].alloc(grid_);
+    use_scatter_ = scatter != 0;
+    destroy_graphs();
+}
+
 // Stage numbering shared with oracle/blub_oracle.c:orc_step_stages (the order of hybrid_fluid.rs:798-974).
 void HybridFluid::run_stage(int stage, float dt) {
     float *u[3] = {u_[0].ptr, u_[1].ptr, u_[2].ptr};
     float2 *nw[3] = {numw_[0].ptr, numw_[1].ptr, numw_[2].ptr};
-    const MarkerFlags flags = {seg_fluid_, row_fluid_, row_near_, seg_shift_, face_valid_};
+    const FluidBits &bits = fluid_bits_;
     const bool shard = slab_world_ > 1 && solver_->comm.world > 1;
     const uint32_t np = slab_world_ > 1 ? max_num_particles_ : num_particles_; // sharded: the device-side count guards the kernels
     switch (stage) {
     case 0: // transfer particle velocity to grid (:806-833)
-        if (!shard) {
-            launch_p2g(stream_, grid_, params_dev_, np, pos_[cur_], row_, u, nw, marker_.ptr, voxels_, flags);
+        if (!shard && !use_scatter_) {
+            // cell lists -> marker (+ FLUID bits) -> one gather per component; deterministic, no accumulator volumes
+            launch_cell_lists(stream_, grid_, params_dev_, np, pos_[cur_], 1.0f, lists_);
+            launch_marker_from_lists(stream_, grid_, lists_, marker_.ptr, voxels_, bits);
+            fluid_bits_stale_ = false;
+            if (np > 0) launch_p2g_gather(stream_, grid_, params_dev_, lists_, pos_[cur_], row_, marker_.ptr, u);
+            else for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(u[c], 0, (size_t)grid_.n * sizeof(float), stream_));
+        } else if (!shard) {
+            launch_p2g_scatter(stream_, grid_, params_dev_, np, pos_[cur_], row_, nw, marker_.ptr);
+            launch_p2g_finish(stream_, grid_, params_dev_, u, nw, marker_.ptr, voxels_, bits);
+            fluid_bits_stale_ = false;
         } else {
             launch_p2g_scatter(stream_, grid_, params_dev_, np, pos_[cur_], row_, nw, marker_.ptr);
             const SlabHaloItem items[4] = {{nw[0], sizeof(float2), 0}, {nw[1], sizeof(float2), 0}, {nw[2], sizeof(float2), 0}, {marker_.ptr, 1, 1}};
             slab_halo_exchange(items, 4); // X1
-            launch_p2g_finish(stream_, grid_, params_dev_, u, nw, marker_.ptr, voxels_, flags);
+            launch_p2g_finish(stream_, grid_, params_dev_, u, nw, marker_.ptr, voxels_, bits);
+            fluid_bits_stale_ = false;
         }
         break;
     case 1: // compute divergence -> PCG residual (:835-840)
@@ -380,7 +403,7 @@ void HybridFluid::run_stage(int stage, float dt) {
         break;
     case 3: // particle binning every n-th step, including step 0 (:854-894)
         if (dynamic_settings_.particle_rebinning_step_frequency != 0 && step_counter_ % dynamic_settings_.particle_rebinning_step_frequency == 0) {
-            launch_binning(stream_, grid_, params_dev_, np, pos_[cur_], pos_[1 - cur_], cell_count_, block_sums_);
+            launch_binning(stream_, grid_, params_dev_, np, pos_[cur_], pos_[1 - cur_], lists_);
             if (np > 0) cur_ = 1 - cur_; // ping-pong instead of the reference's full-buffer copy-back (:884-892)
         }
         break;
@@ -388,7 +411,8 @@ void HybridFluid::run_stage(int stage, float dt) {
         launch_divergence_remove(stream_, grid_, marker_.ptr, field_velocity_->pressure(), voxels_, u);
         break;
     case 5: // extrapolate velocity grid (:906-909)
-        launch_extrapolate(stream_, grid_, marker_.ptr, flags, u);
+        refresh_fluid_bits();
+        launch_extrapolate(stream_, grid_, bits, u);
         if (shard) {
             const SlabHaloItem items[3] = {{u[0], sizeof(float), 2}, {u[1], sizeof(float), 2}, {u[2], sizeof(float), 2}};
             slab_halo_exchange(items, 3); // X2
@@ -408,7 +432,8 @@ void HybridFluid::run_stage(int stage, float dt) {
         }
         break;
     case 8: // density projection: set boundary marker (:923-927)
-        launch_boundary_marker(stream_, grid_, marker_.ptr, voxels_, flags);
+        launch_boundary_marker(stream_, grid_, marker_.ptr, voxels_, bits);
+        fluid_bits_stale_ = false;
         break;
     case 9: // density projection: compute density error (:928-932)
         if (!shard) {
@@ -428,7 +453,8 @@ void HybridFluid::run_stage(int stage, float dt) {
         launch_position_change(stream_, grid_, params_dev_, marker_.ptr, field_density_->pressure(), u);
         break;
     case 12: // extrapolate (:963-966)
-        launch_extrapolate(stream_, grid_, marker_.ptr, flags, u);
+        refresh_fluid_bits();
+        launch_extrapolate(stream_, grid_, bits, u);
         if (shard) {
             const SlabHaloItem items[3] = {{u[0], sizeof(float), 2}, {u[1], sizeof(float), 2}, {u[2], sizeof(float), 2}};
             slab_halo_exchange(items, 3); // X5

@@ -163,6 +163,7 @@ def lib():
         "blub_fluid_step_timed": (C.c_int, [vp, C.c_double, C.POINTER(C.c_float)]),
         "blub_fluid_set_graph_replay": (C.c_int, [vp, C.c_int]),
         "blub_fluid_set_solver_path": (C.c_int, [vp, C.c_int]),
+        "blub_fluid_set_transfer_path": (C.c_int, [vp, C.c_int]),
         "blub_kernel_launch_count": (C.c_uint64, [C.c_int]),
     }
     for name, (res, args) in sig.items():
@@ -441,6 +442,10 @@ class HybridFluid:
         else:
             mode = 2 if persistent in (2, "tma") else (1 if persistent else 0)
         _check(self.L.blub_fluid_set_solver_path(self.h, mode))
+
+    def set_transfer_path(self, scatter):
+        """False / "gather" (default): deterministic gather P2G over per-step cell lists; True / "scatter": warp-aggregated atomic scatter."""
+        _check(self.L.blub_fluid_set_transfer_path(self.h, 1 if scatter in (True, 1, "scatter") else 0))
 
     def stream(self):
         """The CUDA stream (as an integer handle) the fluid's work is enqueued on."""

@@ -263,10 +263,14 @@ int blub_fluid_time_steps(BlubFluid *fluid, double simulation_delta_seconds, int
 /* one eagerly launched step with CUDA events between the 14 stages (same numbering as blub_fluid_step_stages); synchronises */
 int blub_fluid_step_timed(BlubFluid *fluid, double simulation_delta_seconds, float ms_per_stage[14]);
 /* PCG implementation: 1 (default) = one persistent cooperative kernel per solve, 0 = three kernels per iteration,
- * 2 = the persistent kernel with TMA-staged tiles, 3 = its double-buffered one-block-per-SM form (grids with nx % 128 == 0 only),
+ * 2 = the persistent kernel with TMA-staged tiles (grids with nx % 128 == 0 only),
  * 4 = the persistent kernel without its per-thread sparsity skip (bit-identical results; for comparison),
- * 5 = EXPERIMENTAL: the persistent kernel with one warp per 32x4x4 brick (nx % 32 == 0; falls back to 1 otherwise) */
+ * 5 = the persistent kernel with one warp per 32x4x4 brick (nx % 32 == 0, single GPU).  A request that cannot be met returns
+ * BLUB_ERR_INVALID_ARGUMENT and changes nothing. */
 int blub_fluid_set_solver_path(BlubFluid *fluid, int persistent);
+/* particle -> grid velocity transfer (transfer_gather_velocity.comp): 0 (default) = deterministic gather over per-step cell lists,
+ * 1 = warp-aggregated float-atomic scatter into accumulator volumes (what z-slab ranks always use) */
+int blub_fluid_set_transfer_path(BlubFluid *fluid, int scatter);
 /* blub_fluid_step replays a captured CUDA graph of the step by default; 0 = launch every kernel eagerly instead */
 int blub_fluid_set_graph_replay(BlubFluid *fluid, int enabled);
 /* number of kernels launched by this library since the last reset (bench.py's gpu_launches) */

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call, many answers: every call costs 1.5-3 minutes of box time before the command even starts, so measurements are
 # batched.  Usage (from the repository root, on the GPU box):
-#     bash tools/gpu_session.sh [tests] [experimental] [smoke] [timeline] [variants] [bench] [launches] [ncu] [blubrun]
+#     bash tools/gpu_session.sh [tests] [experimental] [smoke] [timeline] [variants] [ncustep] [bench] [launches] [ncu] [blubrun]
 # Everything lands in gpurun_out/session_*.{txt,json,csv}; nothing here is a bench number unless it comes from bench.py outside ncu.
 set -u
 OUT=gpurun_out
@@ -25,16 +25,17 @@ if want timeline; then      # stage times over a dam break
     python tools/profile_targets.py stages dam_halfhalf_highres 3 56 110 > $OUT/session_timeline_default_c3.txt 2>&1
     for f in default default_c3; do echo "== $f"; cat $OUT/session_timeline_$f.txt; done
 fi
-if want variants; then      # each opt-in variant against the default timeline
-    BLUB_EXTRAPOLATE=bytes python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_extrapolate_bytes.txt 2>&1
-    BLUB_SCATTER=aggregate python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_scatter_aggregate.txt 2>&1
+if want variants; then      # comparison paths against the default timeline
+    BLUB_P2G=scatter python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_p2g_scatter.txt 2>&1
     BLUB_PCG=brick python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_brick.txt 2>&1
-    BLUB_PCG=brick BLUB_PCG_BRICK_BLOCKS=3 python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_brick3.txt 2>&1
-    BLUB_PCG=brick python tools/profile_targets.py stages dam_halfhalf_highres 3 56 110 > $OUT/session_timeline_pcg_brick_c3.txt 2>&1
-    python tools/profile_targets.py pcg 256 6 brick > $OUT/session_pcg_dense_brick.txt 2>&1
-    python tools/profile_targets.py pcg 256 6 > $OUT/session_pcg_dense_default.txt 2>&1
-    for f in extrapolate_bytes scatter_aggregate pcg_brick pcg_brick3 pcg_brick_c3; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total|Error|error" $OUT/session_timeline_$f.txt; done
-    cat $OUT/session_pcg_dense_brick.txt $OUT/session_pcg_dense_default.txt
+    for f in p2g_scatter pcg_brick; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total|Error|error" $OUT/session_timeline_$f.txt; done
+fi
+if want ncustep; then       # full captures INSIDE the dam break (eager launches): the sparse PCG solve at step 110, one P2G gather
+    BLUB_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pcg_solve_persistent --launch-skip 220 -c 1 -o $OUT/session_pcg_step110 \
+        python tools/profile_targets.py step dam_256 111 > $OUT/session_ncu_pcg_step110.log 2>&1
+    BLUB_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:p2g_gather --launch-skip 15 -c 3 -o $OUT/session_p2g_gather \
+        python tools/profile_targets.py step dam_256 7 > $OUT/session_ncu_p2g.log 2>&1
+    ls -la $OUT/*.ncu-rep
 fi
 if want bench; then
     timeout 600 python bench.py > $OUT/session_bench.json 2> $OUT/session_bench.err
