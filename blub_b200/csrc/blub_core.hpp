@@ -272,7 +272,7 @@ class HybridFluid {
     FluidBits fluid_bits_ = {nullptr, 0}; // 1 bit per cell "FLUID", rebuilt with every finished marker volume
     bool fluid_bits_stale_ = false;       // the marker volume was written through a tap since
     GridArray<int8_t> marker_;
-    CellLists lists_ = {nullptr, nullptr, nullptr, nullptr}; // per-step cell lists (P2G gather, binning)
+    CellLists lists_ = {nullptr, nullptr, nullptr, nullptr, nullptr}; // per-step cell lists (P2G gather, binning)
     bool use_scatter_ = false;            // scatter form of P2G on a single GPU (comparison path; the sharded step always scatters)
     const uint2 *voxels_ = nullptr;
 

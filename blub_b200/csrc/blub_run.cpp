@@ -39,7 +39,8 @@ static void die(const char *what) {
 int main(int argc, char **argv) {
     if (argc < 2) {
         std::fprintf(stderr, "usage: blub_run scene.json [--steps N] [--batch 16] [--hz 120] [--device 0] [--no-graph]\n"
-                             "                [--stats out.json] [--trace out.json] [--dump particles.f32] [--models DIR] [--record FPS PREFIX]\n");
+                             "                [--stats out.json] [--trace out.json] [--dump particles.f32] [--models DIR] [--record FPS PREFIX]\n"
+                             "                [--solver TOLERANCE MAX_ITERATIONS CHECK_FREQUENCY] [--rebin EVERY_N_STEPS]\n");
         return 2;
     }
     const char *scene = argv[1];
@@ -47,6 +48,8 @@ int main(int argc, char **argv) {
     long hz = 120;
     std::string stats_path, trace_path, dump_path, models_dir = "models", record_prefix;
     double record_fps = 0.0;
+    float solver_tol = -1.0f;
+    int solver_max = 0, solver_freq = 0, rebin = -1;
     for (int i = 2; i < argc; ++i) {
         auto next = [&](const char *flag) -> const char * {
             if (i + 1 >= argc) { std::fprintf(stderr, "blub_run: %s needs a value\n", flag); std::exit(2); }
@@ -61,6 +64,8 @@ int main(int argc, char **argv) {
         else if (!std::strcmp(argv[i], "--trace")) trace_path = next("--trace");
         else if (!std::strcmp(argv[i], "--dump")) dump_path = next("--dump");
         else if (!std::strcmp(argv[i], "--models")) models_dir = next("--models");
+        else if (!std::strcmp(argv[i], "--solver")) { solver_tol = (float)std::atof(next("--solver")); solver_max = std::atoi(next("--solver")); solver_freq = std::atoi(next("--solver")); }
+        else if (!std::strcmp(argv[i], "--rebin")) rebin = std::atoi(next("--rebin"));
         else if (!std::strcmp(argv[i], "--record")) { record_fps = std::atof(next("--record")); record_prefix = next("--record"); }
         else { std::fprintf(stderr, "blub_run: unknown option %s\n", argv[i]); return 2; }
     }
@@ -75,6 +80,15 @@ int main(int argc, char **argv) {
     BlubFluid *fluid = nullptr;
     if (blub_scene_load(&fluid, scene, device, nullptr)) die("cannot create fluid");
     blub_fluid_set_graph_replay(fluid, graph);
+    if (solver_max > 0) { // the GUI's solver sliders (src/gui/mod.rs:228-250) write the same two SolverConfig structs
+        for (int which = 0; which < 2; ++which) {
+            BlubSolverConfig *c = blub_fluid_solver_config(fluid, which);
+            c->error_tolerance = solver_tol;
+            c->max_num_iterations = solver_max;
+            c->error_check_frequency = solver_freq > 0 ? solver_freq : 4;
+        }
+    }
+    if (rebin >= 0) *blub_fluid_rebinning_frequency(fluid) = (uint32_t)rebin;
     std::printf("scene %s: grid %ux%ux%u, %u particles (max %u), %u static object(s), dt %.9f s\n", scene, info.grid_dimension[0],
                 info.grid_dimension[1], info.grid_dimension[2], blub_fluid_num_particles(fluid), info.max_num_particles, info.num_static_objects, dt);
 

@@ -19,6 +19,7 @@ struct FluidBits {
 struct CellLists {
     uint32_t *cell_start; // n + 1 entries
     uint32_t *order;      // max_num_particles entries
+    uint32_t *arrival;    // scratch: the lists in arrival order of the count atomics, before canonicalisation
     uint2 *cell_slot;     // scratch: (cell, arrival slot) per particle
     uint32_t *block_sums; // scratch of the scan
 };

@@ -5,10 +5,27 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "blub_core.hpp"
 #include "fluid_kernels.hpp"
 
 namespace blub {
+
+namespace {
+// NVTX ranges with the reference's profiler scope labels (hybrid_fluid.rs:780-973): a timeline of a run under
+// Nsight shows the same tree the reference's "Write Chrometrace" shows.  Header-only NVTX: no cost without a profiler attached.
+const char *const kScopeLabels[14] = {
+    "transfer particle velocity to grid", "compute divergence", "primary pressure solver (divergence)", "Particle Binning",
+    "make velocity grid divergence free", "extrapolate velocity grid", "clear marker & linked list grids",
+    "advect particles & write new linked list grid", "density projection: set boundary marker",
+    "density projection: compute density error via gather", "secondary pressure solver (density)", "compute position change",
+    "extrapolate velocity grid", "correct particle density error"};
+struct NvtxScope {
+    explicit NvtxScope(const char *name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
+};
+} // namespace
 
 HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num_particles, int device, cudaStream_t stream, int slab_rank,
                          int slab_world)
@@ -57,6 +74,7 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
     BLUB_CUDA_CHECK(cudaMalloc(&lists_.cell_start, (size_t)(grid_.n + 1 + 8) * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMemset(lists_.cell_start, 0, (size_t)(grid_.n + 1 + 8) * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMalloc(&lists_.order, ((size_t)max_num_particles + 64) * sizeof(uint32_t)));
+    BLUB_CUDA_CHECK(cudaMalloc(&lists_.arrival, ((size_t)max_num_particles + 64) * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMalloc(&lists_.cell_slot, ((size_t)max_num_particles + 64) * sizeof(uint2)));
     BLUB_CUDA_CHECK(cudaMalloc(&lists_.block_sums, (size_t)(binning_scan_blocks(grid_) + 1024) * sizeof(uint32_t)));
     configure_transfer_kernels();
@@ -126,6 +144,7 @@ HybridFluid::~HybridFluid() {
     cudaFree(fluid_bits_.words);
     cudaFree(lists_.cell_start);
     cudaFree(lists_.order);
+    cudaFree(lists_.arrival);
     cudaFree(lists_.cell_slot);
     cudaFree(lists_.block_sums);
     if (solver_ && solver_->comm.seq) cudaFree(solver_->comm.seq);
@@ -373,6 +392,7 @@ void HybridFluid::run_stage(int stage, float dt) {
     const FluidBits &bits = fluid_bits_;
     const bool shard = slab_world_ > 1 && solver_->comm.world > 1;
     const uint32_t np = slab_world_ > 1 ? max_num_particles_ : num_particles_; // sharded: the device-side count guards the kernels
+    const NvtxScope scope(stage >= 0 && stage < 14 ? kScopeLabels[stage] : "stage");
     switch (stage) {
     case 0: // transfer particle velocity to grid (:806-833)
         if (!shard && !use_scatter_) {
@@ -473,6 +493,7 @@ void HybridFluid::run_stage(int stage, float dt) {
 // and replayed with one launch -- dt, gravity*dt and the tolerances reach the kernels through the device StepParams block.
 void HybridFluid::step(double simulation_delta_seconds) {
     BLUB_CUDA_CHECK(cudaSetDevice(device_));
+    const NvtxScope scope("HybridFluid step");
     const float dt = (float)simulation_delta_seconds; // Duration::as_secs_f32
     if (!(dt > 0.0f)) throw std::invalid_argument("simulation delta must be positive");
     field_velocity_->retrieve_new_error_samples(); // pressure_solver.rs:614

@@ -680,6 +680,18 @@ __device__ __forceinline__ void load_column_codes(const TileEnv &e, const TileCt
     for (int k = 0; k < PCG_TZ + 2; ++k) w[k] = c.valid ? ldcw(e.codes + c.i + (k - 1) * e.g.sz) : 0u;
 }
 
+// A warp none of whose columns holds a FLUID cell in the tile's planes or in the two planes around them has nothing to do in any tile
+// body: every value it would load is 0 (zero invariant), it would store nothing and add 0 to the partial sums -- and nobody else
+// depends on it (x-neighbours live in the same warp, y / z neighbours are read from memory).  In a dam break most warps of the
+// "active" tiles along the free surface are like that: skipping them at warp granularity removes the body's instruction skeleton,
+// which is what the sparse solve is bound by (profiles/r02_s2_pcg_step110.md: 1.16 G warp instructions, 17 of 32 lanes active).
+__device__ __forceinline__ bool warp_has_no_fluid(const unsigned (&w)[PCG_TZ + 2]) {
+    unsigned any = 0;
+#pragma unroll
+    for (int k = 0; k < PCG_TZ + 2; ++k) any |= w[k];
+    return !__any_sync(0xffffffffu, any != 0u);
+}
+
 // r <- b - A p, partial z.r  (pressure_init.comp:45-83)
 template <bool SKIP>
 __device__ __forceinline__ void init_tile(const TileEnv &e, const TileCtx &c, const unsigned (&w)[PCG_TZ + 2], const float *p, float *r, float &acc) {
@@ -842,6 +854,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
         const TileCtx c = tile_ctx_id(e.g, t, tile & (TILE_DENSE_BIT - 1));
         unsigned w[PCG_TZ + 2];
         load_column_codes(e, c, w);
+        if (SKIP && warp_has_no_fluid(w)) continue;
         if (!SKIP || (tile & TILE_DENSE_BIT)) init_tile<false>(e, c, w, a.p, a.r, acc);
         else init_tile<true>(e, c, w, a.p, a.r, acc);
     }
@@ -860,6 +873,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
             const TileCtx c = tile_ctx_id(e.g, t, tile & (TILE_DENSE_BIT - 1));
             unsigned w[PCG_TZ + 2];
             load_column_codes(e, c, w);
+            if (SKIP && warp_has_no_fluid(w)) continue;
             if (!SKIP || (tile & TILE_DENSE_BIT)) search_tile<false>(e, c, w, a.r, s_in, s_out, beta, acc);
             else search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
         }
@@ -874,6 +888,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
             const TileCtx c = tile_ctx_id(e.g, t, tile & (TILE_DENSE_BIT - 1));
             unsigned w[PCG_TZ + 2];
             load_column_codes(e, c, w);
+            if (SKIP && warp_has_no_fluid(w)) continue;
             if (!SKIP || (tile & TILE_DENSE_BIT)) update_tile<false>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
             else update_tile<true>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
         }
@@ -1007,6 +1022,7 @@ __global__ void __launch_bounds__(PCG_THREADS, BLOCKS_PER_SM) pcg_solve_brick_ke
         const TileCtx c = brick_ctx_id(e.g, a.bricks, tile & (TILE_DENSE_BIT - 1));
         unsigned w[PCG_TZ + 2];
         load_column_codes(e, c, w);
+        if (SKIP && warp_has_no_fluid(w)) continue;
         if (!SKIP || (tile & TILE_DENSE_BIT)) init_tile<false>(e, c, w, a.p, a.r, acc);
         else init_tile<true>(e, c, w, a.p, a.r, acc);
     }
@@ -1025,6 +1041,7 @@ __global__ void __launch_bounds__(PCG_THREADS, BLOCKS_PER_SM) pcg_solve_brick_ke
             const TileCtx c = brick_ctx_id(e.g, a.bricks, tile & (TILE_DENSE_BIT - 1));
             unsigned w[PCG_TZ + 2];
             load_column_codes(e, c, w);
+            if (SKIP && warp_has_no_fluid(w)) continue;
             if (!SKIP || (tile & TILE_DENSE_BIT)) search_tile<false>(e, c, w, a.r, s_in, s_out, beta, acc);
             else search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
         }
@@ -1039,6 +1056,7 @@ __global__ void __launch_bounds__(PCG_THREADS, BLOCKS_PER_SM) pcg_solve_brick_ke
             const TileCtx c = brick_ctx_id(e.g, a.bricks, tile & (TILE_DENSE_BIT - 1));
             unsigned w[PCG_TZ + 2];
             load_column_codes(e, c, w);
+            if (SKIP && warp_has_no_fluid(w)) continue;
             if (!SKIP || (tile & TILE_DENSE_BIT)) update_tile<false>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
             else update_tile<true>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
         }

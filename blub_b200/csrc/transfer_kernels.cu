@@ -8,7 +8,7 @@
 // README.md:76).  Here:
 //
 //   * CELL LISTS (every step): a counting sort of particle INDICES by primal cell -- count (one integer atomic per particle),
-//     exclusive scan, fill, and a per-cell canonicalisation that puts every cell's slice into ascending particle index.  The
+//     exclusive scan, fill, and a canonicalisation (rank counting) that puts every cell's slice into ascending particle index.  The
 //     lists are therefore a pure function of the particle array: the same input gives the same lists, run after run, whatever
 //     order the atomics arrived in.
 //   * P2G GATHER (default): one thread per primal cell walks its own list and keeps the (sum w*value, sum w) of the 18 faces
@@ -32,7 +32,6 @@ namespace {
 constexpr int PT = 256; // threads per block for particle and cell kernels
 
 __device__ __forceinline__ int lin(const GridDim &g, int x, int y, int z) { return (z * g.ny + y) * g.nx + x; }
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 1) / per_block); }
 
 // The position a transfer sees: clamped so that every face / cell a particle touches exists (a simulated particle is always
@@ -155,32 +154,35 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t *__re
     }
 }
 
-// fill: order[cell_start[cell] + slot] = particle index
+// fill: arrival[cell_start[cell] + slot] = particle index (the slot is whatever the count atomic returned: arbitrary inside a cell)
 __global__ void __launch_bounds__(PT) cell_fill_kernel(const StepParams *__restrict__ params, const uint2 *__restrict__ cell_slot,
-                                                       const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ order) {
+                                                       const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ arrival) {
     const uint32_t i = blockIdx.x * PT + threadIdx.x;
     if (i >= params->num_particles) return;
     const uint2 cs = cell_slot[i];
-    order[cell_start[cs.x] + cs.y] = i;
+    arrival[cell_start[cs.x] + cs.y] = i;
 }
 
-// canonicalise: ascending particle index inside every cell (insertion sort; the atomics mostly arrive in thread order, so the
-// slices are nearly sorted already).  After this the lists no longer depend on the arrival order of the count atomics.
-__global__ void __launch_bounds__(PT) cell_canonicalize_kernel(int64_t n, const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ order) {
-    const int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x;
-    if (c >= n) return;
-    const uint32_t s = cell_start[c], e = cell_start[c + 1];
-    for (uint32_t a = s + 1; a < e; ++a) {
-        const uint32_t v = order[a];
-        uint32_t b = a;
-        while (b > s) {
-            const uint32_t u = order[b - 1];
-            if (u <= v) break;
-            order[b] = u;
-            --b;
-        }
-        if (b != a) order[b] = v;
+// canonicalise: ascending particle index inside every cell, by rank counting -- entry j of cell c goes to position
+// cell_start[c] + #{entries of c smaller than it}.  One thread per list entry, k loads each from one or two cache lines; unlike a
+// per-cell sort this has no serial worst case when a cell is crowded (wave impact on a wall: hundreds of particles in a cell).
+// After this the lists no longer depend on the arrival order of the count atomics.  Cells with more than CANON_MAX particles
+// (256 x rest density: only adversarial inputs) keep their arrival order.
+constexpr uint32_t CANON_MAX = 2048;
+__global__ void __launch_bounds__(PT) cell_canonicalize_kernel(const StepParams *__restrict__ params, const uint2 *__restrict__ cell_slot,
+                                                               const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ arrival,
+                                                               uint32_t *__restrict__ order) {
+    const uint32_t j = blockIdx.x * PT + threadIdx.x;
+    if (j >= params->num_particles) return;
+    const uint32_t v = arrival[j];
+    const uint32_t cell = cell_slot[v].x;
+    const uint32_t s = cell_start[cell], e = cell_start[cell + 1];
+    uint32_t rank = j - s;
+    if (e - s <= CANON_MAX) {
+        rank = 0;
+        for (uint32_t t = s; t < e; ++t) rank += arrival[t] < v ? 1u : 0u;
     }
+    order[s + rank] = v;
 }
 
 // Which cells of a 32-cell word the boundary rule makes SOLID: border cells and solid voxels (transfer_set_boundary_marker.comp:11-20)
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(PT) fluid_bits_kernel(GridDim g, FluidBits bit
 // combined across x (shuffles: lane L's face gets lane L+1's "x - 1" slot and lane L-1's "x + 1" slot) and z (shared memory),
 // normalised and stored.  The outermost lanes / warps / rows of a block are halo: computed, never stored.
 constexpr int GW = 6;     // z rows stored by a block (warps = GW + 2)
-constexpr int GLY = 16;   // face rows stored by a block
+constexpr int GLY = 32;   // face rows stored by a block
 constexpr int GXS = 30;   // faces along x stored by a block (lanes 1..30)
 constexpr int GCAP = 384; // particles a warp stages per cell row (7 floats each); the rest of a longer row is read from global memory
 constexpr int GATHER_THREADS = 32 * (GW + 2);
@@ -370,13 +372,17 @@ __global__ void __launch_bounds__(GATHER_THREADS, 2) p2g_gather_kernel(GridDim g
                             const float4 r = rowc[idx];
                             px = p.x; py = p.y; pz = p.z; r0 = r.x; r1 = r.y; r2 = r.z; r3 = r.w;
                         }
-                        float tx[NFX], ty[NFY], tz[NFZ], wx[NFX], wy[NFY], wzv[NFZ];
+                        float tx[NFX], ty[NFY], tz[NFZ], wx[NFX], wy[NFY], wzv[NFZ], vz[NFZ];
 #pragma unroll
                         for (int f = 0; f < NFX; ++f) { tx[f] = ((fcx + (float)(f - 1)) + OX) - px; wx[f] = saturatef(1.0f - fabsf(tx[f])); }
 #pragma unroll
                         for (int f = 0; f < NFY; ++f) { ty[f] = ((fcy + (float)(f - 1)) + OY) - py; wy[f] = saturatef(1.0f - fabsf(ty[f])); }
 #pragma unroll
-                        for (int f = 0; f < NFZ; ++f) { tz[f] = ((fcz + (float)(f - 1)) + OZ) - pz; wzv[f] = saturatef(1.0f - fabsf(tz[f])); }
+                        for (int f = 0; f < NFZ; ++f) {
+                            tz[f] = ((fcz + (float)(f - 1)) + OZ) - pz;
+                            wzv[f] = saturatef(1.0f - fabsf(tz[f]));
+                            vz[f] = fmaf(r2, tz[f], r3);
+                        }
 #pragma unroll
                         for (int fy = 0; fy < NFY; ++fy)
 #pragma unroll
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 2) p2g_gather_kernel(GridDim g
 #pragma unroll
                                 for (int fz = 0; fz < NFZ; ++fz) {
                                     const float w = wxy * wzv[fz];
-                                    const float v = fmaf(r2, tz[fz], vxy) + r3;
+                                    const float v = vxy + vz[fz]; // (r0 tx + r1 ty) + (r2 tz + r3)
                                     acc[fy][fx][fz].x = fmaf(w, v, acc[fy][fx][fz].x);
                                     acc[fy][fx][fz].y += w;
                                 }
@@ -620,8 +626,8 @@ void launch_cell_lists(cudaStream_t st, const GridDim &g, const StepParams *para
     BLUB_LAUNCH(scan_sums_kernel, 1, 1024, 0, st, l.block_sums, nb);
     BLUB_LAUNCH(scan_apply_kernel, nb, SCAN_THREADS, 0, st, l.cell_start, n1, l.block_sums);
     if (np_upper == 0) return;
-    BLUB_LAUNCH(cell_fill_kernel, blocks_for(np_upper, PT), PT, 0, st, params, l.cell_slot, l.cell_start, l.order);
-    BLUB_LAUNCH(cell_canonicalize_kernel, blocks_for(g.n, PT), PT, 0, st, g.n, l.cell_start, l.order);
+    BLUB_LAUNCH(cell_fill_kernel, blocks_for(np_upper, PT), PT, 0, st, params, l.cell_slot, l.cell_start, l.arrival);
+    BLUB_LAUNCH(cell_canonicalize_kernel, blocks_for(np_upper, PT), PT, 0, st, params, l.cell_slot, l.cell_start, l.arrival, l.order);
 }
 
 void launch_marker_from_lists(cudaStream_t st, const GridDim &g, const CellLists &l, int8_t *marker, const uint2 *vox, const FluidBits &bits) {
@@ -646,8 +652,9 @@ void configure_transfer_kernels() {
 void launch_p2g_gather(cudaStream_t st, const GridDim &g, const StepParams *params, const CellLists &l, const float4 *pos, float4 *const row[3],
                        const int8_t *marker, float *const u[3]) {
     const dim3 grid((g.nx + GXS - 1) / GXS, (g.ny + GLY - 1) / GLY, (g.nz + GW - 1) / GW);
-    // faces no block stores (blocks without particles return at once) are 0, like every face away from the fluid
-    for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(u[c], 0, (size_t)g.n * sizeof(float), st));
+    // Faces no block stores (blocks without particles return at once) keep their previous value, as in the reference, which only
+    // writes faces that touch a FLUID cell (transfer_gather_velocity.comp:41-47): nothing reads them before
+    // divergence_remove rewrites every face.
     BLUB_LAUNCH(p2g_gather_kernel<0>, grid, GATHER_THREADS, GATHER_SMEM_BYTES, st, g, params, l.cell_start, l.order, pos, row[0], marker, u[0]);
     BLUB_LAUNCH(p2g_gather_kernel<1>, grid, GATHER_THREADS, GATHER_SMEM_BYTES, st, g, params, l.cell_start, l.order, pos, row[1], marker, u[1]);
     BLUB_LAUNCH(p2g_gather_kernel<2>, grid, GATHER_THREADS, GATHER_SMEM_BYTES, st, g, params, l.cell_start, l.order, pos, row[2], marker, u[2]);

@@ -50,12 +50,12 @@ def test_hydrostatic_known_answer_on_gpu():
     assert np.abs(uy[1:n - 1, 1:8, 1:n - 1]).max() < 3e-3
 
 
-STAGE_TAPS = [(F.TAP_UX, O.ARR_UX), (F.TAP_UY, O.ARR_UY), (F.TAP_UZ, O.ARR_UZ)]
-
-
 @pytest.mark.parametrize("precond", [0, 1])
 def test_stagewise_parity_one_step(precond):
-    """Both implementations walk the 14 stages of one step from identical particles; taps are compared after each."""
+    """Both implementations walk the 14 stages of one step from identical particles; taps are compared after each (tests/stagewise.py).
+    Solver at the reference's defaults (0.1 / 32 / 4): iteration counts must be equal."""
+    from tests import stagewise
+
     orc, gpu = make_pair("dam_small", rebin=0, precond=precond)
     # give the particles a non-trivial velocity / affine state
     rng = np.random.default_rng(5)
@@ -70,56 +70,7 @@ def test_stagewise_parity_one_step(precond):
     for f in (orc, gpu):
         f.set_solver_config(0, 0.1, 32, 4)
         f.set_solver_config(1, 0.1, 32, 4)
-
-    def run(a, b):
-        orc.step_stages(DT, a, b)
-        gpu.step_stages(DT, a, b)
-
-    run(0, 1)  # P2G
-    m_o, m_g = orc.grid(O.ARR_MARKER), gpu.download_grid(F.TAP_MARKER)
-    assert np.array_equal(m_o, m_g)
-    for c, (tg, to) in enumerate(STAGE_TAPS):
-        grid_close(orc.grid(to), gpu.download_grid(tg), f"P2G u[{c}]", mask=util.fluid_adjacent_faces(m_o, c))
-    fl = m_o == O.FLUID
-    run(1, 2)  # rhs 1
-    grid_close(orc.grid(O.ARR_RESIDUAL), gpu.download_grid(F.TAP_RESIDUAL), "rhs1", mask=fl)
-    run(2, 3)  # solve 1
-    eo, io = orc.last_solve(0)
-    eg, ig = gpu.last_solve(0)
-    assert io == ig, (io, ig)
-    grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), "p1", rel=5e-3, abs_=1e-4)
-    # continue from the ORACLE's pressure so that solver round-off does not leak into the per-stage comparison
-    gpu.upload_grid(F.TAP_P_VEL, orc.grid(O.ARR_P_VEL))
-    run(3, 5)  # (binning off) + divergence_remove
-    for c, (tg, to) in enumerate(STAGE_TAPS):
-        grid_close(orc.grid(to), gpu.download_grid(tg), f"projected u[{c}]")
-    run(5, 6)  # extrapolate
-    for c, (tg, to) in enumerate(STAGE_TAPS):
-        grid_close(orc.grid(to), gpu.download_grid(tg), f"extrapolated u[{c}]")
-    for c, (tg, to) in enumerate(STAGE_TAPS):
-        gpu.upload_grid(tg, orc.grid(to))
-    run(6, 9)  # clear + advect + boundary marker
-    assert np.array_equal(orc.grid(O.ARR_MARKER), gpu.download_grid(F.TAP_MARKER))
-    p_o, p_g = orc.particles()[:, :3], gpu.download_particles()[:, :3]
-    assert np.abs(p_o - p_g).max() <= 2e-4
-    vmax = max(np.abs(orc.particles(O.ARR_ROWX)[:, 3]).max(), 1.0)
-    for k, (tg, to) in enumerate([(F.TAP_VX, O.ARR_ROWX), (F.TAP_VY, O.ARR_ROWY), (F.TAP_VZ, O.ARR_ROWZ)]):
-        d = np.abs(orc.particles(to) - gpu.download_particles(tg)).max()
-        assert d <= 1e-3 * vmax, (k, d, vmax)
-    gpu.set_particles(np.c_[p_o, np.zeros(npart, np.float32)], orc.particles(O.ARR_ROWX), orc.particles(O.ARR_ROWY), orc.particles(O.ARR_ROWZ))
-    run(9, 10)  # rhs 2
-    fl = orc.grid(O.ARR_MARKER) == O.FLUID
-    grid_close(orc.grid(O.ARR_RESIDUAL), gpu.download_grid(F.TAP_RESIDUAL), "rhs2", rel=1e-4, abs_=2e-3, mask=fl)
-    run(10, 11)  # solve 2
-    assert orc.last_solve(1)[1] == gpu.last_solve(1)[1]
-    grid_close(orc.grid(O.ARR_P_DEN), gpu.download_grid(F.TAP_P_DEN), "p2", rel=5e-3, abs_=1e-4)
-    gpu.upload_grid(F.TAP_P_DEN, orc.grid(O.ARR_P_DEN))
-    run(11, 13)  # position change + extrapolate
-    for c, (tg, to) in enumerate(STAGE_TAPS):
-        grid_close(orc.grid(to), gpu.download_grid(tg), f"displacement[{c}]")
-        gpu.upload_grid(tg, orc.grid(to))
-    run(13, 14)  # correct particles
-    assert np.abs(orc.particles()[:, :3] - gpu.download_particles()[:, :3]).max() <= 2e-4
+    stagewise.compare_one_step(orc, gpu)
 
 
 def test_binning_is_a_permutation_sorted_by_cell():

@@ -55,6 +55,24 @@ elif mode == "stages_sharded":
         print(f"{name:24s} " + "  ".join(f"{a[i] / reps:8.3f}" for a in acc) + " ms")
     print(f"{'total':24s} " + "  ".join(f"{a.sum() / reps:8.3f}" for a in acc) + " ms (eager, per rank)")
     print("errors", [s.slab_error() for s in slabs], "particles", [s.num_particles for s in slabs])
+elif mode == "cellstats":
+    # python tools/profile_targets.py cellstats [scene] [steps ...]: how crowded do cells get (particles per cell) over a run
+    scene = sys.argv[2] if len(sys.argv) > 2 else "dam_256"
+    checkpoints = [int(a) for a in sys.argv[3:]] or [3, 56, 110]
+    f = blub_b200.HybridFluid.from_scene(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".json"))
+    done = 0
+    for cp in checkpoints:
+        while done < cp:
+            f.step(F.DT_120HZ)
+            done += 1
+        p = f.download_particles()[:, :3]
+        c = np.floor(p).astype(np.int64)
+        cnt = np.bincount((c[:, 2] * f.ny + c[:, 1]) * f.nx + c[:, 0], minlength=f.n)
+        nz = cnt[cnt > 0]
+        rows = cnt.reshape(f.nz, f.ny, f.nx)
+        seg = rows.reshape(f.nz, f.ny, f.nx // 32, 32).sum(-1) if f.nx % 32 == 0 else rows.sum(-1, keepdims=True)
+        print(f"step {cp}: fluid cells {nz.size} ({100.0 * nz.size / f.n:.1f} %), particles per fluid cell mean {nz.mean():.2f} q99.9 {np.quantile(nz, 0.999):.0f} max {cnt.max()}, "
+              f"cells > 32: {(cnt > 32).sum()}, > 100: {(cnt > 100).sum()}, > 1000: {(cnt > 1000).sum()}; particles per 32-cell row segment max {seg.max()}, > 384: {(seg > 384).sum()}", flush=True)
 elif mode == "stages":
     # python tools/profile_targets.py stages [scene] [checkpoint steps ...]: stage times after so many steps (default 3)
     scene = sys.argv[2] if len(sys.argv) > 2 else "dam_256"
