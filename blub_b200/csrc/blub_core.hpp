@@ -129,17 +129,17 @@ class PressureSolver {
     bool use_persistent = true;      // one cooperative launch per solve (diag2 preconditioner); false = three kernels per iteration
     bool use_tma = false;            // persistent solver with TMA-staged tiles (nx % 128 == 0); BLUB_PCG=tma or blub_fluid_set_solver_path(f, 2)
     bool use_dense = false;          // persistent solver without the per-thread sparsity skip (comparison only); set_solver_path(f, 4)
-    bool use_brick = false;          // EXPERIMENTAL: persistent solver with one warp per 32x4x4 brick; BLUB_PCG=brick or set_solver_path(f, 5)
+    bool use_columns = true;         // single GPU: dense tiles by the tile body, the rest as one list of quad columns (default); BLUB_PCG=tiles
+                                     // or set_solver_path(f, 6) walks every active tile with the tile bodies instead
     bool tma_available() const { return tma_blocks_ > 0; }
-    bool brick_available() const { return brick_blocks_ > 0; }
+    bool columns_available() const { return column_blocks_ > 0; }
     bool persistent_available() const { return persistent_blocks_ > 0; }
 
   private:
     void *tma_maps_ = nullptr;       // PcgTmaMaps (tensor maps of r, s0, s1, codes)
-    int tma_blocks_ = 0, brick_blocks_ = 0;
-    uint8_t *brick_active_ = nullptr; // experimental brick solver: per-brick activity, compacted list (ids | count | flagged ids)
-    int *brick_list_ = nullptr;
-    bool brick_three_ = false;        // BLUB_PCG_BRICK_BLOCKS=3: the 80-register build of the brick kernel
+    int tma_blocks_ = 0, column_blocks_ = 0;
+    int *tile_cols_ = nullptr;        // column solver: per-tile column counts | exclusive offsets | total
+    int *col_list_ = nullptr;         // compacted quad columns (linear index of the quad in its tile's first plane)
 
   public:
 };
@@ -272,7 +272,7 @@ class HybridFluid {
     FluidBits fluid_bits_ = {nullptr, 0}; // 1 bit per cell "FLUID", rebuilt with every finished marker volume
     bool fluid_bits_stale_ = false;       // the marker volume was written through a tap since
     GridArray<int8_t> marker_;
-    CellLists lists_ = {nullptr, nullptr, nullptr, nullptr, nullptr}; // per-step cell lists (P2G gather, binning)
+    CellLists lists_ = {nullptr, nullptr, nullptr, nullptr, nullptr, {nullptr, nullptr, nullptr, nullptr}}; // per-step cell lists (P2G gather, binning)
     bool use_scatter_ = false;            // scatter form of P2G on a single GPU (comparison path; the sharded step always scatters)
     const uint2 *voxels_ = nullptr;
 

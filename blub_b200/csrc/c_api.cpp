@@ -502,14 +502,13 @@ int blub_fluid_set_solver_path(BlubFluid *fluid, int persistent) {
     if (!fluid) return fail(BLUB_ERR_INVALID_ARGUMENT, "NULL fluid");
     blub::PressureSolver &s = fluid->impl->solver();
     // validate first: a refused request leaves the solver (and the cached step graphs) exactly as they were
-    if (persistent < 0 || persistent > 5 || persistent == 3) return fail(BLUB_ERR_INVALID_ARGUMENT, "solver path must be 0 (three kernels), 1 (persistent), 2 (TMA-staged), 4 (dense) or 5 (brick)");
+    if (persistent < 0 || persistent > 6 || persistent == 3 || persistent == 5)
+        return fail(BLUB_ERR_INVALID_ARGUMENT, "solver path must be 0 (three kernels), 1 (persistent, default), 2 (TMA-staged), 4 (dense) or 6 (tiles only)");
     if (persistent == 2 && !s.tma_available()) return fail(BLUB_ERR_INVALID_ARGUMENT, "TMA solver needs nx % 128 == 0 and cooperative launch");
-    if (persistent == 5 && !s.brick_available()) return fail(BLUB_ERR_INVALID_ARGUMENT, "brick solver needs nx % 32 == 0 and cooperative launch");
-    if (persistent == 5 && fluid->impl->sharded()) return fail(BLUB_ERR_INVALID_ARGUMENT, "brick solver is single-GPU only");
     s.use_persistent = persistent != 0;
     s.use_tma = persistent == 2;
     s.use_dense = persistent == 4;
-    s.use_brick = persistent == 5;
+    s.use_columns = persistent == 1;
     fluid->impl->invalidate_graphs();
     return BLUB_OK;
 }

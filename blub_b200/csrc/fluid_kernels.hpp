@@ -14,6 +14,15 @@ struct FluidBits {
     int wpr;
 };
 
+// Cells that hold more than 32 particles (see cell_canonicalize_kernel): list, per-cell table slot, and the table of their 18 face sums
+// (one component at a time).
+struct CrowdedCells {
+    uint32_t *count;        // number of crowded cells of the current lists
+    uint32_t *cells;        // their cell indices, max_num_particles / 33 + 1 entries
+    uint32_t *slot_of_cell; // n entries, only valid for crowded cells
+    float2 *sums;           // 18 per crowded cell
+};
+
 // Per-step cell lists (counting sort of particle indices by primal cell, canonical order inside a cell): the particles of cell c are
 // order[cell_start[c] .. cell_start[c + 1]).
 struct CellLists {
@@ -22,6 +31,7 @@ struct CellLists {
     uint32_t *arrival;    // scratch: the lists in arrival order of the count atomics, before canonicalisation
     uint2 *cell_slot;     // scratch: (cell, arrival slot) per particle
     uint32_t *block_sums; // scratch of the scan
+    CrowdedCells crowd;
 };
 
 void configure_transfer_kernels(); // once per device, before the first launch (dynamic shared memory opt-in)

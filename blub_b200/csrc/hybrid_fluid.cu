@@ -77,6 +77,14 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
     BLUB_CUDA_CHECK(cudaMalloc(&lists_.arrival, ((size_t)max_num_particles + 64) * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMalloc(&lists_.cell_slot, ((size_t)max_num_particles + 64) * sizeof(uint2)));
     BLUB_CUDA_CHECK(cudaMalloc(&lists_.block_sums, (size_t)(binning_scan_blocks(grid_) + 1024) * sizeof(uint32_t)));
+    {
+        const size_t max_crowded = (size_t)max_num_particles / 33 + 1;
+        BLUB_CUDA_CHECK(cudaMalloc(&lists_.crowd.count, sizeof(uint32_t)));
+        BLUB_CUDA_CHECK(cudaMemset(lists_.crowd.count, 0, sizeof(uint32_t)));
+        BLUB_CUDA_CHECK(cudaMalloc(&lists_.crowd.cells, max_crowded * sizeof(uint32_t)));
+        BLUB_CUDA_CHECK(cudaMalloc(&lists_.crowd.slot_of_cell, (size_t)grid_.n * sizeof(uint32_t)));
+        BLUB_CUDA_CHECK(cudaMalloc(&lists_.crowd.sums, max_crowded * 18 * sizeof(float2)));
+    }
     configure_transfer_kernels();
     if (const char *tp = std::getenv("BLUB_P2G")) {
         if (std::string(tp) == "scatter") set_transfer_path(1);
@@ -147,6 +155,10 @@ HybridFluid::~HybridFluid() {
     cudaFree(lists_.arrival);
     cudaFree(lists_.cell_slot);
     cudaFree(lists_.block_sums);
+    cudaFree(lists_.crowd.count);
+    cudaFree(lists_.crowd.cells);
+    cudaFree(lists_.crowd.slot_of_cell);
+    cudaFree(lists_.crowd.sums);
     if (solver_ && solver_->comm.seq) cudaFree(solver_->comm.seq);
     solver_.reset();
     field_velocity_.reset();

@@ -207,8 +207,8 @@ __device__ __forceinline__ float guarded_div(float num, float den) { // pressure
 // prepare (once per solve, every tile): marker -> codes + per-tile activity; establish the zero invariant:
 // p <- 0 and rhs <- 0 off-fluid (pressure_init.comp:37-43 zeroes p there), s <- 0 everywhere.
 __global__ void __launch_bounds__(PCG_THREADS) pcg_prepare_kernel(GridDim g, TileMap t, const int8_t *__restrict__ m, uint8_t *__restrict__ codes,
-                                                                  uint8_t *__restrict__ tile_active, float *__restrict__ p, float *__restrict__ r,
-                                                                  float *__restrict__ s) {
+                                                                  uint8_t *__restrict__ tile_active, int *__restrict__ tile_cols, float *__restrict__ p,
+                                                                  float *__restrict__ r, float *__restrict__ s) {
     __shared__ int sh_units;
     const TileCtx c = tile_ctx(g, t);
     if (linear_tid() == 0) sh_units = 0;
@@ -250,12 +250,17 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_prepare_kernel(GridDim g, Til
             st4(s + i, zero4());
         }
     }
+    const int ncols = __syncthreads_count(any > 0); // columns (thread's quad x PCG_TZ planes) that hold a FLUID cell
     any = (int)__reduce_add_sync(0xffffffffu, (unsigned)any);
     if ((linear_tid() & 31) == 0 && any) atomicAdd(&sh_units, any);
     __syncthreads();
     // 0 = no fluid, 1 = some, 2 = at least 3/4 of the (thread, plane) quads hold fluid: the persistent solver runs such a tile
     // with its branch-free body
-    if (linear_tid() == 0) tile_active[c.tile] = (uint8_t)(sh_units == 0 ? 0 : (4 * sh_units >= 3 * PCG_THREADS * PCG_TZ ? 2 : 1));
+    if (linear_tid() == 0) {
+        const int flag = sh_units == 0 ? 0 : (4 * sh_units >= 3 * PCG_THREADS * PCG_TZ ? 2 : 1);
+        tile_active[c.tile] = (uint8_t)flag;
+        tile_cols[c.tile] = flag == 1 ? ncols : 0; // the column solver walks sparsely filled tiles column by column
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -532,17 +537,6 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_search_kernel(GridDim g, Tile
 // stop at once instead of running out a recorded launch list.  Blocks walk the compacted list of active tiles with a
 // fixed stride, so a tile is processed by the same SM in every phase.  24 B/cell/iteration of DRAM traffic at most
 // (A: r, s, code in + s' out = 13; B: p, r, s', code in + p, r out = 21 ... minus what stays in the 126 MB L2).
-struct BrickMap {
-    int bricks_x, bricks_y, bricks_z, nbricks;
-};
-BrickMap make_brickmap(const GridDim &g) {
-    BrickMap b;
-    b.bricks_x = g.nx / 32;
-    b.bricks_y = g.ny / 4;
-    b.bricks_z = g.nz / PCG_TZ;
-    b.nbricks = b.bricks_x * b.bricks_y * b.bricks_z;
-    return b;
-}
 struct PcgSolveArgs {
     GridDim g;
     TileMap t;
@@ -550,9 +544,8 @@ struct PcgSolveArgs {
     const int *tile_list;   // compacted active tiles
     const int *tile_list_flagged; // the same with bit 30 set on tiles that are at least 3/4 full (pcg_prepare_kernel)
     const int *num_active;
-    const int *brick_list_flagged; // experimental brick solver: compacted 32x4x4 bricks (bit 30 = dense), see pcg_solve_brick_kernel
-    const int *num_active_bricks;
-    BrickMap bricks;
+    const int *col_list;    // column solver: compacted quad columns (4 cells x PCG_TZ planes) of the sparsely filled tiles, see pcg_solve_columns_kernel
+    const int *num_cols;
     float *p, *r, *s0, *s1;
     PcgScalars *scal;
     float *partials;        // 3 x gridDim.x
@@ -948,87 +941,131 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
 #undef PCG_FOR_EACH_TILE
 
 // ---------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (solver path 5, BLUB_PCG=brick; not the default, not yet run on a GPU): the persistent solver with a finer work unit.
-// Same phases, barriers, reductions, tile bodies and multi-GPU protocol as pcg_solve_persistent_kernel; what changes is who works on
-// what: one WARP takes a brick of 32 x 4 x 4 cells (lane = 8 quads x 4 rows, marching 4 planes) from a compacted brick list.  A dam
-// break fills 35-50 % of such bricks where it touches 64-88 % of the 128 x 8 x 4 tiles, and thousands of bricks spread over 4736 warps
-// without the pass quantisation of hundreds of tiles over 592 blocks (profiles/r01_v12_work_units_oracle_256x128x128.txt).  The tile
-// bodies only assume that lane - 1 / lane + 1 hold the x-adjacent quads unless the lane is `first` / `last`: true inside each 8-lane
-// row of a brick.  Needs nx % 32 == 0.
-__device__ __forceinline__ TileCtx brick_ctx_id(const GridDim &g, const BrickMap &b, int brick) {
-    const int bx = brick % b.bricks_x, rest = brick / b.bricks_x, by = rest % b.bricks_y, bz = rest / b.bricks_y;
-    const int lane = linear_tid() & 31, lx = lane & 7, ly = lane >> 3;
+// Column solver (default on one GPU): the persistent solver with a work list that follows the fluid.
+//
+// What the in-step profile of the tile kernel showed (profiles/r02_s2_pcg_step110.md, step 110 of the 256^3 dam break, 12.6 % of the
+// cells FLUID): 1.16 G warp instructions per solve, and in the sparsely filled tiles only 4-5 of 32 lanes do anything -- a warp pays the
+// whole instruction skeleton of a plane as soon as ONE of its lanes has a FLUID quad there.  The solve is bound by that skeleton and by
+// the 4-5 sequential tile passes per block and phase, not by bandwidth (the fluid working set is L2-resident).
+// Here tiles that are at least 3/4 full still run the branch-free tile body (an all-fluid grid costs what it cost: the roofline
+// microbench), but everything else is flattened into ONE list of active quad columns (4 cells x PCG_TZ planes, ascending index:
+// deterministic) and dealt to the warps 32 columns at a time: every lane has work, x-adjacent quads still sit in adjacent lanes
+// (coalesced loads), and a phase is ~one pass.  The column body IS the sparse tile body with "first" and "last" set: the x-neighbours
+// come from memory instead of the neighbouring lanes, so every cell sees the operands it saw before and the iterates agree with the
+// tile kernel up to the grouping of the partial sums.  Same phases, barriers, reductions and statistics as pcg_solve_persistent_kernel.
+__global__ void __launch_bounds__(PCG_THREADS) pcg_column_fill_kernel(GridDim g, TileMap t, const uint8_t *__restrict__ codes,
+                                                                      const uint8_t *__restrict__ tile_active, const int *__restrict__ col_offset,
+                                                                      int *__restrict__ col_list) {
+    __shared__ int sh_warp[PCG_THREADS / 32];
+    const TileCtx c = tile_ctx(g, t);
+    if (tile_active[c.tile] != 1) return; // block-uniform
+    bool active = false;
+    if (c.valid) {
+#pragma unroll
+        for (int k = 0; k < PCG_TZ; ++k) active = active || ldcw(codes + c.i + k * g.sz) != 0u;
+    }
+    const int tid = linear_tid(), lane = tid & 31, w = tid >> 5;
+    const unsigned ballot = __ballot_sync(0xffffffffu, active);
+    if (lane == 0) sh_warp[w] = __popc(ballot);
+    __syncthreads();
+    int before = 0;
+    for (int k = 0; k < w; ++k) before += sh_warp[k];
+    if (active) col_list[col_offset[c.tile] + before + __popc(ballot & ((1u << lane) - 1u))] = c.i; // ascending thread order inside a tile
+}
+
+// One block: compacts the tiles the tile loop walks (all active tiles, or only the dense ones when the columns take the rest) and
+// scans the per-tile column counts.  Deterministic (ascending tile id).
+__global__ void __launch_bounds__(1024) pcg_compact_kernel(const uint8_t *__restrict__ tile_active, const int *__restrict__ tile_cols, int tile_lo, int ntiles,
+                                                           int dense_only, int *__restrict__ tile_list, int *__restrict__ tile_list_flagged,
+                                                           int *__restrict__ num_active, int *__restrict__ col_offset, int *__restrict__ num_cols) {
+    __shared__ int sh[1024], shc[1024];
+    __shared__ int carry, carry_c;
+    if (threadIdx.x == 0) { carry = 0; carry_c = 0; }
+    __syncthreads();
+    for (int base = tile_lo; base < ntiles; base += 1024) { // [tile_lo, ntiles): the owned tiles of a slab, else all
+        const int idx = base + threadIdx.x;
+        const int flag = idx < ntiles ? tile_active[idx] : 0;
+        const int v = (dense_only ? flag == 2 : flag != 0) ? 1 : 0;
+        const int nc = dense_only && idx < ntiles ? tile_cols[idx] : 0;
+        sh[threadIdx.x] = v;
+        shc[threadIdx.x] = nc;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int tmp = threadIdx.x >= o ? sh[threadIdx.x - o] : 0, tmpc = threadIdx.x >= o ? shc[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += tmp;
+            shc[threadIdx.x] += tmpc;
+            __syncthreads();
+        }
+        const int incl = sh[threadIdx.x], inclc = shc[threadIdx.x];
+        if (v) {
+            tile_list[carry + incl - 1] = idx;
+            tile_list_flagged[carry + incl - 1] = idx | (flag == 2 ? TILE_DENSE_BIT : 0);
+        }
+        if (dense_only && idx < ntiles) col_offset[idx] = carry_c + inclc - nc;
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry += incl; carry_c += inclc; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *num_active = carry; *num_cols = carry_c; }
+}
+
+#define PCG_FOR_EACH_TILE(tile)                                                                                                      \
+    for (int li_ = blockIdx.x, tile = li_ < nact ? a.tile_list_flagged[li_] : 0, next_ = 0; li_ < nact; li_ += gridDim.x, tile = next_) \
+        if ((next_ = li_ + (int)gridDim.x < nact ? a.tile_list_flagged[li_ + gridDim.x] : 0), true)
+// 32 consecutive list entries per warp and pass; the index of the next pass is fetched one pass ahead.  All 32 lanes stay in the loop
+// (the bodies shuffle): lanes beyond the end of the list carry valid = false.
+#define PCG_FOR_EACH_COLUMN(c)                                                                                                            \
+    for (int cb_ = warp_first, ci_ = cb_ + lane < ncols ? a.col_list[cb_ + lane] : -1, cn_ = -1; cb_ < ncols; cb_ += col_stride, ci_ = cn_) \
+        if ((cn_ = cb_ + col_stride + lane < ncols ? a.col_list[cb_ + col_stride + lane] : -1), true)                                      \
+            if (const TileCtx c = column_ctx(ci_); true)
+__device__ __forceinline__ TileCtx column_ctx(int i) {
     TileCtx c;
-    c.tile = brick;
-    c.tz = bz;
-    c.valid = true; // nx % 32 == 0, ny % 4 == 0, nz % 4 == 0: bricks are never ragged
-    c.first = lx == 0;
-    c.last = lx == 7;
-    c.i = ((bz * PCG_TZ) * g.ny + by * 4 + ly) * g.nx + bx * 32 + 4 * lx;
+    c.tile = 0;
+    c.tz = 0;
+    c.valid = i >= 0;
+    c.first = true; // x-neighbours from memory: the neighbouring lanes hold unrelated columns
+    c.last = true;
+    c.i = i >= 0 ? i : 0;
     return c;
 }
-// per brick: 0 = no fluid, 1 = some, 2 = at least 3/4 of its (thread, plane) units hold fluid (runs the branch-free body).  One warp per brick.
-__global__ void __launch_bounds__(PCG_THREADS) pcg_brick_flags_kernel(GridDim g, BrickMap b, const uint8_t *__restrict__ codes, uint8_t *__restrict__ brick_active) {
-    const int brick = blockIdx.x * (PCG_THREADS / 32) + (linear_tid() >> 5);
-    if (brick >= b.nbricks) return;
-    const TileCtx c = brick_ctx_id(g, b, brick);
-    int units = 0;
-#pragma unroll
-    for (int k = 0; k < PCG_TZ; ++k) units += ldcw(codes + c.i + k * g.sz) != 0u ? 1 : 0;
-    units = (int)__reduce_add_sync(0xffffffffu, (unsigned)units);
-    if ((linear_tid() & 31) == 0) brick_active[brick] = (uint8_t)(units == 0 ? 0 : (4 * units >= 3 * 32 * PCG_TZ ? 2 : 1));
-}
 
-#define PCG_FOR_EACH_BRICK(tile)                                                                                                         \
-    for (int li_ = warp_id, tile = li_ < nact ? a.brick_list_flagged[li_] : 0, next_ = 0; li_ < nact; li_ += num_warps, tile = next_)  \
-        if ((next_ = li_ + num_warps < nact ? a.brick_list_flagged[li_ + num_warps] : 0), true)
-
-template <int BLOCKS_PER_SM> // 4: 64 registers (some spills), 32 warps per SM; 3: 80 registers, no spills, 24 warps per SM -- to be measured
-__global__ void __launch_bounds__(PCG_THREADS, BLOCKS_PER_SM) pcg_solve_brick_kernel(PcgSolveArgs a) {
-    constexpr bool SKIP = true;
+__global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSolveArgs a) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ float sh[PCG_THREADS / 32];
     __shared__ double shd;
     __shared__ float shf;
-    __shared__ double sh_csum[SLAB_MAX_WORLD];
-    __shared__ float sh_cmax[SLAB_MAX_WORLD];
-    __shared__ int sh_dead;
     const TileMap t = a.t;
-    const SlabComm &cm_ = a.comm;
-    const bool sharded = cm_.world > 1;
-    const int nact = *a.num_active_bricks;
-    const int warp_id = blockIdx.x * (PCG_THREADS / 32) + (linear_tid() >> 5), num_warps = gridDim.x * (PCG_THREADS / 32);
+    const int nact = *a.num_active, ncols = *a.num_cols;
+    const int lane = linear_tid() & 31;
+    const int warp_first = (blockIdx.x * (PCG_THREADS / 32) + (linear_tid() >> 5)) * 32, col_stride = gridDim.x * PCG_THREADS;
     float *psumA = a.partials, *psumB = a.partials + gridDim.x, *pmax = a.partials + 2 * gridDim.x;
     TileEnv e;
     e.g = a.g;
     e.codes = a.codes;
-    e.sharded = sharded;
-    // slab geometry: tiles tz_first..tz_last are owned; the planes just outside are ghost planes fed by the neighbours
-    e.tz_first = cm_.halo / PCG_TZ;
-    e.tz_last = t.tiles_z - 1 - cm_.halo / PCG_TZ;
-    e.push = cm_.owned_nz * a.g.sz; // index distance between an owned boundary plane and its image in the neighbour
-    e.peer_r_lo = cm_.peer_r[0];
-    e.peer_r_hi = cm_.peer_r[1];
-    unsigned seq = 0;
-    if (linear_tid() == 0) sh_dead = 0;
-    if (sharded) seq = *cm_.seq;
-    __syncthreads();
-    if (sharded) slab_start_handshake(cm_, seq, sh_csum, sh_cmax, &sh_dead);
+    e.sharded = false; // single GPU only: a z-slab rank runs pcg_solve_persistent_kernel
+    e.tz_first = 0;
+    e.tz_last = t.tiles_z - 1;
+    e.push = 0;
+    e.peer_r_lo = nullptr;
+    e.peer_r_hi = nullptr;
 
     // ---- init: r <- b - A p, sigma <- z.r (pressure_init.comp:45-83, pressure_solver.rs:625-649); s stays 0
     float acc = 0.0f;
-    PCG_FOR_EACH_BRICK(tile) {
-        const TileCtx c = brick_ctx_id(e.g, a.bricks, tile & (TILE_DENSE_BIT - 1));
+    PCG_FOR_EACH_TILE(tile) {
+        const TileCtx c = tile_ctx_id(e.g, t, tile & (TILE_DENSE_BIT - 1));
         unsigned w[PCG_TZ + 2];
         load_column_codes(e, c, w);
-        if (SKIP && warp_has_no_fluid(w)) continue;
-        if (!SKIP || (tile & TILE_DENSE_BIT)) init_tile<false>(e, c, w, a.p, a.r, acc);
-        else init_tile<true>(e, c, w, a.p, a.r, acc);
+        init_tile<false>(e, c, w, a.p, a.r, acc);
+    }
+    PCG_FOR_EACH_COLUMN(c) {
+        unsigned w[PCG_TZ + 2];
+        load_column_codes(e, c, w);
+        init_tile<true>(e, c, w, a.p, a.r, acc);
     }
     double tot = grid_sum(grid, psumB, acc, sh, &shd);
     float gmax = 0.0f;
-    if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
     float sigma = (float)tot;
     float alpha = 0.0f, beta = 0.0f, max_error = 0.0f;
     int num_iterations = 0;
@@ -1037,28 +1074,33 @@ __global__ void __launch_bounds__(PCG_THREADS, BLOCKS_PER_SM) pcg_solve_brick_ke
         const float *s_in = (it & 1) ? a.s1 : a.s0;
         float *s_out = (it & 1) ? a.s0 : a.s1;
         acc = 0.0f;
-        PCG_FOR_EACH_BRICK(tile) {
-            const TileCtx c = brick_ctx_id(e.g, a.bricks, tile & (TILE_DENSE_BIT - 1));
+        PCG_FOR_EACH_TILE(tile) {
+            const TileCtx c = tile_ctx_id(e.g, t, tile & (TILE_DENSE_BIT - 1));
             unsigned w[PCG_TZ + 2];
             load_column_codes(e, c, w);
-            if (SKIP && warp_has_no_fluid(w)) continue;
-            if (!SKIP || (tile & TILE_DENSE_BIT)) search_tile<false>(e, c, w, a.r, s_in, s_out, beta, acc);
-            else search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
+            search_tile<false>(e, c, w, a.r, s_in, s_out, beta, acc);
+        }
+        PCG_FOR_EACH_COLUMN(c) {
+            unsigned w[PCG_TZ + 2];
+            load_column_codes(e, c, w);
+            search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
         }
         tot = grid_sum(grid, psumA, acc, sh, &shd);
-        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
         alpha = guarded_div(sigma, (float)tot); // RESULTMODE_ALPHA, pressure_reduce.comp:73-75
 
         const bool with_err = (a.max_iterations == it) || (it > 0 && it % a.check_frequency == 0); // pressure_solver.rs:676-677
         acc = 0.0f;
         float err = 0.0f;
-        PCG_FOR_EACH_BRICK(tile) {
-            const TileCtx c = brick_ctx_id(e.g, a.bricks, tile & (TILE_DENSE_BIT - 1));
+        PCG_FOR_EACH_TILE(tile) {
+            const TileCtx c = tile_ctx_id(e.g, t, tile & (TILE_DENSE_BIT - 1));
             unsigned w[PCG_TZ + 2];
             load_column_codes(e, c, w);
-            if (SKIP && warp_has_no_fluid(w)) continue;
-            if (!SKIP || (tile & TILE_DENSE_BIT)) update_tile<false>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
-            else update_tile<true>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
+            update_tile<false>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
+        }
+        PCG_FOR_EACH_COLUMN(c) {
+            unsigned w[PCG_TZ + 2];
+            load_column_codes(e, c, w);
+            update_tile<true>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
         }
         {
             const float bm = block_max(err, sh);
@@ -1072,7 +1114,6 @@ __global__ void __launch_bounds__(PCG_THREADS, BLOCKS_PER_SM) pcg_solve_brick_ke
             gmax = shf;
             __syncthreads();
         }
-        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
         const float zr = (float)tot;
         if (with_err) {
             const float tol = a.params->tolerance[a.which];
@@ -1085,35 +1126,17 @@ __global__ void __launch_bounds__(PCG_THREADS, BLOCKS_PER_SM) pcg_solve_brick_ke
         beta = guarded_div(zr, sigma); // RESULTMODE_BETA, pressure_reduce.comp:77-80
         sigma = zr;
     }
-    if (sharded) {
-        // hand the boundary planes of the solution to the neighbours (warm start of their next init, pressure gradient
-        // across the slab face), then one more round so that nobody leaves before its ghost planes are complete
-        float *const peer_p_lo = cm_.peer_p[a.which][0], *const peer_p_hi = cm_.peer_p[a.which][1];
-        for (int li = warp_id; li < nact; li += num_warps) {
-            const TileCtx c = brick_ctx_id(e.g, a.bricks, a.brick_list_flagged[li] & (TILE_DENSE_BIT - 1));
-            if (!c.valid) continue;
-            if (c.tz == e.tz_first && peer_p_lo) st4(peer_p_lo + c.i + e.push, ld4(a.p + c.i));
-            if (c.tz == e.tz_last && peer_p_hi) {
-                const int i = c.i + (PCG_TZ - 1) * e.g.sz;
-                st4(peer_p_hi + i - e.push, ld4(a.p + i));
-            }
-        }
-        grid.sync();
-        double dummy = 0.0;
-        float dmax = 0.0f;
-        comm_allreduce(cm_, ++seq, dummy, dmax, sh_csum, sh_cmax, &sh_dead);
-        if (blockIdx.x == 0 && linear_tid() == 0) *cm_.seq = seq;
-    }
     if (blockIdx.x == 0 && linear_tid() == 0) {
         a.scal->alpha = alpha;
         a.scal->beta = beta;
         a.scal->sigma = sigma;
         a.scal->max_error = max_error;
         a.scal->num_iterations = num_iterations;
-        a.scal->done = sh_dead ? -1 : 1;
+        a.scal->done = 1;
     }
 }
-#undef PCG_FOR_EACH_BRICK
+#undef PCG_FOR_EACH_COLUMN
+#undef PCG_FOR_EACH_TILE
 
 // ---------------------------------------------------------------------------------------------------------------
 // TMA-tiled variant of the persistent solver (grids whose x extent is a multiple of 128 cells).
@@ -1405,37 +1428,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_tma_kernel(const __g
     }
 }
 
-// deterministic compaction of the active tiles (ascending tile id) by one block
-__global__ void __launch_bounds__(1024) pcg_compact_tiles_kernel(const uint8_t *__restrict__ tile_active, int tile_lo, int ntiles,
-                                                                 int *__restrict__ tile_list, int *__restrict__ tile_list_flagged,
-                                                                 int *__restrict__ num_active) {
-    __shared__ int sh[1024];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = tile_lo; base < ntiles; base += 1024) { // [tile_lo, ntiles): the owned tiles of a slab, else all
-        const int idx = base + threadIdx.x;
-        const int v = idx < ntiles && tile_active[idx] ? 1 : 0;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const int tmp = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += tmp;
-            __syncthreads();
-        }
-        const int incl = sh[threadIdx.x];
-        if (v) {
-            tile_list[carry + incl - 1] = idx;
-            tile_list_flagged[carry + incl - 1] = idx | (tile_active[idx] == 2 ? TILE_DENSE_BIT : 0);
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry += incl;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *num_active = carry;
-}
-
 __global__ void pcg_reset_scalars_kernel(PcgScalars *scal) {
     scal->alpha = 0.0f; scal->beta = 0.0f; scal->sigma = 0.0f;
     scal->max_error = 0.0f; scal->num_iterations = 0; scal->done = 0; scal->ticket = 0u;
@@ -1572,23 +1564,19 @@ PressureSolver::PressureSolver(const GridDim &grid, void *external_residual) : g
         }
     }
     use_tma = tma_blocks_ > 0 && env && std::string(env) == "tma";
-    // experimental brick-granular solver (path 5): needs whole 32-cell bricks along x
-    brick_blocks_ = 0;
-    if (persistent_blocks_ > 0 && grid.nx % 32 == 0) {
-        const BrickMap b = make_brickmap(grid);
-        BLUB_CUDA_CHECK(cudaMalloc(&brick_active_, (size_t)b.nbricks));
-        BLUB_CUDA_CHECK(cudaMemset(brick_active_, 0, (size_t)b.nbricks));
-        BLUB_CUDA_CHECK(cudaMalloc(&brick_list_, sizeof(int) * (2 * (size_t)b.nbricks + 1))); // ids | count | ids with the dense flag
-        BLUB_CUDA_CHECK(cudaMemset(brick_list_, 0, sizeof(int) * (2 * (size_t)b.nbricks + 1)));
+    // column solver (default on one GPU): list of the active quad columns of the sparsely filled tiles
+    column_blocks_ = 0;
+    if (persistent_blocks_ > 0) {
+        const size_t max_cols = (size_t)t.ntiles * PCG_THREADS;
+        BLUB_CUDA_CHECK(cudaMalloc(&tile_cols_, sizeof(int) * (2 * (size_t)t.ntiles + 2))); // counts | offsets | total
+        BLUB_CUDA_CHECK(cudaMemset(tile_cols_, 0, sizeof(int) * (2 * (size_t)t.ntiles + 2)));
+        BLUB_CUDA_CHECK(cudaMalloc(&col_list_, sizeof(int) * max_cols));
         int per = 0;
-        const char *bps = std::getenv("BLUB_PCG_BRICK_BLOCKS");
-        brick_three_ = bps && std::string(bps) == "3";
-        if (brick_three_) BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_brick_kernel<3>, PCG_THREADS, 0));
-        else BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_brick_kernel<4>, PCG_THREADS, 0));
-        brick_blocks_ = sms * per;
-        if (brick_blocks_ > 2048) brick_blocks_ = 2048;
+        BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_columns_kernel, PCG_THREADS, 0));
+        column_blocks_ = sms * per;
+        if (column_blocks_ > 2048) column_blocks_ = 2048;
     }
-    use_brick = brick_blocks_ > 0 && env && std::string(env) == "brick";
+    use_columns = column_blocks_ > 0 && !(env && std::string(env) == "tiles");
 }
 
 PressureSolver::~PressureSolver() {
@@ -1596,8 +1584,8 @@ PressureSolver::~PressureSolver() {
     if (partials_) cudaFree(partials_);
     if (tile_active_) cudaFree(tile_active_);
     if (tile_list_) cudaFree(tile_list_);
-    if (brick_active_) cudaFree(brick_active_);
-    if (brick_list_) cudaFree(brick_list_);
+    if (tile_cols_) cudaFree(tile_cols_);
+    if (col_list_) cudaFree(col_list_);
     delete static_cast<PcgTmaMaps *>(tma_maps_);
 }
 
@@ -1617,7 +1605,8 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
     field.touched = true; // the volume is zero-initialised at allocation (pressure_solver.rs:601-603)
 
     BLUB_LAUNCH(pcg_reset_scalars_kernel, 1, 1, 0, stream, scal);
-    BLUB_LAUNCH(pcg_prepare_kernel, grid, block, 0, stream, g, t, marker, codes_.ptr, tile_active_, p, r, s);
+    int *const scratch_cols = tile_cols_ ? tile_cols_ : num_active_; // (no cooperative launch: the counts are not used)
+    BLUB_LAUNCH(pcg_prepare_kernel, grid, block, 0, stream, g, t, marker, codes_.ptr, tile_active_, scratch_cols, p, r, s);
     if (mode != 0) { // the stored preconditioner vectors must obey the zero invariant as well
         BLUB_CUDA_CHECK(cudaMemsetAsync(aux_.ptr, 0, (size_t)g.n * sizeof(float), stream));
         BLUB_CUDA_CHECK(cudaMemsetAsync(aux_temp_.ptr, 0, (size_t)g.n * sizeof(float), stream));
@@ -1628,24 +1617,21 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
         // one cooperative launch for the whole solve; s ping-pongs between search_ and aux_ (both zero off the active tiles)
         BLUB_CUDA_CHECK(cudaMemsetAsync(aux_.ptr, 0, (size_t)g.n * sizeof(float), stream));
         const int ghost_tiles = (comm.halo / PCG_TZ) * t.tiles_x * t.tiles_y; // ghost planes are whole tiles (SLAB_HALO == PCG_TZ)
-        BLUB_LAUNCH(pcg_compact_tiles_kernel, 1, 1024, 0, stream, tile_active_, ghost_tiles, t.ntiles - ghost_tiles, tile_list_, num_active_ + 1, num_active_);
+        const bool columns = use_columns && column_blocks_ > 0 && comm.world == 1 && !use_tma && !use_dense;
+        int *col_offset = tile_cols_ + t.ntiles, *num_cols = tile_cols_ + 2 * t.ntiles;
+        BLUB_LAUNCH(pcg_compact_kernel, 1, 1024, 0, stream, tile_active_, tile_cols_, ghost_tiles, t.ntiles - ghost_tiles, columns ? 1 : 0, tile_list_, num_active_ + 1,
+                    num_active_, col_offset, num_cols);
         PcgSolveArgs args;
         args.g = g; args.t = t; args.codes = st; args.tile_list = tile_list_; args.tile_list_flagged = num_active_ + 1; args.num_active = num_active_;
         args.p = p; args.r = r; args.s0 = s; args.s1 = aux_.ptr; args.scal = scal; args.partials = partials_;
         args.params = dparams; args.which = which; args.max_iterations = max_it; args.check_frequency = freq;
         args.comm = comm;
-        args.bricks = BrickMap{0, 0, 0, 0}; args.brick_list_flagged = nullptr; args.num_active_bricks = nullptr;
-        if (use_brick && brick_blocks_ > 0) { // experimental: one warp per 32x4x4 brick
-            const BrickMap b = make_brickmap(g);
-            int *brick_count = brick_list_ + b.nbricks;
-            const int ghost_bricks = (comm.halo / PCG_TZ) * b.bricks_x * b.bricks_y;
-            BLUB_LAUNCH(pcg_brick_flags_kernel, (b.nbricks + PCG_THREADS / 32 - 1) / (PCG_THREADS / 32), PCG_THREADS, 0, stream, g, b, st, brick_active_);
-            BLUB_LAUNCH(pcg_compact_tiles_kernel, 1, 1024, 0, stream, brick_active_, ghost_bricks, b.nbricks - ghost_bricks, brick_list_, brick_count + 1, brick_count);
-            args.bricks = b; args.brick_list_flagged = brick_count + 1; args.num_active_bricks = brick_count;
-            int nblocks = brick_blocks_;
+        args.col_list = col_list_; args.num_cols = num_cols;
+        if (columns) { // dense tiles by the tile body, everything else column by column
+            BLUB_LAUNCH(pcg_column_fill_kernel, grid, block, 0, stream, g, t, st, ta, col_offset, col_list_);
+            int nblocks = column_blocks_;
             void *kargs[] = {&args};
-            BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel(brick_three_ ? (const void *)pcg_solve_brick_kernel<3> : (const void *)pcg_solve_brick_kernel<4>, dim3(nblocks), dim3(PCG_THREADS, 1, 1), kargs, 0,
-                                                        stream));
+            BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_columns_kernel, dim3(nblocks), t.block(), kargs, 0, stream));
             g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
             return;
         }

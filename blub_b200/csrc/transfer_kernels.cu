@@ -164,23 +164,30 @@ __global__ void __launch_bounds__(PT) cell_fill_kernel(const StepParams *__restr
 }
 
 // canonicalise: ascending particle index inside every cell, by rank counting -- entry j of cell c goes to position
-// cell_start[c] + #{entries of c smaller than it}.  One thread per list entry, k loads each from one or two cache lines; unlike a
-// per-cell sort this has no serial worst case when a cell is crowded (wave impact on a wall: hundreds of particles in a cell).
-// After this the lists no longer depend on the arrival order of the count atomics.  Cells with more than CANON_MAX particles
-// (256 x rest density: only adversarial inputs) keep their arrival order.
-constexpr uint32_t CANON_MAX = 2048;
+// cell_start[c] + #{entries of c smaller than it}.  One thread per list entry, k loads each from one or two cache lines.
+// After this the lists no longer depend on the arrival order of the count atomics.
+// CROWDED cells (more than CROWD_T particles: a wave piling up against a wall puts thousands of particles into single cells --
+// 7380 at step 56 of the 256^3 dam break, profiles/r02_s3_p2g_parts.md -- where the reference simply stops reading its lists after 12
+// entries) keep their arrival order and are appended to the crowded-cell list instead: their sums are formed by a whole warp in exact
+// integer arithmetic (p2g_crowded_kernel), which is order independent, so the result stays deterministic without an O(k^2) rank count
+// and without one thread walking thousands of particles.
+constexpr uint32_t CROWD_T = 32;
 __global__ void __launch_bounds__(PT) cell_canonicalize_kernel(const StepParams *__restrict__ params, const uint2 *__restrict__ cell_slot,
                                                                const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ arrival,
-                                                               uint32_t *__restrict__ order) {
+                                                               uint32_t *__restrict__ order, CrowdedCells crowd) {
     const uint32_t j = blockIdx.x * PT + threadIdx.x;
     if (j >= params->num_particles) return;
     const uint32_t v = arrival[j];
     const uint32_t cell = cell_slot[v].x;
     const uint32_t s = cell_start[cell], e = cell_start[cell + 1];
     uint32_t rank = j - s;
-    if (e - s <= CANON_MAX) {
+    if (e - s <= CROWD_T) {
         rank = 0;
         for (uint32_t t = s; t < e; ++t) rank += arrival[t] < v ? 1u : 0u;
+    } else if (j == s) {
+        const uint32_t slot = atomicAdd(crowd.count, 1u); // table slots are handed out in arrival order: the table CONTENT does not depend on it
+        crowd.cells[slot] = cell;
+        crowd.slot_of_cell[cell] = slot;
     }
     order[s + rank] = v;
 }
@@ -300,7 +307,8 @@ constexpr int GATHER_SMEM_BYTES = (GW + 2) * GATHER_STAGE_FLOATS * 4 + 2 * 3 * (
 template <int AXIS>
 __global__ void __launch_bounds__(GATHER_THREADS, 2) p2g_gather_kernel(GridDim g, const StepParams *__restrict__ params, const uint32_t *__restrict__ cell_start,
                                                                        const uint32_t *__restrict__ order, const float4 *__restrict__ pos,
-                                                                       const float4 *__restrict__ rowc, const int8_t *__restrict__ marker, float *__restrict__ u) {
+                                                                       const float4 *__restrict__ rowc, const int8_t *__restrict__ marker, float *__restrict__ u,
+                                                                       CrowdedCells crowd) {
     constexpr int NFX = AXIS == 0 ? 2 : 3, NFY = AXIS == 1 ? 2 : 3, NFZ = AXIS == 2 ? 2 : 3;
     constexpr float OX = AXIS == 0 ? 1.0f : 0.5f, OY = AXIS == 1 ? 1.0f : 0.5f, OZ = AXIS == 2 ? 1.0f : 0.5f;
     extern __shared__ float smem[];
@@ -356,7 +364,21 @@ __global__ void __launch_bounds__(GATHER_THREADS, 2) p2g_gather_kernel(GridDim g
                     stage[3 * GCAP + j] = r.x; stage[4 * GCAP + j] = r.y; stage[5 * GCAP + j] = r.z; stage[6 * GCAP + j] = r.w;
                 }
                 __syncwarp();
-                const uint32_t cnt = ce - cs;
+                uint32_t cnt = ce - cs;
+                if (cnt > CROWD_T) { // crowded cell: its 18 face sums were formed by p2g_crowded_kernel
+                    const float2 *tab = crowd.sums + (size_t)crowd.slot_of_cell[ci] * 18;
+#pragma unroll
+                    for (int fy = 0; fy < NFY; ++fy)
+#pragma unroll
+                        for (int fx = 0; fx < NFX; ++fx)
+#pragma unroll
+                            for (int fz = 0; fz < NFZ; ++fz) {
+                                const float2 tsum = tab[(fy * NFX + fx) * NFZ + fz];
+                                acc[fy][fx][fz].x += tsum.x;
+                                acc[fy][fx][fz].y += tsum.y;
+                            }
+                    cnt = 0;
+                }
                 const uint32_t kmax = __reduce_max_sync(0xffffffffu, cnt);
                 const float fcy = (float)y;
                 for (uint32_t k = 0; k < kmax; ++k) {
@@ -454,6 +476,78 @@ __global__ void __launch_bounds__(GATHER_THREADS, 2) p2g_gather_kernel(GridDim g
                 for (int fy = 0; fy + 1 < NFY; ++fy) acc[fy][fx][fz] = acc[fy + 1][fx][fz];
                 acc[NFY - 1][fx][fz] = make_float2(0.f, 0.f);
             }
+    }
+}
+
+// The (sum w*value, sum w) of the 18 faces of every CROWDED cell, one warp per cell: the lanes take the cell's particles round robin,
+// convert every contribution to 40.24 fixed point and add integers -- exact, hence independent of the order of the particles and of
+// the split across lanes -- then the warp total goes back to float.  |w * value| < 2^39 and a cell would need more than 10^9
+// particles to overflow; the quantisation (2^-24 per contribution) is below the float rounding of the sums it replaces.
+template <int AXIS>
+__global__ void __launch_bounds__(PT) p2g_crowded_kernel(GridDim g, const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ order,
+                                                         const float4 *__restrict__ pos, const float4 *__restrict__ rowc, CrowdedCells crowd) {
+    constexpr int NFX = AXIS == 0 ? 2 : 3, NFY = AXIS == 1 ? 2 : 3, NFZ = AXIS == 2 ? 2 : 3;
+    constexpr float OX = AXIS == 0 ? 1.0f : 0.5f, OY = AXIS == 1 ? 1.0f : 0.5f, OZ = AXIS == 2 ? 1.0f : 0.5f;
+    constexpr float FIX = 16777216.0f; // 2^24
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = *crowd.count;
+    for (uint32_t ci = blockIdx.x * (PT / 32) + (threadIdx.x >> 5); ci < n; ci += gridDim.x * (PT / 32)) {
+        const uint32_t cell = crowd.cells[ci];
+        const uint32_t tq = cell / (uint32_t)g.nx;
+        const float fcx = (float)(cell - tq * (uint32_t)g.nx), fcy = (float)(tq % (uint32_t)g.ny), fcz = (float)(tq / (uint32_t)g.ny);
+        const uint32_t cs = cell_start[cell], ce = cell_start[cell + 1];
+        long long acc[NFY][NFX][NFZ][2];
+#pragma unroll
+        for (int a = 0; a < NFY; ++a)
+#pragma unroll
+            for (int b = 0; b < NFX; ++b)
+#pragma unroll
+                for (int c = 0; c < NFZ; ++c) acc[a][b][c][0] = acc[a][b][c][1] = 0;
+        for (uint32_t k = cs + lane; k < ce; k += 32) {
+            const uint32_t idx = order[k];
+            const float3 p = transfer_position(g, pos[idx], 1.0f);
+            const float4 r = rowc[idx];
+            float tx[NFX], ty[NFY], tz[NFZ], wx[NFX], wy[NFY], wzv[NFZ], vz[NFZ];
+#pragma unroll
+            for (int f = 0; f < NFX; ++f) { tx[f] = ((fcx + (float)(f - 1)) + OX) - p.x; wx[f] = saturatef(1.0f - fabsf(tx[f])); }
+#pragma unroll
+            for (int f = 0; f < NFY; ++f) { ty[f] = ((fcy + (float)(f - 1)) + OY) - p.y; wy[f] = saturatef(1.0f - fabsf(ty[f])); }
+#pragma unroll
+            for (int f = 0; f < NFZ; ++f) {
+                tz[f] = ((fcz + (float)(f - 1)) + OZ) - p.z;
+                wzv[f] = saturatef(1.0f - fabsf(tz[f]));
+                vz[f] = fmaf(r.z, tz[f], r.w);
+            }
+#pragma unroll
+            for (int fy = 0; fy < NFY; ++fy)
+#pragma unroll
+                for (int fx = 0; fx < NFX; ++fx) {
+                    const float wxy = wx[fx] * wy[fy];
+                    const float vxy = fmaf(r.y, ty[fy], r.x * tx[fx]);
+#pragma unroll
+                    for (int fz = 0; fz < NFZ; ++fz) {
+                        const float w = wxy * wzv[fz];
+                        const float v = vxy + vz[fz];
+                        acc[fy][fx][fz][0] += __float2ll_rn((w * v) * FIX);
+                        acc[fy][fx][fz][1] += __float2ll_rn(w * FIX);
+                    }
+                }
+        }
+        float2 *out = crowd.sums + (size_t)ci * 18;
+#pragma unroll
+        for (int fy = 0; fy < NFY; ++fy)
+#pragma unroll
+            for (int fx = 0; fx < NFX; ++fx)
+#pragma unroll
+                for (int fz = 0; fz < NFZ; ++fz) {
+                    long long a0 = acc[fy][fx][fz][0], a1 = acc[fy][fx][fz][1];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                    }
+                    if (lane == 0) out[(fy * NFX + fx) * NFZ + fz] = make_float2(__ll2float_rn(a0) * (1.0f / FIX), __ll2float_rn(a1) * (1.0f / FIX));
+                }
     }
 }
 
@@ -627,7 +721,8 @@ void launch_cell_lists(cudaStream_t st, const GridDim &g, const StepParams *para
     BLUB_LAUNCH(scan_apply_kernel, nb, SCAN_THREADS, 0, st, l.cell_start, n1, l.block_sums);
     if (np_upper == 0) return;
     BLUB_LAUNCH(cell_fill_kernel, blocks_for(np_upper, PT), PT, 0, st, params, l.cell_slot, l.cell_start, l.arrival);
-    BLUB_LAUNCH(cell_canonicalize_kernel, blocks_for(np_upper, PT), PT, 0, st, params, l.cell_slot, l.cell_start, l.arrival, l.order);
+    BLUB_CUDA_CHECK(cudaMemsetAsync(l.crowd.count, 0, sizeof(uint32_t), st));
+    BLUB_LAUNCH(cell_canonicalize_kernel, blocks_for(np_upper, PT), PT, 0, st, params, l.cell_slot, l.cell_start, l.arrival, l.order, l.crowd);
 }
 
 void launch_marker_from_lists(cudaStream_t st, const GridDim &g, const CellLists &l, int8_t *marker, const uint2 *vox, const FluidBits &bits) {
@@ -649,15 +744,20 @@ void configure_transfer_kernels() {
     BLUB_CUDA_CHECK(cudaFuncSetAttribute(p2g_gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_SMEM_BYTES));
 }
 
+constexpr int CROWD_BLOCKS = 296; // 2 blocks of 8 warps per SM walk the crowded-cell list (usually empty: the kernel then costs a launch)
+
 void launch_p2g_gather(cudaStream_t st, const GridDim &g, const StepParams *params, const CellLists &l, const float4 *pos, float4 *const row[3],
                        const int8_t *marker, float *const u[3]) {
     const dim3 grid((g.nx + GXS - 1) / GXS, (g.ny + GLY - 1) / GLY, (g.nz + GW - 1) / GW);
     // Faces no block stores (blocks without particles return at once) keep their previous value, as in the reference, which only
     // writes faces that touch a FLUID cell (transfer_gather_velocity.comp:41-47): nothing reads them before
     // divergence_remove rewrites every face.
-    BLUB_LAUNCH(p2g_gather_kernel<0>, grid, GATHER_THREADS, GATHER_SMEM_BYTES, st, g, params, l.cell_start, l.order, pos, row[0], marker, u[0]);
-    BLUB_LAUNCH(p2g_gather_kernel<1>, grid, GATHER_THREADS, GATHER_SMEM_BYTES, st, g, params, l.cell_start, l.order, pos, row[1], marker, u[1]);
-    BLUB_LAUNCH(p2g_gather_kernel<2>, grid, GATHER_THREADS, GATHER_SMEM_BYTES, st, g, params, l.cell_start, l.order, pos, row[2], marker, u[2]);
+    BLUB_LAUNCH(p2g_crowded_kernel<0>, CROWD_BLOCKS, PT, 0, st, g, l.cell_start, l.order, pos, row[0], l.crowd);
+    BLUB_LAUNCH(p2g_gather_kernel<0>, grid, GATHER_THREADS, GATHER_SMEM_BYTES, st, g, params, l.cell_start, l.order, pos, row[0], marker, u[0], l.crowd);
+    BLUB_LAUNCH(p2g_crowded_kernel<1>, CROWD_BLOCKS, PT, 0, st, g, l.cell_start, l.order, pos, row[1], l.crowd);
+    BLUB_LAUNCH(p2g_gather_kernel<1>, grid, GATHER_THREADS, GATHER_SMEM_BYTES, st, g, params, l.cell_start, l.order, pos, row[1], marker, u[1], l.crowd);
+    BLUB_LAUNCH(p2g_crowded_kernel<2>, CROWD_BLOCKS, PT, 0, st, g, l.cell_start, l.order, pos, row[2], l.crowd);
+    BLUB_LAUNCH(p2g_gather_kernel<2>, grid, GATHER_THREADS, GATHER_SMEM_BYTES, st, g, params, l.cell_start, l.order, pos, row[2], marker, u[2], l.crowd);
 }
 
 void launch_p2g_scatter(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float4 *const row[3],

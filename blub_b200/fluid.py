@@ -434,13 +434,10 @@ class HybridFluid:
         return [float(x) for x in ms]
 
     def set_solver_path(self, persistent):
-        """True / 1: persistent cooperative PCG (default); False / 0: three kernels per iteration; 2 or "tma": TMA-staged tiles."""
-        if persistent in (4, "dense"):  # persistent kernel without the per-thread sparsity skip
-            mode = 4
-        elif persistent in (5, "brick"):  # experimental: one warp per 32x4x4 brick
-            mode = 5
-        else:
-            mode = 2 if persistent in (2, "tma") else (1 if persistent else 0)
+        """True / 1: persistent cooperative PCG, dense tiles + column list (default); False / 0: three kernels per iteration;
+        2 / "tma": TMA-staged tiles; 4 / "dense": tile kernel without the sparsity skip; 6 / "tiles": tile kernel with the sparse tile bodies."""
+        names = {"tma": 2, "dense": 4, "tiles": 6}
+        mode = names[persistent] if persistent in names else (int(persistent) if persistent not in (True, False) else (1 if persistent else 0))
         _check(self.L.blub_fluid_set_solver_path(self.h, mode))
 
     def set_transfer_path(self, scatter):

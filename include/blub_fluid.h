@@ -262,10 +262,11 @@ int blub_fluid_time_solve(BlubFluid *fluid, int which, double simulation_delta_s
 int blub_fluid_time_steps(BlubFluid *fluid, double simulation_delta_seconds, int steps, float *ms_total);
 /* one eagerly launched step with CUDA events between the 14 stages (same numbering as blub_fluid_step_stages); synchronises */
 int blub_fluid_step_timed(BlubFluid *fluid, double simulation_delta_seconds, float ms_per_stage[14]);
-/* PCG implementation: 1 (default) = one persistent cooperative kernel per solve, 0 = three kernels per iteration,
- * 2 = the persistent kernel with TMA-staged tiles (grids with nx % 128 == 0 only),
- * 4 = the persistent kernel without its per-thread sparsity skip (bit-identical results; for comparison),
- * 5 = the persistent kernel with one warp per 32x4x4 brick (nx % 32 == 0, single GPU).  A request that cannot be met returns
+/* PCG implementation: 1 (default) = one persistent cooperative kernel per solve -- tiles that are at least 3/4 FLUID by the
+ * branch-free tile body, everything else as one compacted list of quad columns (z-slab ranks: tiles only);
+ * 0 = three kernels per iteration; 2 = the persistent tile kernel with TMA-staged tiles (grids with nx % 128 == 0 only);
+ * 4 = the persistent tile kernel without its per-thread sparsity skip; 6 = the persistent tile kernel (sparse tile bodies, no columns).
+ * All paths run the same recurrence; 4 and 6 are bit-identical to each other.  A request that cannot be met returns
  * BLUB_ERR_INVALID_ARGUMENT and changes nothing. */
 int blub_fluid_set_solver_path(BlubFluid *fluid, int persistent);
 /* particle -> grid velocity transfer (transfer_gather_velocity.comp): 0 (default) = deterministic gather over per-step cell lists,

@@ -17,7 +17,7 @@ def pytest_configure(config):
 _ORDER = [
     "test_host", "test_oracle_kat", "test_transfer_kat", "test_stage_kat", "test_variants_emulated", "test_slab_gloo", "test_bench_contract",
     "test_gpu_pcg", "test_gpu_transfer", "test_gpu_parity", "test_golden", "test_gpu_solids", "test_zz_mesh_voxelizer", "test_gpu_runner",
-    "test_gpu_configs", "test_gpu_fullsize", "test_gpu_multi", "test_zz_experimental",
+    "test_gpu_configs", "test_gpu_fullsize", "test_gpu_multi",
 ]
 
 

@@ -30,32 +30,41 @@ def particles_close(p_o, p_g, what, tol, frac=1.0, loose=None):
     return d.max()
 
 
-def solve_stage(orc, gpu, which, stage, fixed_iterations):
+def solve_stage(orc, gpu, which, stage, converged):
     """Stage 2 / 10.  With the scene's solver configuration the iteration counts must agree (stop decisions are taken at every 4th iteration
-    on max|r| < tol; `fixed_iterations` = None).  On the big scenes that test can be borderline, so the iterate is ALSO compared after a
-    fixed number of iterations (tolerance 0) from the same right-hand side, which is free of stop decisions."""
+    on max|r| < tol).  Small scenes (`converged` = False) also compare the iterate itself at that point.  On the BASELINE-size scenes the
+    unconverged 32-iteration iterate of an fp32 CG is not a well-conditioned quantity (the two implementations sum their dot products in
+    different orders and drift apart by > 1 % of max|p| within 32 iterations at 256 x 128 x 128), so there the SOLUTION is compared: both
+    run the same right-hand side to convergence (tolerance 1e-4), the CUDA result must satisfy max|b - A p| < tolerance when the
+    residual is recomputed independently in float64, need about as many iterations as the oracle, and agree with the oracle's pressure."""
     tap_p, arr_p = (F.TAP_P_VEL, O.ARR_P_VEL) if which == 0 else (F.TAP_P_DEN, O.ARR_P_DEN)
     rhs = orc.grid(O.ARR_RESIDUAL).copy()
     p0 = orc.grid(arr_p).copy()
+    m = orc.grid(O.ARR_MARKER).copy()
     orc.step_stages(DT, stage, stage + 1)
     gpu.step_stages(DT, stage, stage + 1)
     (eo, io), (eg, ig) = orc.last_solve(which), gpu.last_solve(which)
-    if fixed_iterations is None:
+    if not converged:
         assert io == ig, (which, io, ig)
         grid_close(orc.grid(arr_p), gpu.download_grid(tap_p), f"p{which + 1}", rel=5e-3, abs_=1e-4)
         return io
     assert abs(io - ig) <= 4 and ig % 4 == 0, (which, io, ig, eo, eg)
     p_default = orc.grid(arr_p).copy()
-    cfg = (0.0, fixed_iterations, 4)
-    for f, put_r, put_p in ((orc, lambda a: orc.grid(O.ARR_RESIDUAL).__setitem__(slice(None), a), lambda a: orc.grid(arr_p).__setitem__(slice(None), a)),
-                            (gpu, lambda a: gpu.upload_grid(F.TAP_RESIDUAL, a), lambda a: gpu.upload_grid(tap_p, a))):
-        f.set_solver_config(which, *cfg)
-        put_r(rhs)
-        put_p(p0)
+    tol = 1e-4
+    for f in (orc, gpu):
+        f.set_solver_config(which, tol, 4000, 4)
+    orc.grid(O.ARR_RESIDUAL)[:] = rhs
+    orc.grid(arr_p)[:] = p0
+    gpu.upload_grid(F.TAP_RESIDUAL, rhs)
+    gpu.upload_grid(tap_p, p0)
     orc.solve(which, DT)
     gpu.solve_only(which, DT)
-    assert orc.last_solve(which)[1] == gpu.last_solve(which)[1] == fixed_iterations
-    grid_close(orc.grid(arr_p), gpu.download_grid(tap_p), f"p{which + 1} after {fixed_iterations} iterations", rel=5e-3, abs_=1e-4)
+    (eo, io), (eg, ig) = orc.last_solve(which), gpu.last_solve(which)
+    assert 0 < io < 4000 and 0 < ig < 4000 and abs(io - ig) <= 8 + 0.05 * io, (which, io, ig)
+    pg = gpu.download_grid(tap_p)
+    res = np.where(m == O.FLUID, rhs, 0.0) - util.apply_A(m, pg)
+    assert eg < tol / DT and np.abs(res).max() <= 1.05 * tol / DT + 1e-4 * np.abs(rhs).max(), (eg, np.abs(res).max(), tol / DT)
+    grid_close(orc.grid(arr_p), pg, f"p{which + 1} converged ({io} / {ig} iterations)", rel=5e-3, abs_=1e-3)
     for f in (orc, gpu):
         f.set_solver_config(which, 0.1, 32, 4)
     orc.grid(arr_p)[:] = p_default  # continue from the default solve's pressure
@@ -77,7 +86,7 @@ def compare_one_step(orc, gpu, robust=False, before_step=None):
     run(1, 2)  # rhs 1
     report["rhs1"] = grid_close(orc.grid(O.ARR_RESIDUAL), gpu.download_grid(F.TAP_RESIDUAL), "rhs1", mask=fl)
     gpu.upload_grid(F.TAP_RESIDUAL, orc.grid(O.ARR_RESIDUAL))
-    report["iterations1"] = solve_stage(orc, gpu, 0, 2, 32 if robust else None)
+    report["iterations1"] = solve_stage(orc, gpu, 0, 2, robust)
     # continue from the ORACLE's pressure so that solver round-off does not leak into the per-stage comparison
     gpu.upload_grid(F.TAP_P_VEL, orc.grid(O.ARR_P_VEL))
     run(3, 5)  # (binning off) + divergence_remove
@@ -101,7 +110,7 @@ def compare_one_step(orc, gpu, robust=False, before_step=None):
     fl = orc.grid(O.ARR_MARKER) == O.FLUID
     report["rhs2"] = grid_close(orc.grid(O.ARR_RESIDUAL), gpu.download_grid(F.TAP_RESIDUAL), "rhs2", rel=1e-4, abs_=2e-3, mask=fl)
     gpu.upload_grid(F.TAP_RESIDUAL, orc.grid(O.ARR_RESIDUAL))
-    report["iterations2"] = solve_stage(orc, gpu, 1, 10, 32 if robust else None)
+    report["iterations2"] = solve_stage(orc, gpu, 1, 10, robust)
     gpu.upload_grid(F.TAP_P_DEN, orc.grid(O.ARR_P_DEN))
     run(11, 13)  # position change + extrapolate
     for c, (tg, to) in enumerate(STAGE_TAPS):

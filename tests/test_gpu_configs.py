@@ -34,7 +34,7 @@ def pair(name):
 
 
 def trajectory(orc, gpu, steps, before_step=None):
-    util.tight_solver(orc, gpu)
+    util.tight_solver(orc, gpu, max_it=4000)  # converged: a 256 x 128 x 128 solve needs several hundred iterations, not 128
     for k in range(steps):
         if before_step:
             before_step(k)
@@ -86,12 +86,13 @@ def test_c5_double_dam_with_moving_solid_five_steps():
     dims, scale, origin = (d["x"], d["y"], d["z"]), sc["fluid"]["grid_to_world_scale"], [sc["fluid"]["world_position"][c] for c in "xyz"]
     # box of 24 x 40 x 24 cells travelling +-20 cells about the middle of the basin, SmoothStep over 2 s (bench.py's double_dam_box workload,
     # animation parameters of scenes/#double_dam_wgpulogo_rotating.json)
-    solid = {"world_position": [0.44, 0.20, 0.32], "scale": 1.0, "rotation_angles": [0.0, 0.0, 0.0], "shape": "box", "half_extent": [0.12, 0.20, 0.12],
+    # here it starts INSIDE the left dam and the clock starts at 0.5 s, so that the solid moves at ~30 cells/s through the fluid from the first step
+    solid = {"world_position": [0.22, 0.20, 0.32], "scale": 1.0, "rotation_angles": [0.0, 0.0, 0.0], "shape": "box", "half_extent": [0.12, 0.20, 0.12],
              "translation": {"target": [0.84, 0.20, 0.32], "curve": "SmoothStep", "duration": 2.0}}
     vol = torch.zeros((dims[2], dims[1], dims[0], 4), dtype=torch.float16, device="cuda")
     torch.cuda.synchronize()
     gpu.set_solid_voxels(vol.data_ptr())
-    clock = {"t": 0.0}
+    clock = {"t": 0.5}
 
     def scene_step(k):  # Scene::step: advance the clock, voxelize at the new time, then the fluid step
         clock["t"] += DT
@@ -105,6 +106,6 @@ def test_c5_double_dam_with_moving_solid_five_steps():
     q, mx = trajectory(orc, gpu, 5, before_step=scene_step)
     util.markers_agree(orc.grid(O.ARR_MARKER), gpu.download_grid(F.TAP_MARKER), allowed=16)
     solid_cells = vol[..., 3].cpu().numpy() > 0
-    assert solid_cells.sum() == 24 * 40 * 24
+    assert solid_cells.sum() > 20000
     c = np.floor(gpu.download_particles()[:, :3]).astype(int)
     assert solid_cells[c[:, 2], c[:, 1], c[:, 0]].mean() < 0.002

@@ -140,9 +140,10 @@ def test_tma_tiled_pcg_matches_oracle(max_it, freq, tol):
 
 
 @pytest.mark.parametrize("fill", [0.05, 0.5, 0.97])
-def test_sparse_skip_is_bit_identical_to_the_dense_kernel(fill):
-    """The per-thread sparsity skip of the persistent solver only drops work whose result is exactly 0 (zero invariant): the
-    pressure must equal the dense form of the same kernel (solver path 4) bit for bit, on ragged sparse and dense FLUID sets."""
+def test_sparse_paths_agree_with_the_dense_kernel(fill):
+    """The sparse tile bodies only drop work whose result is exactly 0 (zero invariant): the tile kernel (solver path 6) must equal its
+    dense form (path 4) bit for bit, on ragged sparse and dense FLUID sets.  The column solver (default, path 1) applies the same bodies
+    to a compacted column list: every cell sees the same operands, only the grouping of the per-block partial sums differs."""
     nx, ny, nz = 136, 24, 24  # ragged in x: 34 quads, a partial second tile
     rng = np.random.default_rng(int(fill * 100))
     m = np.full((nz, ny, nx), O.AIR, dtype=np.int8)
@@ -157,7 +158,7 @@ def test_sparse_skip_is_bit_identical_to_the_dense_kernel(fill):
     orc.grid(O.ARR_RESIDUAL)[:] = b
     orc.solve(0, DT)
     out = {}
-    for path in (True, "dense"):
+    for path in (True, "tiles", "dense"):
         gpu = blub_b200.HybridFluid(nx, ny, nz, 8)
         gpu.set_solver_path(path)
         gpu.set_solver_config(0, 0.0, 24, 4)
@@ -168,7 +169,38 @@ def test_sparse_skip_is_bit_identical_to_the_dense_kernel(fill):
             if rep == 0:
                 grid_close(orc.grid(O.ARR_P_VEL), gpu.download_grid(F.TAP_P_VEL), f"pressure path={path}", rel=3e-3, abs_=1e-4)
         out[path] = (gpu.download_grid(F.TAP_P_VEL), gpu.last_solve(0))
-    assert out[True][1] == out["dense"][1]
-    assert np.array_equal(out[True][0], out["dense"][0])
+    assert out["tiles"][1] == out["dense"][1]
+    assert np.array_equal(out["tiles"][0], out["dense"][0])
+    assert out[True][1][1] == out["dense"][1][1] == 24
+    grid_close(out["dense"][0], out[True][0], "column solver vs tile kernel", rel=2e-3, abs_=1e-4)
+    assert (out[True][0][m != O.FLUID] == 0).all()
 
 
+def test_column_solver_is_deterministic_and_handles_mixed_fill():
+    """A grid with a dense block (tile body), a sparse sheet and spray (column list): two solves of the same system are bit-identical, and the
+    result equals the oracle's."""
+    nx, ny, nz = 256, 32, 24
+    rng = np.random.default_rng(17)
+    m = np.full((nz, ny, nx), O.AIR, dtype=np.int8)
+    m[2:20, 2:26, 4:140] = O.FLUID                       # dense body: whole tiles >= 3/4 full
+    m[4:8, 10:12, 140:250] = O.FLUID                     # a thin sheet
+    m[rng.random((nz, ny, nx)) < 0.01] = O.FLUID         # spray
+    m[rng.random((nz, ny, nx)) < 0.01] = O.SOLID
+    m[0], m[-1], m[:, 0], m[:, -1], m[:, :, 0], m[:, :, -1] = 0, 0, 0, 0, 0, 0
+    b = rng.uniform(-1, 1, (nz, ny, nx)).astype(np.float32)
+    orc = O.OracleFluid(nx, ny, nz, 8)
+    orc.set_solver_config(0, 0.0, 20, 4)
+    orc.grid(O.ARR_MARKER)[:] = m
+    orc.grid(O.ARR_RESIDUAL)[:] = b
+    orc.solve(0, DT)
+    res = []
+    for _ in range(2):
+        gpu = blub_b200.HybridFluid(nx, ny, nz, 8)
+        gpu.set_solver_config(0, 0.0, 20, 4)
+        gpu.upload_grid(F.TAP_MARKER, m)
+        gpu.upload_grid(F.TAP_RESIDUAL, b)
+        gpu.solve_only(0, DT)
+        res.append((gpu.download_grid(F.TAP_P_VEL), gpu.download_grid(F.TAP_RESIDUAL), gpu.last_solve(0)))
+    assert res[0][2] == res[1][2] and np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    grid_close(orc.grid(O.ARR_P_VEL), res[0][0], "pressure", rel=2e-3, abs_=1e-4)
+    assert (res[0][0][m != O.FLUID] == 0).all()

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call, many answers: every call costs 1.5-3 minutes of box time before the command even starts, so measurements are
 # batched.  Usage (from the repository root, on the GPU box):
-#     bash tools/gpu_session.sh [tests] [experimental] [smoke] [timeline] [variants] [p2gparts] [ncustep] [bench] [launches] [ncu] [blubrun]
+#     bash tools/gpu_session.sh [tests] [smoke] [timeline] [variants] [p2gparts] [ncustep] [bench] [launches] [ncu] [blubrun]
 # Everything lands in gpurun_out/session_*.{txt,json,csv}; nothing here is a bench number unless it comes from bench.py outside ncu.
 set -u
 OUT=gpurun_out
@@ -13,10 +13,6 @@ if want tests; then         # the whole GPU suite, WITHOUT -x: every failure is 
     timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider 2>&1 | grep -v "^$" > $OUT/session_tests.txt
     tail -40 $OUT/session_tests.txt
 fi
-if want experimental; then  # the opt-in variants must first reproduce the default kernels
-    BLUB_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_experimental.py -m gpu -q --tb=short -p no:cacheprovider 2>&1 | grep -v "^$" | tail -40 > $OUT/session_experimental.txt
-    tail -15 $OUT/session_experimental.txt
-fi
 if want smoke; then         # twice: the round-1 failure was run-to-run
     for k in 1 2; do timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/session_smoke$k.txt 2>&1; tail -2 $OUT/session_smoke$k.txt; done
 fi
@@ -27,8 +23,9 @@ if want timeline; then      # stage times over a dam break
 fi
 if want variants; then      # comparison paths against the default timeline
     BLUB_P2G=scatter python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_p2g_scatter.txt 2>&1
-    BLUB_PCG=brick python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_brick.txt 2>&1
-    for f in p2g_scatter pcg_brick; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total|Error|error" $OUT/session_timeline_$f.txt; done
+    BLUB_PCG=tiles python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_tiles.txt 2>&1
+    python tools/profile_targets.py pcg 256 6 > $OUT/session_pcg_dense_default.txt 2>&1; cat $OUT/session_pcg_dense_default.txt
+    for f in p2g_scatter pcg_tiles; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total|Error|error" $OUT/session_timeline_$f.txt; done
 fi
 if want p2gparts; then      # which kernel of the P2G stage is slow late in the run: launch list of stage 0 at step 56 (eager launches) + cell statistics
     python tools/profile_targets.py cellstats dam_256 3 56 110 > $OUT/session_cellstats.txt 2>&1; cat $OUT/session_cellstats.txt
