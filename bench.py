@@ -147,16 +147,17 @@ def pcg_roofline(device, n=256, reps=5):
         peaks = json.load(open(pk))
         peak = float(peaks.get("hbm_gbs", peak))
         src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
-    traffic = None
+    traffic = traffic_src = None
     tp = os.path.join(ROOT, "profiles", "pcg_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_solve")
+    if os.path.exists(tp):  # DRAM bytes of this kernel on this workload from the committed ncu --set full capture (not measurable without a profiler)
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("dram_bytes_per_solve"), tj.get("source")
     ach = bytes_alg / t / 1e9
     e, it = f.last_solve(0)
     f.close()
     return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
             "kernel": "PCG solve (init + 33 x {dot, update, search})", "grid": f"{n}^3 all-fluid", "ms_per_solve": round(t * 1e3, 4),
-            "algorithmic_bytes_per_solve": bytes_alg, "peak_source": src, "iterations": it}
+            "algorithmic_bytes_per_solve": bytes_alg, "peak_source": src, "iterations_run": it + 1, "max_num_iterations": it, "traffic_source": traffic_src}
 
 
 def pcg_sharded(rank, world, local, n=512, reps=5):
@@ -250,6 +251,71 @@ def cpu_baseline_sample(workload, steps):
             "sample": f"{steps} step(s) of {workload} after 1 untimed step, OpenMP over {cores} host threads (linked-list builds serial)"}
 
 
+def config_block(desc, particles, dt, parallelism, window):
+    """The `config` object of the JSON line -- same keys in the blub arm and in the reference arm."""
+    return {"workload": desc, "particles": particles, "dt": dt, "solver": "tol 0.1 / max 32 / check 4 (reference defaults)", "rebin_every": 60,
+            "parallelism": parallelism, "l2": "inputs larger than L2 (>= 1 GB of particle state, 64 MiB per grid volume)", "window": window}
+
+
+def late_window_and_in_step(fluid, step, stepper, dt, steps_done, args, early_ms_per_step):
+    """The timed region of the contract (K steps after W warm-up steps) is the CHEAPEST phase of a dam break: the step gets more expensive
+    as the wave spreads (more active solver tiles, more surface).  So the same simulation is carried on to step `late_start` and a second
+    window of 20 steps is timed there with the same method; then one eagerly launched step is timed stage by stage and the in-step PCG solves
+    are put on the roofline of the bytes they TOUCH (work lists of the solver), next to the dense microbench of `roofline`."""
+    import numpy as np
+
+    from blub_b200 import fluid as F
+
+    late_start, late_steps = args.late_start, 20
+    while steps_done < late_start:
+        step(dt)
+        steps_done += 1
+    fluid.synchronize()
+    ms_late = stepper.time_steps(dt, late_steps) if stepper else fluid.time_steps(dt, late_steps)
+    steps_done += late_steps
+    phases = {"early": {"first_step": max(args.warmup, 3), "steps": args.steps, "ms_per_step": round(early_ms_per_step, 4), "steps_per_s": round(1e3 / early_ms_per_step, 3)},
+              "late": {"first_step": late_start, "steps": late_steps, "ms_per_step": round(ms_late / late_steps, 4), "steps_per_s": round(late_steps / (ms_late * 1e-3), 3)}}
+    if stepper:
+        return phases, None, None, steps_done
+    stage_ms = fluid.step_timed(dt)
+    steps_done += 1
+    work = fluid.solver_work()  # of the density solve (the last one); the velocity solve of the same step walks almost the same lists
+    it = [fluid.last_solve(w)[1] for w in (0, 1)]
+    touched_cells = work["tiles"] * work["cells_per_tile"] + work["columns"] * work["cells_per_column"]
+    m = fluid.download_grid(F.TAP_MARKER)
+    fluid_cells = int((m == 1).sum())
+    peak = 6650.0
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = float(json.load(open(pk)).get("hbm_gbs", peak))
+    solves = []
+    for which, stage in ((0, 2), (1, 10)):
+        passes = it[which] + 1  # iterations 0 .. it are run (pressure_solver.rs:654-723)
+        t = stage_ms[stage] * 1e-3
+        b_touched, b_fluid = (42 * passes + 21) * touched_cells, (42 * passes + 21) * fluid_cells
+        solves.append({"solve": F.STAGES[stage], "ms": round(stage_ms[stage], 4), "iterations_run": passes,
+                       "touched_GBps": round(b_touched / t / 1e9, 1), "touched_frac_of_hbm_peak": round(b_touched / t / 1e9 / peak, 4),
+                       "fluid_cell_GBps": round(b_fluid / t / 1e9, 1), "fluid_cell_frac_of_hbm_peak": round(b_fluid / t / 1e9 / peak, 4)})
+    in_step = {"at_step": steps_done - 1, "fluid_cells": fluid_cells, "fluid_fraction": round(fluid_cells / fluid.n, 4),
+               "solver_work": work, "touched_cells": touched_cells, "bytes_per_cell_and_pass": 42, "solves": solves,
+               "stage_ms": {name: round(v, 4) for name, v in zip(F.STAGES, stage_ms)}, "stage_total_ms": round(float(sum(stage_ms)), 4),
+               "note": "touched = cells of the tiles and quad columns on the solver's work lists; the fluid working set of this scene is L2-resident, so the in-step solve is "
+                       "latency / instruction bound, not HBM bound -- the HBM roofline of the kernel is the dense microbench in `roofline`"}
+    # what a consumer pays to GET the result: nothing on the device (blub_fluid_view hands out the ten device pointers the renderer binds,
+    # hybrid_fluid.rs:351-369); a host copy of the particle positions is a plain D2H transfer
+    t0 = time.perf_counter()
+    pos = fluid.download_particles()
+    t_dl = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    fluid.view()
+    t_view = time.perf_counter() - t0
+    handoff = {"device_view": {"call": "blub_fluid_view", "bytes_copied": 0, "ms": round(t_view * 1e3, 4)},
+               "host_download_positions": {"call": "blub_fluid_download(BLUB_TAP_PARTICLE_POS)", "bytes": int(pos.nbytes), "ms": round(t_dl * 1e3, 3),
+                                           "note": "pageable destination; not part of the step, not in e2e"}}
+    del np
+    return phases, in_step, handoff, steps_done
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -287,7 +353,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 5), "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1e3 * t / timed, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "particles": f.num_particles, "note": "reference wgpu path cannot run here; CPU restatement (oracle/) on host cores"},
+            "config": config_block(desc, f.num_particles, O.DT_120HZ, f"CPU restatement of the reference (oracle/), OpenMP over {cores} host threads; the wgpu reference cannot run here",
+                                   f"{timed} step(s) after {min(args.warmup, 1)} untimed"),
             "cpu_baseline": {"value": round(v, 5), "unit": "steps/s", "cores": cores, "kind": "port",
                              "sample": f"{timed} of the {args.steps} requested step(s) of {args.workload} timed ({budget:.0f} s budget), after {min(args.warmup, 1)} untimed"},
             "e2e": {"value": round(v, 5), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -305,6 +372,8 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-sharded-pcg", action="store_true")
     ap.add_argument("--no-scaling-reference", action="store_true")
+    ap.add_argument("--no-phases", action="store_true", help="skip the late-window timing and the in-step stage / roofline analysis (N = 1)")
+    ap.add_argument("--late-start", type=int, default=100, help="first step of the late timing window (N = 1)")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "stacked", "replicas"],
                     help="N > 1: one z-slab sharded simulation of a z-uniform dam (default, balanced), of N stacked dam_256 cubes, or N independent replicas")
     args = ap.parse_args()
@@ -415,6 +484,10 @@ def main():
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e.item())
     stats = fluid.pressure_solver_stats(0)[-1], fluid.pressure_solver_stats(1)[-1]
+    steps_done = max(args.warmup, 3) + 2 * args.steps
+    scene_phases = in_step = handoff = None
+    if world == 1 and not args.no_phases:
+        scene_phases, in_step, handoff, steps_done = late_window_and_in_step(fluid, step, stepper, dt, steps_done, args, ms / args.steps)
     slab_err = fluid.slab_error() if sharded_step else 0
     slab_counts = None
     if sharded_step:
@@ -453,19 +526,24 @@ def main():
             "metric": METRIC, "value": round(steps_per_s, 3), "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": desc, "particles": npart, "dt": dt, "solver": "tol 0.1 / max 32 / check 4 (reference defaults)", "rebin_every": 60,
-                       "parallelism": parallelism,
-                       "l2": "inputs larger than L2 (>= 1 GB of particle state, 64 MiB per grid volume)",
-                       "last_solver_stats": {"velocity": stats[0], "density": stats[1]}},
+            "config": config_block(desc, npart, dt, parallelism, f"steps {max(args.warmup, 3)}..{max(args.warmup, 3) + args.steps - 1} of the scene (see scene_phases for a later window)"),
+            "last_solver_stats": {"velocity": stats[0], "density": stats[1]},
             "clocks": clocks,
             "e2e": {"value": round(world * args.steps / e2e_s, 3), "unit": "steps/s", "h2d_bytes_per_step": 36, "d2h_bytes_per_step": 16,
-                    "note": "blub_fluid_step + blub_fluid_synchronize + blub_fluid_update_statistics per step (host-timed)"},
+                    "note": "blub_fluid_step + blub_fluid_synchronize + blub_fluid_update_statistics per step (host-timed); the state stays on the device as in the "
+                            "reference (hybrid_fluid.rs:770): per step the host sends the 36-byte parameter block and reads the two 8-byte solver statistics; see result_handoff"},
             "gpu_launches": int(launches),
             "slab_error": slab_err,
             "slab_particles": slab_counts,
             "roofline": roof,
             "cpu_baseline": cpu,
         }
+        if scene_phases is not None:
+            line["scene_phases"] = scene_phases
+        if in_step is not None:
+            line["in_step"] = in_step
+        if handoff is not None:
+            line["result_handoff"] = handoff
         if scaling_ref is not None:
             line["scaling_reference"] = scaling_ref
         if sharded is not None:

@@ -113,6 +113,8 @@ class PressureSolver {
     void solve(cudaStream_t stream, PressureField &field, int which, const int8_t *marker, const StepParams *dparams,
                const Quirks &quirks);
     SlabComm comm; // filled by HybridFluid::attach_slab_peers; world == 1 when not sharded
+    // {tiles walked by the tile body, quad columns walked by the column body, cells per tile, cells per column} of the last solve (blocking)
+    void read_work(cudaStream_t stream, uint32_t out[4]);
 
   private:
     GridDim grid_;
@@ -273,7 +275,8 @@ class HybridFluid {
     bool fluid_bits_stale_ = false;       // the marker volume was written through a tap since
     GridArray<int8_t> marker_;
     CellLists lists_ = {nullptr, nullptr, nullptr, nullptr, nullptr, {nullptr, nullptr, nullptr, nullptr}}; // per-step cell lists (P2G gather, binning)
-    bool use_scatter_ = false;            // scatter form of P2G on a single GPU (comparison path; the sharded step always scatters)
+    uint32_t *particle_words_ = nullptr;  // 1 bit per cell "a particle marked this cell" (scatter form: which accumulators to visit and re-zero)
+    bool use_scatter_ = true;             // scatter form of P2G (default; z-slab ranks always); false = deterministic gather over cell lists
     const uint2 *voxels_ = nullptr;
 
     std::unique_ptr<PressureSolver> solver_;

@@ -440,6 +440,15 @@ int blub_fluid_last_solve(BlubFluid *fluid, int which, float *max_error, int32_t
     });
 }
 
+int blub_fluid_solver_work(BlubFluid *fluid, uint32_t out[4]) {
+    if (!fluid || !out) return fail(BLUB_ERR_INVALID_ARGUMENT, "bad argument");
+    return guarded([&] {
+        BLUB_CUDA_CHECK(cudaSetDevice(fluid->impl->device()));
+        fluid->impl->solver().read_work(fluid->impl->stream(), out);
+        return BLUB_OK;
+    });
+}
+
 int blub_fluid_time_solve(BlubFluid *fluid, int which, double dt, int repetitions, float *ms_each) {
     if (!fluid || which < 0 || which > 1 || repetitions <= 0 || !ms_each) return fail(BLUB_ERR_INVALID_ARGUMENT, "bad argument");
     return guarded([&] {

@@ -64,13 +64,15 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
         BLUB_CUDA_CHECK(cudaMalloc(&row_[c], pbytes));
         BLUB_CUDA_CHECK(cudaMemset(row_[c], 0, pbytes));
         u_[c].alloc(grid_);
-        if (slab_world_ > 1) numw_[c].alloc(grid_); // accumulators of the scatter form (sharded step); single GPU: on demand
+        // accumulators of the scatter form: allocated by set_transfer_path / always on a z-slab rank
     }
     density_.alloc(grid_);
     marker_.alloc(grid_);
     fluid_bits_.wpr = ((int)nx + 31) / 32;
     BLUB_CUDA_CHECK(cudaMalloc(&fluid_bits_.words, (size_t)fluid_bits_.wpr * ny * nz * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMemset(fluid_bits_.words, 0, (size_t)fluid_bits_.wpr * ny * nz * sizeof(uint32_t)));
+    BLUB_CUDA_CHECK(cudaMalloc(&particle_words_, (size_t)fluid_bits_.wpr * ny * nz * sizeof(uint32_t)));
+    BLUB_CUDA_CHECK(cudaMemset(particle_words_, 0, (size_t)fluid_bits_.wpr * ny * nz * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMalloc(&lists_.cell_start, (size_t)(grid_.n + 1 + 8) * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMemset(lists_.cell_start, 0, (size_t)(grid_.n + 1 + 8) * sizeof(uint32_t)));
     BLUB_CUDA_CHECK(cudaMalloc(&lists_.order, ((size_t)max_num_particles + 64) * sizeof(uint32_t)));
@@ -86,8 +88,12 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
         BLUB_CUDA_CHECK(cudaMalloc(&lists_.crowd.sums, max_crowded * 18 * sizeof(float2)));
     }
     configure_transfer_kernels();
-    if (const char *tp = std::getenv("BLUB_P2G")) {
-        if (std::string(tp) == "scatter") set_transfer_path(1);
+    {
+        // Default: the scatter form.  Measured on the 256^3 dam break (profiles/r02_s4_timelines.md): scatter 1.30 / 1.60 / 1.53 ms at steps
+        // 3 / 56 / 110, gather 2.20 / 3.51 / 3.36 ms -- the gather is bit-reproducible, the scatter is faster.  BLUB_P2G=gather or
+        // blub_fluid_set_transfer_path(f, 0) selects the gather.
+        const char *tp = std::getenv("BLUB_P2G");
+        set_transfer_path(tp && std::string(tp) == "gather" ? 0 : 1);
     }
     SolverConfig cfg; // defaults .1 / 32 / 4, hybrid_fluid.rs:253-257
     if (slab_world_ > 1) {
@@ -150,6 +156,7 @@ HybridFluid::~HybridFluid() {
     density_.release();
     marker_.release();
     cudaFree(fluid_bits_.words);
+    cudaFree(particle_words_);
     cudaFree(lists_.cell_start);
     cudaFree(lists_.order);
     cudaFree(lists_.arrival);
@@ -391,9 +398,9 @@ void HybridFluid::refresh_fluid_bits() {
 // 0: gather form of P2G (default), 1: scatter form (RED.ADD.F32x2 into accumulator volumes; what the sharded step uses)
 void HybridFluid::set_transfer_path(int scatter) {
     BLUB_CUDA_CHECK(cudaSetDevice(device_));
-    if (scatter && !numw_[0].ptr)
-        for (int c = 0; c < 3; ++c) numw_[c].alloc(grid_);
-    use_scatter_ = scatter != 0;
+    if ((scatter || slab_world_ > 1) && !numw_[0].ptr)
+        for (int c = 0; c < 3; ++c) numw_[c].alloc(grid_); // zero-filled; the finish pass keeps them zero between steps
+    use_scatter_ = scatter != 0 || slab_world_ > 1;
     destroy_graphs();
 }
 
@@ -415,14 +422,14 @@ void HybridFluid::run_stage(int stage, float dt) {
             if (np > 0) launch_p2g_gather(stream_, grid_, params_dev_, lists_, pos_[cur_], row_, marker_.ptr, u);
             else for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(u[c], 0, (size_t)grid_.n * sizeof(float), stream_));
         } else if (!shard) {
-            launch_p2g_scatter(stream_, grid_, params_dev_, np, pos_[cur_], row_, nw, marker_.ptr);
-            launch_p2g_finish(stream_, grid_, params_dev_, u, nw, marker_.ptr, voxels_, bits);
+            launch_p2g_scatter(stream_, grid_, params_dev_, np, pos_[cur_], row_, nw, marker_.ptr, false);
+            launch_p2g_finish(stream_, grid_, params_dev_, u, nw, marker_.ptr, voxels_, bits, particle_words_);
             fluid_bits_stale_ = false;
         } else {
-            launch_p2g_scatter(stream_, grid_, params_dev_, np, pos_[cur_], row_, nw, marker_.ptr);
+            launch_p2g_scatter(stream_, grid_, params_dev_, np, pos_[cur_], row_, nw, marker_.ptr, true);
             const SlabHaloItem items[4] = {{nw[0], sizeof(float2), 0}, {nw[1], sizeof(float2), 0}, {nw[2], sizeof(float2), 0}, {marker_.ptr, 1, 1}};
             slab_halo_exchange(items, 4); // X1
-            launch_p2g_finish(stream_, grid_, params_dev_, u, nw, marker_.ptr, voxels_, bits);
+            launch_p2g_finish(stream_, grid_, params_dev_, u, nw, marker_.ptr, voxels_, bits, particle_words_);
             fluid_bits_stale_ = false;
         }
         break;

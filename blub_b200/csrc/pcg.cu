@@ -1039,7 +1039,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
     const TileMap t = a.t;
     const int nact = *a.num_active, ncols = *a.num_cols;
     const int lane = linear_tid() & 31;
-    const int warp_first = (blockIdx.x * (PCG_THREADS / 32) + (linear_tid() >> 5)) * 32, col_stride = gridDim.x * PCG_THREADS;
+    // Tiles are dealt to the blocks from block 0 upwards, columns to the warps from the LAST warp of the last block downwards: when there are
+    // fewer dense tiles than blocks (or a remainder), the blocks without a tile take the columns first and a phase is one pass, not two.
+    const int col_stride = gridDim.x * PCG_THREADS;
+    const int warp_first = col_stride - 32 - (blockIdx.x * (PCG_THREADS / 32) + (linear_tid() >> 5)) * 32;
     float *psumA = a.partials, *psumB = a.partials + gridDim.x, *pmax = a.partials + 2 * gridDim.x;
     TileEnv e;
     e.g = a.g;
@@ -1587,6 +1590,18 @@ PressureSolver::~PressureSolver() {
     if (tile_cols_) cudaFree(tile_cols_);
     if (col_list_) cudaFree(col_list_);
     delete static_cast<PcgTmaMaps *>(tma_maps_);
+}
+
+void PressureSolver::read_work(cudaStream_t stream, uint32_t out[4]) {
+    const TileMap t = make_tilemap(grid_);
+    int tiles = 0, cols = 0;
+    BLUB_CUDA_CHECK(cudaMemcpyAsync(&tiles, num_active_, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (tile_cols_) BLUB_CUDA_CHECK(cudaMemcpyAsync(&cols, tile_cols_ + 2 * t.ntiles, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    BLUB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    out[0] = (uint32_t)tiles;
+    out[1] = (uint32_t)cols;
+    out[2] = (uint32_t)(4 * t.bx * t.by * PCG_TZ);
+    out[3] = (uint32_t)(4 * PCG_TZ);
 }
 
 void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which, const int8_t *marker, const StepParams *dparams,

@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(PT) marker_from_lists_kernel(GridDim g, FluidB
 
 // marker <- boundary rule applied to an existing marker volume (transfer_set_boundary_marker.comp:11-20; every other cell keeps its
 // value), + the FLUID bit mask of the result
-__global__ void __launch_bounds__(PT) marker_finalize_kernel(GridDim g, FluidBits bits, int8_t *__restrict__ marker, const uint2 *__restrict__ vox) {
+__global__ void __launch_bounds__(PT) marker_finalize_kernel(GridDim g, FluidBits bits, int8_t *__restrict__ marker, const uint2 *__restrict__ vox,
+                                                             uint32_t *__restrict__ particle_words) {
     const int w = blockIdx.x * PT + threadIdx.x;
     if (w >= bits.wpr * g.ny * g.nz) return;
     const int xw = w % bits.wpr, rowi = w / bits.wpr, y = rowi % g.ny, z = rowi / g.ny;
@@ -253,6 +254,9 @@ __global__ void __launch_bounds__(PT) marker_finalize_kernel(GridDim g, FluidBit
     unsigned fluid = 0;
     for (int k8 = 0; k8 < cells; k8 += 8) {
         unsigned long long v = *reinterpret_cast<const unsigned long long *>(m + k8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if ((int8_t)((v >> (8 * k)) & 0xffull) == (int8_t)CELL_FLUID) fluid |= 1u << (k8 + k);
         const unsigned s8 = (solid >> k8) & 0xffu;
         if (s8) {
 #pragma unroll
@@ -260,11 +264,9 @@ __global__ void __launch_bounds__(PT) marker_finalize_kernel(GridDim g, FluidBit
                 if (s8 & (1u << k)) v &= ~(0xffull << (8 * k)); // CELL_SOLID == 0
             *reinterpret_cast<unsigned long long *>(m + k8) = v;
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if ((int8_t)((v >> (8 * k)) & 0xffull) == (int8_t)CELL_FLUID) fluid |= 1u << (k8 + k);
     }
-    bits.words[w] = fluid;
+    if (particle_words) particle_words[w] = fluid; // cells that were marked FLUID by a particle, whatever the boundary rule makes of them
+    bits.words[w] = fluid & ~solid;
 }
 
 // FLUID bit mask of a marker volume that is already final (uploaded through the test taps)
@@ -620,30 +622,65 @@ __global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepPa
     }
 }
 
-// Normalisation + global forces + "don't flow into solid" for the scatter form: transfer_gather_velocity.comp:116-127.
-__global__ void __launch_bounds__(PT) p2g_normalize_kernel(GridDim g, const StepParams *__restrict__ params,
-                                                           const int8_t *__restrict__ marker, float *__restrict__ ux,
-                                                           float *__restrict__ uy, float *__restrict__ uz,
-                                                           const float2 *__restrict__ nwx, const float2 *__restrict__ nwy,
-                                                           const float2 *__restrict__ nwz) {
-    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
-    if (i >= g.n) return;
-    const int ma = marker[i];
-    const int mb[3] = {marker[i + 1], marker[i + g.sy], marker[i + g.sz]};
-    float *const u[3] = {ux, uy, uz};
-    const float2 *const nw[3] = {nwx, nwy, nwz};
+// Normalisation + global forces + "don't flow into solid" for the scatter form: transfer_gather_velocity.comp:116-127 -- and the
+// accumulators are put back to zero on the way, so that no memset is needed: a particle of cell C only ever touches accumulators of
+// cells C-1 .. C+1 (in every dimension), so the cells to visit are the one-cell dilation of the cells that hold particles
+// (particle_words, written by marker_finalize_kernel).  One warp per 32 words of 32 cells: the lanes first work out which of their
+// words are touched at all (almost none away from the fluid), then the warp walks the touched words with lane = cell (coalesced).
+// Faces away from the fluid keep their previous value, as in the reference.
+__device__ __forceinline__ unsigned pbits(const GridDim &g, const uint32_t *__restrict__ pw, int wpr, int xw, int y, int z) {
+    if (xw < 0 || xw >= wpr || y < 0 || y >= g.ny || z < 0 || z >= g.nz) return 0u;
+    return __ldg(pw + (z * g.ny + y) * wpr + xw);
+}
+__global__ void __launch_bounds__(PT) p2g_normalize_kernel(GridDim g, int wpr, const uint32_t *__restrict__ particle_words, const StepParams *__restrict__ params,
+                                                           const int8_t *__restrict__ marker, float *__restrict__ ux, float *__restrict__ uy,
+                                                           float *__restrict__ uz, float2 *__restrict__ nwx, float2 *__restrict__ nwy,
+                                                           float2 *__restrict__ nwz) {
+    const int nwords = wpr * g.ny * g.nz;
+    const int w = blockIdx.x * PT + threadIdx.x, lane = threadIdx.x & 31;
+    unsigned touched = 0;
+    int xw = 0, y = 0, z = 0;
+    if (w < nwords) {
+        xw = w % wpr;
+        const int rowi = w / wpr;
+        y = rowi % g.ny;
+        z = rowi / g.ny;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float out = 0.0f;
-        if (ma == CELL_FLUID || mb[c] == CELL_FLUID) {
-            if (ma != CELL_SOLID && mb[c] != CELL_SOLID) {
-                const float2 a = nw[c][i];
-                float v = a.x;
-                if (a.y > 0.0f) v /= a.y;
-                out = v + params->gravity_dt[c];
+        for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const unsigned b = pbits(g, particle_words, wpr, xw, y + dy, z + dz);
+                touched |= b | (b << 1) | (b >> 1) | (pbits(g, particle_words, wpr, xw - 1, y + dy, z + dz) >> 31) | (pbits(g, particle_words, wpr, xw + 1, y + dy, z + dz) << 31);
             }
+        const int cells = min(32, g.nx - xw * 32);
+        if (cells < 32) touched &= (1u << cells) - 1u;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, touched != 0u);
+    float *const u[3] = {ux, uy, uz};
+    float2 *const nw[3] = {nwx, nwy, nwz};
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned tw = __shfl_sync(0xffffffffu, touched, src);
+        const int sxw = __shfl_sync(0xffffffffu, xw, src), sy = __shfl_sync(0xffffffffu, y, src), sz = __shfl_sync(0xffffffffu, z, src);
+        if (!((tw >> lane) & 1u)) continue;
+        const int i = lin(g, sxw * 32 + lane, sy, sz);
+        const int ma = marker[i];
+        const int mb[3] = {marker[i + 1], marker[i + g.sy], marker[i + g.sz]};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 a = nw[c][i];
+            if (a.x != 0.0f || a.y != 0.0f) nw[c][i] = make_float2(0.0f, 0.0f);
+            float out = 0.0f;
+            if (ma == CELL_FLUID || mb[c] == CELL_FLUID) {
+                if (ma != CELL_SOLID && mb[c] != CELL_SOLID) {
+                    float v = a.x;
+                    if (a.y > 0.0f) v /= a.y;
+                    out = v + params->gravity_dt[c];
+                }
+            }
+            u[c][i] = out;
         }
-        u[c][i] = out;
     }
 }
 
@@ -729,8 +766,8 @@ void launch_marker_from_lists(cudaStream_t st, const GridDim &g, const CellLists
     BLUB_LAUNCH(marker_from_lists_kernel, blocks_for((int64_t)bits.wpr * g.ny * g.nz, PT), PT, 0, st, g, bits, l.cell_start, marker, vox);
 }
 
-void launch_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, const uint2 *vox, const FluidBits &bits) {
-    BLUB_LAUNCH(marker_finalize_kernel, blocks_for((int64_t)bits.wpr * g.ny * g.nz, PT), PT, 0, st, g, bits, marker, vox);
+void launch_boundary_marker(cudaStream_t st, const GridDim &g, int8_t *marker, const uint2 *vox, const FluidBits &bits, uint32_t *particle_words) {
+    BLUB_LAUNCH(marker_finalize_kernel, blocks_for((int64_t)bits.wpr * g.ny * g.nz, PT), PT, 0, st, g, bits, marker, vox, particle_words);
 }
 
 void launch_fluid_bits(cudaStream_t st, const GridDim &g, const int8_t *marker, const FluidBits &bits) {
@@ -761,18 +798,22 @@ void launch_p2g_gather(cudaStream_t st, const GridDim &g, const StepParams *para
 }
 
 void launch_p2g_scatter(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float4 *const row[3],
-                        float2 *const nw[3], int8_t *marker) {
-    // transfer_clear.comp: marker <- AIR; the (num, weight) volumes replace the linked-list head volume
+                        float2 *const nw[3], int8_t *marker, bool clear_accumulators) {
+    // transfer_clear.comp: marker <- AIR.  The (num, weight) volumes (they replace the linked-list head volume) are all zero here on one GPU:
+    // they are allocated zeroed and launch_p2g_finish puts back to zero what the scatter touched.  A z-slab rank also receives partial sums
+    // from its neighbours in the overlap planes, some of them from particles whose cells it never sees: it clears the volumes the plain way.
     BLUB_CUDA_CHECK(cudaMemsetAsync(marker, 0xFF, (size_t)g.n, st));
-    for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(nw[c], 0, (size_t)g.n * sizeof(float2), st));
+    if (clear_accumulators)
+        for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(nw[c], 0, (size_t)g.n * sizeof(float2), st));
     if (np_upper == 0) return;
     BLUB_LAUNCH(p2g_scatter_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
 }
 
 void launch_p2g_finish(cudaStream_t st, const GridDim &g, const StepParams *params, float *const u[3], float2 *const nw[3], int8_t *marker,
-                       const uint2 *vox, const FluidBits &bits) {
-    launch_boundary_marker(st, g, marker, vox, bits);
-    BLUB_LAUNCH(p2g_normalize_kernel, blocks_for(g.n, PT), PT, 0, st, g, params, marker, u[0], u[1], u[2], nw[0], nw[1], nw[2]);
+                       const uint2 *vox, const FluidBits &bits, uint32_t *particle_words) {
+    launch_boundary_marker(st, g, marker, vox, bits, particle_words);
+    BLUB_LAUNCH(p2g_normalize_kernel, blocks_for((int64_t)bits.wpr * g.ny * g.nz, PT), PT, 0, st, g, bits.wpr, particle_words, params, marker, u[0], u[1], u[2], nw[0],
+                nw[1], nw[2]);
 }
 
 void launch_density_scatter(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float *density) {

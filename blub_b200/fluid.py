@@ -158,6 +158,7 @@ def lib():
         "blub_fluid_step_stages": (C.c_int, [vp, C.c_double, C.c_int, C.c_int]),
         "blub_fluid_solve_only": (C.c_int, [vp, C.c_int, C.c_double]),
         "blub_fluid_last_solve": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+        "blub_fluid_solver_work": (C.c_int, [vp, C.POINTER(u32)]),
         "blub_fluid_time_solve": (C.c_int, [vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_float)]),
         "blub_fluid_time_steps": (C.c_int, [vp, C.c_double, C.c_int, C.POINTER(C.c_float)]),
         "blub_fluid_step_timed": (C.c_int, [vp, C.c_double, C.POINTER(C.c_float)]),
@@ -423,6 +424,12 @@ class HybridFluid:
         _check(self.L.blub_fluid_last_solve(self.h, which, C.byref(e), C.byref(it)))
         return float(e.value), int(it.value)
 
+    def solver_work(self):
+        """{tiles, columns, cells_per_tile, cells_per_column} of the most recent solve's work lists."""
+        out = (C.c_uint32 * 4)()
+        _check(self.L.blub_fluid_solver_work(self.h, out))
+        return {"tiles": int(out[0]), "columns": int(out[1]), "cells_per_tile": int(out[2]), "cells_per_column": int(out[3])}
+
     def time_solve(self, which, dt, repetitions):
         ms = (C.c_float * repetitions)()
         _check(self.L.blub_fluid_time_solve(self.h, which, dt, repetitions, ms))
@@ -441,7 +448,7 @@ class HybridFluid:
         _check(self.L.blub_fluid_set_solver_path(self.h, mode))
 
     def set_transfer_path(self, scatter):
-        """False / "gather" (default): deterministic gather P2G over per-step cell lists; True / "scatter": warp-aggregated atomic scatter."""
+        """True / "scatter" (default): warp-aggregated atomic scatter; False / "gather": deterministic gather P2G over per-step cell lists."""
         _check(self.L.blub_fluid_set_transfer_path(self.h, 1 if scatter in (True, 1, "scatter") else 0))
 
     def stream(self):

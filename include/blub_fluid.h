@@ -254,6 +254,9 @@ int blub_fluid_step_stages(BlubFluid *fluid, double simulation_delta_seconds, in
 int blub_fluid_solve_only(BlubFluid *fluid, int which, double simulation_delta_seconds);
 /* last finished solve of a field, synchronously: max|r| (not multiplied by dt) and iteration count */
 int blub_fluid_last_solve(BlubFluid *fluid, int which, float *max_error, int32_t *iterations);
+/* work list of the most recent solve (diagnostics for the in-step roofline; synchronises): out[0] = tiles walked by the tile body,
+ * out[1] = quad columns walked by the column body, out[2] = cells per tile, out[3] = cells per column */
+int blub_fluid_solver_work(BlubFluid *fluid, uint32_t out[4]);
 /* PCG micro-benchmark: `repetitions` times { restore the rhs that is in the residual tap now, zero the pressure field,
  * solve } with CUDA events around each solve on the fluid's stream; ms_each[repetitions] receives device milliseconds.
  * Synchronises. */
@@ -269,8 +272,9 @@ int blub_fluid_step_timed(BlubFluid *fluid, double simulation_delta_seconds, flo
  * All paths run the same recurrence; 4 and 6 are bit-identical to each other.  A request that cannot be met returns
  * BLUB_ERR_INVALID_ARGUMENT and changes nothing. */
 int blub_fluid_set_solver_path(BlubFluid *fluid, int persistent);
-/* particle -> grid velocity transfer (transfer_gather_velocity.comp): 0 (default) = deterministic gather over per-step cell lists,
- * 1 = warp-aggregated float-atomic scatter into accumulator volumes (what z-slab ranks always use) */
+/* particle -> grid velocity transfer (transfer_gather_velocity.comp): 1 (default) = warp-aggregated float-atomic scatter into accumulator
+ * volumes (faster; sums differ in the last bits from run to run; what z-slab ranks always use), 0 = gather over per-step cell lists
+ * (bit-identical output run to run) */
 int blub_fluid_set_transfer_path(BlubFluid *fluid, int scatter);
 /* blub_fluid_step replays a captured CUDA graph of the step by default; 0 = launch every kernel eagerly instead */
 int blub_fluid_set_graph_replay(BlubFluid *fluid, int enabled);

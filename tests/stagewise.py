@@ -62,8 +62,12 @@ def solve_stage(orc, gpu, which, stage, converged):
     (eo, io), (eg, ig) = orc.last_solve(which), gpu.last_solve(which)
     assert 0 < io < 4000 and 0 < ig < 4000 and abs(io - ig) <= 8 + 0.05 * io, (which, io, ig)
     pg = gpu.download_grid(tap_p)
-    res = np.where(m == O.FLUID, rhs, 0.0) - util.apply_A(m, pg)
-    assert eg < tol / DT and np.abs(res).max() <= 1.05 * tol / DT + 1e-4 * np.abs(rhs).max(), (eg, np.abs(res).max(), tol / DT)
+    b64 = np.where(m == O.FLUID, rhs, 0.0)
+    res_g = np.abs(b64 - util.apply_A(m, pg)).max()
+    res_o = np.abs(b64 - util.apply_A(m, orc.grid(arr_p))).max()
+    # the recursive residual of an fp32 CG drifts away from the true one over hundreds of iterations (in the oracle as well): the TRUE
+    # residual of the CUDA solution, recomputed in float64, has to be as good as the oracle's
+    assert eg < tol / DT and res_g <= 1.25 * max(res_o, tol / DT) + 1e-6 * np.abs(rhs).max(), (eg, res_g, res_o, tol / DT)
     grid_close(orc.grid(arr_p), pg, f"p{which + 1} converged ({io} / {ig} iterations)", rel=5e-3, abs_=1e-3)
     for f in (orc, gpu):
         f.set_solver_config(which, 0.1, 32, 4)

