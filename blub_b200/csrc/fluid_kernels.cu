@@ -16,111 +16,160 @@ constexpr int PT = 256; // threads per block for particle and cell kernels
 // Cell indices fit 32 bits (HybridFluid::new rejects grids of 2^31 cells or more): no 64-bit multiplies / divisions in the
 // per-cell and per-particle kernels.
 __device__ __forceinline__ int lin(const GridDim &g, int x, int y, int z) { return (z * g.ny + y) * g.nx + x; }
-__device__ __forceinline__ void cell_of(const GridDim &g, int64_t i64, int &x, int &y, int &z) {
-    const unsigned i = (unsigned)i64, nx = (unsigned)g.nx, ny = (unsigned)g.ny;
-    const unsigned t = i / nx;
-    x = (int)(i - t * nx);
-    z = (int)(t / ny);
-    y = (int)(t - (unsigned)z * ny);
-}
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
 __device__ __forceinline__ float signf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
-// divergence_compute.comp:28-86
-__global__ void __launch_bounds__(PT) divergence_compute_kernel(GridDim g, const int8_t *__restrict__ marker,
+// ------------------------------------------------------------------------------------------------ grid passes
+// All grid passes work on the 1-bit-per-cell FLUID mask (FluidBits, rebuilt with every finished marker volume): one thread per 32-cell
+// word of a row decides from a handful of mask words whether any of its cells has anything to do (in a dam break ~85 % of the words
+// have not), then the WARP walks the words that have, lane = cell, so that the loads and stores of a word are coalesced.  Cells that
+// are more than one cell away from every FLUID cell are not visited at all: nothing reads their faces (P2G rewrites every face a
+// particle can reach, the extrapolation fills the one-cell ring G2P can reach), the reference leaves them stale as well.
+__device__ __forceinline__ unsigned fbits(const GridDim &g, const FluidBits &b, int xw, int y, int z) {
+    if (xw < 0 || xw >= b.wpr || y < 0 || y >= g.ny || z < 0 || z >= g.nz) return 0u;
+    return __ldg(b.words + (z * g.ny + y) * b.wpr + xw);
+}
+struct WordPos {
+    int xw, y, z, cells;
+    bool inside;
+};
+__device__ __forceinline__ WordPos word_of_thread(const GridDim &g, const FluidBits &b) {
+    const int w = blockIdx.x * PT + threadIdx.x;
+    WordPos p;
+    p.inside = w < b.wpr * g.ny * g.nz;
+    p.xw = p.inside ? w % b.wpr : 0;
+    const int rowi = p.inside ? w / b.wpr : 0;
+    p.y = rowi % g.ny;
+    p.z = rowi / g.ny;
+    p.cells = min(32, g.nx - p.xw * 32);
+    return p;
+}
+__device__ __forceinline__ unsigned cells_mask(const WordPos &p) { return p.cells == 32 ? 0xffffffffu : ((1u << p.cells) - 1u); }
+// FLUID cells of the word dilated by one cell in every dimension
+__device__ __forceinline__ unsigned near_fluid_word(const GridDim &g, const FluidBits &b, const WordPos &p) {
+    unsigned near = 0;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const unsigned f = fbits(g, b, p.xw, p.y + dy, p.z + dz);
+            near |= f | (f << 1) | (f >> 1) | (fbits(g, b, p.xw - 1, p.y + dy, p.z + dz) >> 31) | (fbits(g, b, p.xw + 1, p.y + dy, p.z + dz) << 31);
+        }
+    return near & cells_mask(p);
+}
+// The warp walks the words whose `todo` mask is not empty; body(cell index, x, y, z, lane of the word's owner) runs with lane = cell on the
+// set bits.  All 32 lanes of the warp must call this.
+template <class Body>
+__device__ __forceinline__ void warp_walk(const GridDim &g, unsigned todo, const WordPos &p, Body &&body) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned words = __ballot_sync(full, todo != 0u);
+    while (words) {
+        const int src = __ffs(words) - 1;
+        words &= words - 1;
+        const unsigned tw = __shfl_sync(full, todo, src);
+        const int xw = __shfl_sync(full, p.xw, src), y = __shfl_sync(full, p.y, src), z = __shfl_sync(full, p.z, src);
+        body((tw >> lane) & 1u, xw * 32 + lane, y, z, src);
+    }
+}
+
+// divergence_compute.comp:28-86 (only FLUID cells get a right-hand side; the solver zeroes the rest)
+__global__ void __launch_bounds__(PT) divergence_compute_kernel(GridDim g, FluidBits b, const int8_t *__restrict__ marker,
                                                                 const float *__restrict__ ux, const float *__restrict__ uy,
                                                                 const float *__restrict__ uz, const uint2 *__restrict__ vox,
                                                                 float *__restrict__ rhs) {
-    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
-    if (i >= g.n) return;
-    if (marker[i] != CELL_FLUID) return;
-    const float px = ux[i], py = uy[i], pz = uz[i];
-    const float nx = ux[i - 1], ny = uy[i - g.sy], nz = uz[i - g.sz];
-    float d = px - nx;
-    d += py - ny;
-    d += pz - nz;
-    if (marker[i - 1] == CELL_SOLID) d += nx - load_voxel(vox, i - 1).x;
-    if (marker[i - g.sy] == CELL_SOLID) d += ny - load_voxel(vox, i - g.sy).y;
-    if (marker[i - g.sz] == CELL_SOLID) d += nz - load_voxel(vox, i - g.sz).z;
-    if (marker[i + 1] == CELL_SOLID) d -= px - load_voxel(vox, i + 1).x;
-    if (marker[i + g.sy] == CELL_SOLID) d -= py - load_voxel(vox, i + g.sy).y;
-    if (marker[i + g.sz] == CELL_SOLID) d -= pz - load_voxel(vox, i + g.sz).z;
-    rhs[i] = d;
+    const WordPos p = word_of_thread(g, b);
+    const unsigned todo = p.inside ? fbits(g, b, p.xw, p.y, p.z) : 0u;
+    warp_walk(g, todo, p, [&](unsigned on, int x, int y, int z, int) {
+        if (!on) return;
+        const int i = lin(g, x, y, z);
+        const float px = ux[i], py = uy[i], pz = uz[i];
+        const float nx = ux[i - 1], ny = uy[i - g.sy], nz = uz[i - g.sz];
+        float d = px - nx;
+        d += py - ny;
+        d += pz - nz;
+        if (marker[i - 1] == CELL_SOLID) d += nx - load_voxel(vox, i - 1).x;
+        if (marker[i - g.sy] == CELL_SOLID) d += ny - load_voxel(vox, i - g.sy).y;
+        if (marker[i - g.sz] == CELL_SOLID) d += nz - load_voxel(vox, i - g.sz).z;
+        if (marker[i + 1] == CELL_SOLID) d -= px - load_voxel(vox, i + 1).x;
+        if (marker[i + g.sy] == CELL_SOLID) d -= py - load_voxel(vox, i + g.sy).y;
+        if (marker[i + g.sz] == CELL_SOLID) d -= pz - load_voxel(vox, i + g.sz).z;
+        rhs[i] = d;
+    });
 }
 
-// divergence_remove.comp:19-49
-__global__ void __launch_bounds__(PT) divergence_remove_kernel(GridDim g, const int8_t *__restrict__ marker,
+// divergence_remove.comp:19-49, on the cells within one cell of the fluid
+__global__ void __launch_bounds__(PT) divergence_remove_kernel(GridDim g, FluidBits b, const int8_t *__restrict__ marker,
                                                                const float *__restrict__ p, const uint2 *__restrict__ vox,
                                                                float *__restrict__ ux, float *__restrict__ uy, float *__restrict__ uz) {
-    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
-    if (i >= g.n) return;
-    int x, y, z;
-    cell_of(g, i, x, y, z);
-    const int mc = marker[i];
-    const float pc = mc == CELL_FLUID ? p[i] : 0.0f;
-    float *const u[3] = {ux, uy, uz};
-    const int64_t nb[3] = {i + 1, i + g.sy, i + g.sz};
-    const bool inb[3] = {x + 1 < g.nx, y + 1 < g.ny, z + 1 < g.nz};
+    const WordPos wp = word_of_thread(g, b);
+    const unsigned todo = wp.inside ? near_fluid_word(g, b, wp) : 0u;
+    warp_walk(g, todo, wp, [&](unsigned on, int x, int y, int z, int) {
+        if (!on) return;
+        const int i = lin(g, x, y, z);
+        const int mc = marker[i];
+        const float pc = mc == CELL_FLUID ? p[i] : 0.0f;
+        float *const u[3] = {ux, uy, uz};
+        const int nb[3] = {i + 1, i + g.sy, i + g.sz};
+        const bool inb[3] = {x + 1 < g.nx, y + 1 < g.ny, z + 1 < g.nz};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int mn = inb[c] ? marker[nb[c]] : CELL_SOLID;
-        float v = 0.0f;
-        if (mc == CELL_FLUID || mn == CELL_FLUID) {
-            if (mc == CELL_SOLID) {
-                const Voxel s = load_voxel(vox, i);
-                v = c == 0 ? s.x : (c == 1 ? s.y : s.z);
-            } else if (mn == CELL_SOLID) {
-                Voxel s = {0, 0, 0, 0};
-                if (inb[c]) s = load_voxel(vox, nb[c]);
-                v = c == 0 ? s.x : (c == 1 ? s.y : s.z);
-            } else {
-                const float pn = mn == CELL_FLUID ? p[nb[c]] : 0.0f;
-                v = u[c][i] - (pc - pn);
+        for (int c = 0; c < 3; ++c) {
+            const int mn = inb[c] ? marker[nb[c]] : CELL_SOLID;
+            float v = 0.0f;
+            if (mc == CELL_FLUID || mn == CELL_FLUID) {
+                if (mc == CELL_SOLID) {
+                    const Voxel s = load_voxel(vox, i);
+                    v = c == 0 ? s.x : (c == 1 ? s.y : s.z);
+                } else if (mn == CELL_SOLID) {
+                    Voxel s = {0, 0, 0, 0};
+                    if (inb[c]) s = load_voxel(vox, nb[c]);
+                    v = c == 0 ? s.x : (c == 1 ? s.y : s.z);
+                } else {
+                    const float pn = mn == CELL_FLUID ? p[nb[c]] : 0.0f;
+                    v = u[c][i] - (pc - pn);
+                }
             }
+            u[c][i] = v;
         }
-        u[c][i] = v;
-    }
+    });
 }
 
-// density_projection_position_change.comp:18-51 (writes the displacement field INTO the velocity volumes)
-__global__ void __launch_bounds__(PT) position_change_kernel(GridDim g, const StepParams *__restrict__ params,
+// density_projection_position_change.comp:18-51 (writes the displacement field INTO the velocity volumes), on the cells within one
+// cell of the fluid
+__global__ void __launch_bounds__(PT) position_change_kernel(GridDim g, FluidBits b, const StepParams *__restrict__ params,
                                                              const int8_t *__restrict__ marker, const float *__restrict__ p,
                                                              float *__restrict__ ux, float *__restrict__ uy, float *__restrict__ uz) {
-    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
-    if (i >= g.n) return;
-    int x, y, z;
-    cell_of(g, i, x, y, z);
+    const WordPos wp = word_of_thread(g, b);
+    const unsigned todo = wp.inside ? near_fluid_word(g, b, wp) : 0u;
     const float dt = params->dt;
-    const int mc = marker[i];
-    const float pc = mc == CELL_FLUID ? p[i] : 0.0f;
-    float *const u[3] = {ux, uy, uz};
-    const int64_t nb[3] = {i + 1, i + g.sy, i + g.sz};
-    const bool inb[3] = {x + 1 < g.nx, y + 1 < g.ny, z + 1 < g.nz};
+    warp_walk(g, todo, wp, [&](unsigned on, int x, int y, int z, int) {
+        if (!on) return;
+        const int i = lin(g, x, y, z);
+        const int mc = marker[i];
+        const float pc = mc == CELL_FLUID ? p[i] : 0.0f;
+        float *const u[3] = {ux, uy, uz};
+        const int nb[3] = {i + 1, i + g.sy, i + g.sz};
+        const bool inb[3] = {x + 1 < g.nx, y + 1 < g.ny, z + 1 < g.nz};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int mn = inb[c] ? marker[nb[c]] : CELL_SOLID;
-        const float pn = mn == CELL_FLUID ? p[nb[c]] : 0.0f;
-        float d = (pn - pc) * dt;
-        if (mc == CELL_SOLID || mn == CELL_SOLID) d = 0.0f;
-        u[c][i] = d;
-    }
+        for (int c = 0; c < 3; ++c) {
+            const int mn = inb[c] ? marker[nb[c]] : CELL_SOLID;
+            const float pn = mn == CELL_FLUID ? p[nb[c]] : 0.0f;
+            float d = (pn - pc) * dt;
+            if (mc == CELL_SOLID || mn == CELL_SOLID) d = 0.0f;
+            u[c][i] = d;
+        }
+    });
 }
 
 // extrapolate_velocity.comp:26-90.  In place: only invalid faces are written, only valid faces are read.
 // A face of component c is VALID when its cell or the cell's +c neighbour is FLUID (:5-10); an invalid face takes the average of
 // the valid ones among its 8 in-plane neighbours (:26-90, first in-plane axis fastest, as in the shader's contribution lists).
-//
-// Works on the 1-bit-per-cell FLUID mask (FluidBits): one thread per 32-cell word of a row forms the validity words of its 3x3
-// neighbourhood with shifts and ORs, knows at once whether any of its 32 cells has anything to do (almost none has: the work is the
-// one-cell ring around the fluid surface) and only then touches the velocity volumes.  Same neighbours, same order, same
-// arithmetic as the per-cell form it replaces (0.73 ms -> see profiles/ at step 110 of the 256^3 dam break).
-__device__ __forceinline__ unsigned fbits(const GridDim &g, const FluidBits &b, int xw, int y, int z) {
-    if (xw < 0 || xw >= b.wpr || y < 0 || y >= g.ny || z < 0 || z >= g.nz) return 0u;
-    return __ldg(b.words + (z * g.ny + y) * b.wpr + xw);
-}
-// validity words of component c for the word (xw, y, z): bit k = face of cell 32 xw + k is valid
+// The owner thread of a word forms the validity words of the 3 x 3 in-plane neighbourhood with shifts and ORs and from them the mask
+// of cells that get a value; the warp then walks those words, every lane testing its own bit of the eight neighbour words (handed over
+// by shuffles).  Same neighbours, same order, same arithmetic as a per-cell pass over the marker volume.
+// validity word of component c for the word (xw, y, z): bit k = the face of cell 32 xw + k is valid
 __device__ __forceinline__ unsigned valid_word(const GridDim &g, const FluidBits &b, int c, int xw, int y, int z) {
     const unsigned f = fbits(g, b, xw, y, z);
     if (c == 0) return f | (f >> 1) | (fbits(g, b, xw + 1, y, z) << 31);
@@ -128,70 +177,71 @@ __device__ __forceinline__ unsigned valid_word(const GridDim &g, const FluidBits
     return f | fbits(g, b, xw, y, z + 1);
 }
 template <int C>
-__device__ __forceinline__ void extrapolate_component(const GridDim &g, const FluidBits &b, int xw, int y, int z, unsigned cells_mask, unsigned fluid,
-                                                      float *__restrict__ u) {
+__device__ __forceinline__ void extrapolate_component(const GridDim &g, const FluidBits &b, const WordPos &p, bool near, float *__restrict__ u) {
     // nb[ob + 1][oa + 1]: validity of the in-plane neighbour (oa along the first in-plane axis, ob along the second), as a word aligned
     // with this thread's cells
     unsigned nb[3][3];
-    if (C == 0) { // in-plane axes y (fast), z
 #pragma unroll
-        for (int ob = -1; ob <= 1; ++ob)
+    for (int ob = 0; ob < 3; ++ob)
 #pragma unroll
-            for (int oa = -1; oa <= 1; ++oa) nb[ob + 1][oa + 1] = valid_word(g, b, 0, xw, y + oa, z + ob);
-    } else {      // in-plane axes x (fast) and z (C == 1) or y (C == 2)
+        for (int oa = 0; oa < 3; ++oa) nb[ob][oa] = 0u;
+    if (near) {
+        if (C == 0) { // in-plane axes y (fast), z
 #pragma unroll
-        for (int ob = -1; ob <= 1; ++ob) {
-            const int yy = C == 1 ? y : y + ob, zz = C == 1 ? z + ob : z;
-            const unsigned m = valid_word(g, b, C, xw, yy, zz), l = valid_word(g, b, C, xw - 1, yy, zz), r = valid_word(g, b, C, xw + 1, yy, zz);
-            nb[ob + 1][0] = (m << 1) | (l >> 31); // neighbour x - 1
-            nb[ob + 1][1] = m;
-            nb[ob + 1][2] = (m >> 1) | (r << 31); // neighbour x + 1
+            for (int ob = -1; ob <= 1; ++ob)
+#pragma unroll
+                for (int oa = -1; oa <= 1; ++oa) nb[ob + 1][oa + 1] = valid_word(g, b, 0, p.xw, p.y + oa, p.z + ob);
+        } else {      // in-plane axes x (fast) and z (C == 1) or y (C == 2)
+#pragma unroll
+            for (int ob = -1; ob <= 1; ++ob) {
+                const int yy = C == 1 ? p.y : p.y + ob, zz = C == 1 ? p.z + ob : p.z;
+                const unsigned m = valid_word(g, b, C, p.xw, yy, zz), l = valid_word(g, b, C, p.xw - 1, yy, zz), r = valid_word(g, b, C, p.xw + 1, yy, zz);
+                nb[ob + 1][0] = (m << 1) | (l >> 31); // neighbour x - 1
+                nb[ob + 1][1] = m;
+                nb[ob + 1][2] = (m >> 1) | (r << 31); // neighbour x + 1
+            }
         }
     }
-    const unsigned own = nb[1][1];
     unsigned any = 0;
 #pragma unroll
     for (int ob = 0; ob < 3; ++ob)
 #pragma unroll
         for (int oa = 0; oa < 3; ++oa)
             if (oa != 1 || ob != 1) any |= nb[ob][oa];
-    unsigned todo = cells_mask & ~fluid & ~own & any; // non-FLUID cells whose face is invalid and has a valid neighbour
-    const int row = (z * g.ny + y) * g.nx + xw * 32;
+    // non-FLUID cells whose face is invalid and has a valid neighbour (a FLUID cell's own faces are valid: ~own covers ~fluid)
+    const unsigned todo = cells_mask(p) & ~nb[1][1] & any;
     const int sa = C == 0 ? g.sy : 1, sb = C == 2 ? g.sy : g.sz;
-    while (todo) {
-        const int k = __ffs(todo) - 1;
-        todo &= todo - 1;
+    const int lane = threadIdx.x & 31;
+    warp_walk(g, todo, p, [&](unsigned on, int x, int y, int z, int src) {
+        unsigned nbw[3][3]; // the owner's neighbour words (shuffles: every lane takes part)
+#pragma unroll
+        for (int ob = 0; ob < 3; ++ob)
+#pragma unroll
+            for (int oa = 0; oa < 3; ++oa) nbw[ob][oa] = (oa != 1 || ob != 1) ? __shfl_sync(0xffffffffu, nb[ob][oa], src) : 0u;
+        if (!on) return;
+        const int i = lin(g, x, y, z);
         float numv = 0.0f, avg = 0.0f;
 #pragma unroll
         for (int ob = -1; ob <= 1; ++ob)
 #pragma unroll
             for (int oa = -1; oa <= 1; ++oa) {
                 if (oa == 0 && ob == 0) continue;
-                if ((nb[ob + 1][oa + 1] >> k) & 1u) {
+                if ((nbw[ob + 1][oa + 1] >> lane) & 1u) {
                     numv += 1.0f;
-                    avg += u[row + k + oa * sa + ob * sb];
+                    avg += u[i + oa * sa + ob * sb];
                 }
             }
-        u[row + k] = avg / numv; // numv > 0: the cell is in `any`
-    }
+        u[i] = avg / numv; // numv > 0: the cell is in `any`
+    });
 }
 __global__ void __launch_bounds__(PT) extrapolate_kernel(GridDim g, FluidBits b, float *__restrict__ ux, float *__restrict__ uy, float *__restrict__ uz) {
-    const int w = blockIdx.x * PT + threadIdx.x;
-    if (w >= b.wpr * g.ny * g.nz) return;
-    const int xw = w % b.wpr, rowi = w / b.wpr, y = rowi % g.ny, z = rowi / g.ny;
-    // nothing to do unless a FLUID cell lies in [x-1, x+2] x [y-1, y+2] x [z-1, z+2] of one of this word's cells
-    unsigned near = 0;
-#pragma unroll
-    for (int dz = -1; dz <= 2; ++dz)
-#pragma unroll
-        for (int dy = -1; dy <= 2; ++dy) near |= fbits(g, b, xw, y + dy, z + dz) | (fbits(g, b, xw - 1, y + dy, z + dz) >> 31) | (fbits(g, b, xw + 1, y + dy, z + dz) & 3u);
-    if (!near) return;
-    const int cells = min(32, g.nx - xw * 32);
-    const unsigned cells_mask = cells == 32 ? 0xffffffffu : ((1u << cells) - 1u);
-    const unsigned fluid = fbits(g, b, xw, y, z);
-    extrapolate_component<0>(g, b, xw, y, z, cells_mask, fluid, ux);
-    extrapolate_component<1>(g, b, xw, y, z, cells_mask, fluid, uy);
-    extrapolate_component<2>(g, b, xw, y, z, cells_mask, fluid, uz);
+    const WordPos p = word_of_thread(g, b);
+    // nothing to do unless a FLUID cell lies within one cell of one of this word's cells
+    const bool near = p.inside && near_fluid_word(g, b, p) != 0u;
+    if (!__any_sync(0xffffffffu, near)) return;
+    extrapolate_component<0>(g, b, p, near, ux);
+    extrapolate_component<1>(g, b, p, near, uy);
+    extrapolate_component<2>(g, b, p, near, uz);
 }
 
 // ------------------------------------------------------------------------------------------------ G2P + advection
@@ -443,16 +493,18 @@ inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 
 } // namespace
 
 // ------------------------------------------------------------------------------------------------ launchers
-void launch_divergence_compute(cudaStream_t st, const GridDim &g, const int8_t *marker, float *const u[3], const uint2 *vox, float *rhs) {
-    BLUB_LAUNCH(divergence_compute_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, u[0], u[1], u[2], vox, rhs);
+static int word_blocks(const GridDim &g, const FluidBits &bits) { return blocks_for((int64_t)bits.wpr * g.ny * g.nz, PT); }
+
+void launch_divergence_compute(cudaStream_t st, const GridDim &g, const FluidBits &bits, const int8_t *marker, float *const u[3], const uint2 *vox, float *rhs) {
+    BLUB_LAUNCH(divergence_compute_kernel, word_blocks(g, bits), PT, 0, st, g, bits, marker, u[0], u[1], u[2], vox, rhs);
 }
 
-void launch_divergence_remove(cudaStream_t st, const GridDim &g, const int8_t *marker, const float *p, const uint2 *vox, float *const u[3]) {
-    BLUB_LAUNCH(divergence_remove_kernel, blocks_for(g.n, PT), PT, 0, st, g, marker, p, vox, u[0], u[1], u[2]);
+void launch_divergence_remove(cudaStream_t st, const GridDim &g, const FluidBits &bits, const int8_t *marker, const float *p, const uint2 *vox, float *const u[3]) {
+    BLUB_LAUNCH(divergence_remove_kernel, word_blocks(g, bits), PT, 0, st, g, bits, marker, p, vox, u[0], u[1], u[2]);
 }
 
 void launch_extrapolate(cudaStream_t st, const GridDim &g, const FluidBits &bits, float *const u[3]) {
-    BLUB_LAUNCH(extrapolate_kernel, blocks_for((int64_t)bits.wpr * g.ny * g.nz, PT), PT, 0, st, g, bits, u[0], u[1], u[2]);
+    BLUB_LAUNCH(extrapolate_kernel, word_blocks(g, bits), PT, 0, st, g, bits, u[0], u[1], u[2]);
 }
 
 void launch_clear_marker(cudaStream_t st, const GridDim &g, int8_t *marker) {
@@ -471,8 +523,8 @@ void launch_advect_migrate(cudaStream_t st, const GridDim &g, const StepParams *
     BLUB_LAUNCH(advect_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2], vox, marker, mig);
 }
 
-void launch_position_change(cudaStream_t st, const GridDim &g, const StepParams *params, const int8_t *marker, const float *p, float *const u[3]) {
-    BLUB_LAUNCH(position_change_kernel, blocks_for(g.n, PT), PT, 0, st, g, params, marker, p, u[0], u[1], u[2]);
+void launch_position_change(cudaStream_t st, const GridDim &g, const FluidBits &bits, const StepParams *params, const int8_t *marker, const float *p, float *const u[3]) {
+    BLUB_LAUNCH(position_change_kernel, word_blocks(g, bits), PT, 0, st, g, bits, params, marker, p, u[0], u[1], u[2]);
 }
 
 void launch_correct_particles(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos,

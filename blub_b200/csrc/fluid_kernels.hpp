@@ -56,15 +56,16 @@ void launch_fluid_bits(cudaStream_t st, const GridDim &g, const int8_t *marker, 
 int binning_scan_blocks(const GridDim &g);
 void launch_binning(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *src, float4 *dst, const CellLists &l);
 
-void launch_divergence_compute(cudaStream_t st, const GridDim &g, const int8_t *marker, float *const u[3], const uint2 *vox, float *rhs);
-void launch_divergence_remove(cudaStream_t st, const GridDim &g, const int8_t *marker, const float *p, const uint2 *vox, float *const u[3]);
+// grid passes: they visit the cells within one cell of the fluid only (FluidBits), everything further away keeps its previous value
+void launch_divergence_compute(cudaStream_t st, const GridDim &g, const FluidBits &bits, const int8_t *marker, float *const u[3], const uint2 *vox, float *rhs);
+void launch_divergence_remove(cudaStream_t st, const GridDim &g, const FluidBits &bits, const int8_t *marker, const float *p, const uint2 *vox, float *const u[3]);
 void launch_extrapolate(cudaStream_t st, const GridDim &g, const FluidBits &bits, float *const u[3]);
 void launch_clear_marker(cudaStream_t st, const GridDim &g, int8_t *marker);
 void launch_advect(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos, float4 *const row[3],
                    float *const u[3], const uint2 *vox, int8_t *marker);
 void launch_advect_migrate(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos, float4 *const row[3],
                            float *const u[3], const uint2 *vox, int8_t *marker, const MigrateOut &mig);
-void launch_position_change(cudaStream_t st, const GridDim &g, const StepParams *params, const int8_t *marker, const float *p, float *const u[3]);
+void launch_position_change(cudaStream_t st, const GridDim &g, const FluidBits &bits, const StepParams *params, const int8_t *marker, const float *p, float *const u[3]);
 void launch_correct_particles(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos,
                               const int8_t *marker, float *const u[3]);
 

@@ -434,7 +434,8 @@ void HybridFluid::run_stage(int stage, float dt) {
         }
         break;
     case 1: // compute divergence -> PCG residual (:835-840)
-        launch_divergence_compute(stream_, grid_, marker_.ptr, u, voxels_, solver_->residual());
+        refresh_fluid_bits();
+        launch_divergence_compute(stream_, grid_, bits, marker_.ptr, u, voxels_, solver_->residual());
         break;
     case 2: // primary pressure solver (:843-852)
         solver_->solve(stream_, *field_velocity_, 0, marker_.ptr, params_dev_, quirks);
@@ -447,7 +448,8 @@ void HybridFluid::run_stage(int stage, float dt) {
         }
         break;
     case 4: // make velocity grid divergence free (:901-904)
-        launch_divergence_remove(stream_, grid_, marker_.ptr, field_velocity_->pressure(), voxels_, u);
+        refresh_fluid_bits();
+        launch_divergence_remove(stream_, grid_, bits, marker_.ptr, field_velocity_->pressure(), voxels_, u);
         break;
     case 5: // extrapolate velocity grid (:906-909)
         refresh_fluid_bits();
@@ -489,7 +491,8 @@ void HybridFluid::run_stage(int stage, float dt) {
         if (!capturing_) field_density_->enqueue_error_buffer_read(stream_, dt);
         break;
     case 11: // compute position change (:959-962)
-        launch_position_change(stream_, grid_, params_dev_, marker_.ptr, field_density_->pressure(), u);
+        refresh_fluid_bits();
+        launch_position_change(stream_, grid_, bits, params_dev_, marker_.ptr, field_density_->pressure(), u);
         break;
     case 12: // extrapolate (:963-966)
         refresh_fluid_bits();

@@ -93,12 +93,13 @@ def compare_one_step(orc, gpu, robust=False, before_step=None):
     report["iterations1"] = solve_stage(orc, gpu, 0, 2, robust)
     # continue from the ORACLE's pressure so that solver round-off does not leak into the per-stage comparison
     gpu.upload_grid(F.TAP_P_VEL, orc.grid(O.ARR_P_VEL))
+    near = util.near_fluid(m_o)  # the grid passes visit the cells within one cell of the fluid (see util.near_fluid)
     run(3, 5)  # (binning off) + divergence_remove
     for c, (tg, to) in enumerate(STAGE_TAPS):
-        grid_close(orc.grid(to), gpu.download_grid(tg), f"projected u[{c}]")
+        grid_close(orc.grid(to), gpu.download_grid(tg), f"projected u[{c}]", mask=near)
     run(5, 6)  # extrapolate
     for c, (tg, to) in enumerate(STAGE_TAPS):
-        grid_close(orc.grid(to), gpu.download_grid(tg), f"extrapolated u[{c}]")
+        grid_close(orc.grid(to), gpu.download_grid(tg), f"extrapolated u[{c}]", mask=near)
     for c, (tg, to) in enumerate(STAGE_TAPS):
         gpu.upload_grid(tg, orc.grid(to))
     run(6, 9)  # clear + advect + boundary marker
@@ -116,9 +117,10 @@ def compare_one_step(orc, gpu, robust=False, before_step=None):
     gpu.upload_grid(F.TAP_RESIDUAL, orc.grid(O.ARR_RESIDUAL))
     report["iterations2"] = solve_stage(orc, gpu, 1, 10, robust)
     gpu.upload_grid(F.TAP_P_DEN, orc.grid(O.ARR_P_DEN))
+    near = util.near_fluid(orc.grid(O.ARR_MARKER))
     run(11, 13)  # position change + extrapolate
     for c, (tg, to) in enumerate(STAGE_TAPS):
-        grid_close(orc.grid(to), gpu.download_grid(tg), f"displacement[{c}]")
+        grid_close(orc.grid(to), gpu.download_grid(tg), f"displacement[{c}]", mask=near)
         gpu.upload_grid(tg, orc.grid(to))
     run(13, 14)  # correct particles
     report["correct"] = particles_close(orc.particles()[:, :3], gpu.download_particles()[:, :3], "corrected positions", 2e-4, frac, loose=0.5)

@@ -82,3 +82,20 @@ def tight_solver(*fluids, tol=1e-4, max_it=128):
     for f in fluids:
         f.set_solver_config(0, tol, max_it, 4)
         f.set_solver_config(1, tol, max_it, 4)
+
+
+def near_fluid(marker):
+    """Cells within one cell (Chebyshev) of a FLUID cell: the region the grid passes of the CUDA path visit.  Further away nothing reads the
+    faces (P2G rewrites every face a particle can reach, extrapolation fills the one-cell ring G2P can reach) and the reference's P2G leaves
+    them stale too, so grid fields are compared inside this region."""
+    fl = marker == O.FLUID
+    out = fl.copy()
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                sh = np.zeros_like(fl)
+                src = [slice(max(0, -d), fl.shape[k] - max(0, d)) for k, d in enumerate((dz, dy, dx))]
+                dst = [slice(max(0, d), fl.shape[k] - max(0, -d)) for k, d in enumerate((dz, dy, dx))]
+                sh[tuple(dst)] = fl[tuple(src)]
+                out |= sh
+    return out

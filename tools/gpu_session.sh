@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call, many answers: every call costs 1.5-3 minutes of box time before the command even starts, so measurements are
 # batched.  Usage (from the repository root, on the GPU box):
-#     bash tools/gpu_session.sh [tests] [smoke] [timeline] [variants] [p2gparts] [pcgparts] [ncustep] [bench] [launches] [ncu] [blubrun]
+#     bash tools/gpu_session.sh [tests] [smoke] [timeline] [variants] [p2gparts] [pcgparts] [overhead] [sanitize] [ncustep] [bench] [launches] [ncu] [blubrun]
 # Everything lands in gpurun_out/session_*.{txt,json,csv}; nothing here is a bench number unless it comes from bench.py outside ncu.
 set -u
 OUT=gpurun_out
@@ -43,6 +43,12 @@ if want pcgparts; then      # launch list of the solver kernels of one early ste
 import csv,sys
 for r in csv.DictReader(sys.stdin):
     if r.get('Metric Name')=='gpu__time_duration.sum': print(r['Kernel Name'][:60], r['Metric Value'], r['Metric Unit'])"
+fi
+if want overhead; then
+    python tools/profile_targets.py pcg_overhead > $OUT/session_pcg_overhead.txt 2>&1; cat $OUT/session_pcg_overhead.txt
+fi
+if want sanitize; then
+    bash tools/sanitize.sh pcg step 2>&1 | tee $OUT/session_sanitize.txt | tail -40
 fi
 if want ncustep; then       # full captures INSIDE the dam break (eager launches): the sparse PCG solve at step 110, one P2G gather
     BLUB_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pcg_solve_persistent --launch-skip 220 -c 1 -o $OUT/session_pcg_step110 \

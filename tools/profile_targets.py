@@ -73,6 +73,22 @@ elif mode == "cellstats":
         seg = rows.reshape(f.nz, f.ny, f.nx // 32, 32).sum(-1) if f.nx % 32 == 0 else rows.sum(-1, keepdims=True)
         print(f"step {cp}: fluid cells {nz.size} ({100.0 * nz.size / f.n:.1f} %), particles per fluid cell mean {nz.mean():.2f} q99.9 {np.quantile(nz, 0.999):.0f} max {cnt.max()}, "
               f"cells > 32: {(cnt > 32).sum()}, > 100: {(cnt > 100).sum()}, > 1000: {(cnt > 1000).sum()}; particles per 32-cell row segment max {seg.max()}, > 384: {(seg > 384).sum()}", flush=True)
+elif mode == "pcg_overhead":
+    # the fixed cost of an iteration: a 256^3 grid whose only fluid is one small block (one tile / a few columns): ms per solve / 66 = barrier +
+    # reduction cost of one phase
+    n = 256
+    for blob in (8, 64):
+        f = blub_b200.HybridFluid(n, n, n, 8)
+        m = np.full((n, n, n), -1, dtype=np.int8)
+        m[0], m[-1], m[:, 0], m[:, -1], m[:, :, 0], m[:, :, -1] = 0, 0, 0, 0, 0, 0
+        m[100:100 + blob, 100:100 + blob, 128:128 + blob] = 1
+        b = np.random.default_rng(1).uniform(-1, 1, (n, n, n)).astype(np.float32)
+        f.upload_grid(F.TAP_MARKER, m)
+        f.upload_grid(F.TAP_RESIDUAL, b)
+        f.set_solver_config(0, 0.0, 32, 4)
+        ms = sorted(f.time_solve(0, F.DT_120HZ, 7))
+        print(f"fluid block {blob}^3: ms per solve {ms[len(ms) // 2]:.4f} = {1e3 * ms[len(ms) // 2] / 66:.2f} us per phase; work {f.solver_work()}", flush=True)
+        f.close()
 elif mode == "stages":
     # python tools/profile_targets.py stages [scene] [checkpoint steps ...]: stage times after so many steps (default 3)
     scene = sys.argv[2] if len(sys.argv) > 2 else "dam_256"
