@@ -955,10 +955,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
 // tile kernel up to the grouping of the partial sums.  Same phases, barriers, reductions and statistics as pcg_solve_persistent_kernel.
 __global__ void __launch_bounds__(PCG_THREADS) pcg_column_fill_kernel(GridDim g, TileMap t, const uint8_t *__restrict__ codes,
                                                                       const uint8_t *__restrict__ tile_active, const int *__restrict__ col_offset,
-                                                                      int *__restrict__ col_list) {
+                                                                      int tile_lo, int tile_hi, int *__restrict__ col_list) {
     __shared__ int sh_warp[PCG_THREADS / 32];
     const TileCtx c = tile_ctx(g, t);
-    if (tile_active[c.tile] != 1) return; // block-uniform
+    if (c.tile < tile_lo || c.tile >= tile_hi || tile_active[c.tile] != 1) return; // block-uniform; [tile_lo, tile_hi): the owned tiles of a slab
     bool active = false;
     if (c.valid) {
 #pragma unroll
@@ -1018,15 +1018,15 @@ __global__ void __launch_bounds__(1024) pcg_compact_kernel(const uint8_t *__rest
 #define PCG_FOR_EACH_COLUMN(c)                                                                                                            \
     for (int cb_ = warp_first, ci_ = cb_ + lane < ncols ? a.col_list[cb_ + lane] : -1, cn_ = -1; cb_ < ncols; cb_ += col_stride, ci_ = cn_) \
         if ((cn_ = cb_ + col_stride + lane < ncols ? a.col_list[cb_ + col_stride + lane] : -1), true)                                      \
-            if (const TileCtx c = column_ctx(ci_); true)
-__device__ __forceinline__ TileCtx column_ctx(int i) {
+            if (const TileCtx c = column_ctx(ci_, sz); true)
+__device__ __forceinline__ TileCtx column_ctx(int i, int sz) {
     TileCtx c;
     c.tile = 0;
-    c.tz = 0;
     c.valid = i >= 0;
     c.first = true; // x-neighbours from memory: the neighbouring lanes hold unrelated columns
     c.last = true;
     c.i = i >= 0 ? i : 0;
+    c.tz = (c.i / sz) / PCG_TZ; // tile layer of the column (z-slab ranks: which columns touch a ghost plane)
     return c;
 }
 
@@ -1036,7 +1036,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
     __shared__ float sh[PCG_THREADS / 32];
     __shared__ double shd;
     __shared__ float shf;
+    __shared__ double sh_csum[SLAB_MAX_WORLD];
+    __shared__ float sh_cmax[SLAB_MAX_WORLD];
+    __shared__ int sh_dead;
     const TileMap t = a.t;
+    const SlabComm &cm_ = a.comm;
+    const bool sharded = cm_.world > 1;
     const int nact = *a.num_active, ncols = *a.num_cols;
     const int lane = linear_tid() & 31;
     // Tiles are dealt to the blocks from block 0 upwards, columns to the warps from the LAST warp of the last block downwards: when there are
@@ -1047,12 +1052,19 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
     TileEnv e;
     e.g = a.g;
     e.codes = a.codes;
-    e.sharded = false; // single GPU only: a z-slab rank runs pcg_solve_persistent_kernel
-    e.tz_first = 0;
-    e.tz_last = t.tiles_z - 1;
-    e.push = 0;
-    e.peer_r_lo = nullptr;
-    e.peer_r_hi = nullptr;
+    e.sharded = sharded;
+    // slab geometry: tile layers tz_first..tz_last are owned; the planes just outside are ghost planes fed by the neighbours
+    e.tz_first = cm_.halo / PCG_TZ;
+    e.tz_last = t.tiles_z - 1 - cm_.halo / PCG_TZ;
+    e.push = cm_.owned_nz * a.g.sz; // index distance between an owned boundary plane and its image in the neighbour
+    e.peer_r_lo = cm_.peer_r[0];
+    e.peer_r_hi = cm_.peer_r[1];
+    const int sz = a.g.sz;
+    unsigned seq = 0;
+    if (linear_tid() == 0) sh_dead = 0;
+    if (sharded) seq = *cm_.seq;
+    __syncthreads();
+    if (sharded) slab_start_handshake(cm_, seq, sh_csum, sh_cmax, &sh_dead);
 
     // ---- init: r <- b - A p, sigma <- z.r (pressure_init.comp:45-83, pressure_solver.rs:625-649); s stays 0
     float acc = 0.0f;
@@ -1069,6 +1081,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
     }
     double tot = grid_sum(grid, psumB, acc, sh, &shd);
     float gmax = 0.0f;
+    if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
     float sigma = (float)tot;
     float alpha = 0.0f, beta = 0.0f, max_error = 0.0f;
     int num_iterations = 0;
@@ -1089,6 +1102,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
             search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
         }
         tot = grid_sum(grid, psumA, acc, sh, &shd);
+        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
         alpha = guarded_div(sigma, (float)tot); // RESULTMODE_ALPHA, pressure_reduce.comp:73-75
 
         const bool with_err = (a.max_iterations == it) || (it > 0 && it % a.check_frequency == 0); // pressure_solver.rs:676-677
@@ -1117,6 +1131,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
             gmax = shf;
             __syncthreads();
         }
+        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
         const float zr = (float)tot;
         if (with_err) {
             const float tol = a.params->tolerance[a.which];
@@ -1129,13 +1144,40 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
         beta = guarded_div(zr, sigma); // RESULTMODE_BETA, pressure_reduce.comp:77-80
         sigma = zr;
     }
+    if (sharded) {
+        // hand the boundary planes of the solution to the neighbours (warm start of their next init, pressure gradient across the slab
+        // face), then one more round so that nobody leaves before its ghost planes are complete
+        float *const peer_p_lo = cm_.peer_p[a.which][0], *const peer_p_hi = cm_.peer_p[a.which][1];
+        PCG_FOR_EACH_TILE(tile) {
+            const TileCtx c = tile_ctx_id(e.g, t, tile & (TILE_DENSE_BIT - 1));
+            if (!c.valid) continue;
+            if (c.tz == e.tz_first && peer_p_lo) st4(peer_p_lo + c.i + e.push, ld4(a.p + c.i));
+            if (c.tz == e.tz_last && peer_p_hi) {
+                const int i = c.i + (PCG_TZ - 1) * e.g.sz;
+                st4(peer_p_hi + i - e.push, ld4(a.p + i));
+            }
+        }
+        PCG_FOR_EACH_COLUMN(c) {
+            if (!c.valid) continue;
+            if (c.tz == e.tz_first && peer_p_lo) st4(peer_p_lo + c.i + e.push, ld4(a.p + c.i));
+            if (c.tz == e.tz_last && peer_p_hi) {
+                const int i = c.i + (PCG_TZ - 1) * e.g.sz;
+                st4(peer_p_hi + i - e.push, ld4(a.p + i));
+            }
+        }
+        grid.sync();
+        double dummy = 0.0;
+        float dmax = 0.0f;
+        comm_allreduce(cm_, ++seq, dummy, dmax, sh_csum, sh_cmax, &sh_dead);
+        if (blockIdx.x == 0 && linear_tid() == 0) *cm_.seq = seq;
+    }
     if (blockIdx.x == 0 && linear_tid() == 0) {
         a.scal->alpha = alpha;
         a.scal->beta = beta;
         a.scal->sigma = sigma;
         a.scal->max_error = max_error;
         a.scal->num_iterations = num_iterations;
-        a.scal->done = 1;
+        a.scal->done = sh_dead ? -1 : 1;
     }
 }
 #undef PCG_FOR_EACH_COLUMN
@@ -1632,7 +1674,7 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
         // one cooperative launch for the whole solve; s ping-pongs between search_ and aux_ (both zero off the active tiles)
         BLUB_CUDA_CHECK(cudaMemsetAsync(aux_.ptr, 0, (size_t)g.n * sizeof(float), stream));
         const int ghost_tiles = (comm.halo / PCG_TZ) * t.tiles_x * t.tiles_y; // ghost planes are whole tiles (SLAB_HALO == PCG_TZ)
-        const bool columns = use_columns && column_blocks_ > 0 && comm.world == 1 && !use_tma && !use_dense;
+        const bool columns = use_columns && column_blocks_ > 0 && !use_tma && !use_dense;
         int *col_offset = tile_cols_ + t.ntiles, *num_cols = tile_cols_ + 2 * t.ntiles;
         BLUB_LAUNCH(pcg_compact_kernel, 1, 1024, 0, stream, tile_active_, tile_cols_, ghost_tiles, t.ntiles - ghost_tiles, columns ? 1 : 0, tile_list_, num_active_ + 1,
                     num_active_, col_offset, num_cols);
@@ -1643,7 +1685,7 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
         args.comm = comm;
         args.col_list = col_list_; args.num_cols = num_cols;
         if (columns) { // dense tiles by the tile body, everything else column by column
-            BLUB_LAUNCH(pcg_column_fill_kernel, grid, block, 0, stream, g, t, st, ta, col_offset, col_list_);
+            BLUB_LAUNCH(pcg_column_fill_kernel, grid, block, 0, stream, g, t, st, ta, col_offset, ghost_tiles, t.ntiles - ghost_tiles, col_list_);
             int nblocks = column_blocks_;
             void *kargs[] = {&args};
             BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_columns_kernel, dim3(nblocks), t.block(), kargs, 0, stream));

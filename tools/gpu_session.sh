@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call, many answers: every call costs 1.5-3 minutes of box time before the command even starts, so measurements are
 # batched.  Usage (from the repository root, on the GPU box):
-#     bash tools/gpu_session.sh [tests] [smoke] [timeline] [variants] [p2gparts] [pcgparts] [overhead] [sanitize] [ncustep] [bench] [launches] [ncu] [blubrun]
+#     bash tools/gpu_session.sh [tests] [smoke] [timeline] [variants] [p2gparts] [pcgparts] [overhead] [multi2] [barrier] [sanitize] [ncustep] [bench] [launches] [ncu] [blubrun]
 # Everything lands in gpurun_out/session_*.{txt,json,csv}; nothing here is a bench number unless it comes from bench.py outside ncu.
 set -u
 OUT=gpurun_out
@@ -46,6 +46,15 @@ for r in csv.DictReader(sys.stdin):
 fi
 if want overhead; then
     python tools/profile_targets.py pcg_overhead > $OUT/session_pcg_overhead.txt 2>&1; cat $OUT/session_pcg_overhead.txt
+fi
+if want multi2; then        # needs gpurun --gpus 2: the multi-GPU tests, per-stage times of the sharded step, sanitizers on the 2-slab target
+    timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q --tb=short -p no:cacheprovider 2>&1 | grep -v "^$" | tail -30 > $OUT/session_multi_tests.txt; tail -12 $OUT/session_multi_tests.txt
+    timeout 600 python tools/profile_targets.py stages_sharded 2 > $OUT/session_stages_sharded2.txt 2>&1; cat $OUT/session_stages_sharded2.txt
+    SANITIZE_TIMEOUT=400 bash tools/sanitize.sh slab 2>&1 | tee $OUT/session_sanitize_slab.txt | tail -12
+fi
+if want barrier; then       # cost of one grid-wide sum, candidates in isolation (tools/barrier_bench.cu; built here if the binary did not travel)
+    [ -x tools/barrier_bench ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/barrier_bench tools/barrier_bench.cu
+    ./tools/barrier_bench > $OUT/session_barrier.txt 2>&1; cat $OUT/session_barrier.txt
 fi
 if want sanitize; then
     bash tools/sanitize.sh pcg step 2>&1 | tee $OUT/session_sanitize.txt | tail -40

@@ -9,9 +9,9 @@ mkdir -p $OUT
 TARGETS="${*:-pcg step}"
 export BLUB_NO_GRAPH=1
 for target in $TARGETS; do
-    for tool in memcheck racecheck synccheck; do
+    for tool in ${SANITIZE_TOOLS:-memcheck racecheck synccheck}; do
         log=$OUT/sanitize_${tool}_${target}.log
-        timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_targets.py $target > $log 2>&1
+        timeout ${SANITIZE_TIMEOUT:-900} compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_targets.py $target > $log 2>&1
         echo "== $tool $target: rc $? -- $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $log | tail -1)"
         grep -E "^(pcg|step|slab) " $log | tail -12
     done
