@@ -142,6 +142,7 @@ class PressureSolver {
     int tma_blocks_ = 0, column_blocks_ = 0;
     int *tile_cols_ = nullptr;        // column solver: per-tile column counts | exclusive offsets | total
     int *col_list_ = nullptr;         // compacted quad columns (linear index of the quad in its tile's first plane)
+    unsigned *barrier_ = nullptr;     // arrival counter of the column solver's grid-wide reductions
 
   public:
 };

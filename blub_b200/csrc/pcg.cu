@@ -544,6 +544,7 @@ struct PcgSolveArgs {
     const int *tile_list;   // compacted active tiles
     const int *tile_list_flagged; // the same with bit 30 set on tiles that are at least 3/4 full (pcg_prepare_kernel)
     const int *num_active;
+    unsigned *barrier;      // column solver: arrival counter of its grid-wide reductions (0 at the start of a solve)
     const int *col_list;    // column solver: compacted quad columns (4 cells x PCG_TZ planes) of the sparsely filled tiles, see pcg_solve_columns_kernel
     const int *num_cols;
     float *p, *r, *s0, *s1;
@@ -941,6 +942,76 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_persistent_kernel(Pc
 #undef PCG_FOR_EACH_TILE
 
 // ---------------------------------------------------------------------------------------------------------------
+// Grid-wide reduction of the column solver.  With the fluid working set in L2 the solve is bound by the latency of these two
+// reductions per iteration (profiles/r02_s6_pcg_overhead.md: ~8 us per phase with no work at all), so they are kept lean
+// (tools/barrier_bench.cu, profiles/r02_s7_barrier_bench.md: cooperative_groups grid.sync() + re-read 4.5 us, this form 3.7 us at 592 blocks):
+// one shared-memory pass forms the block's sum and maximum, thread 0 publishes them, arrives on a monotonically increasing counter
+// (red.release) and spins with ld.acquire until everybody of this round has arrived; then every block re-reads all partials and adds
+// them in the same fixed order in fp64: bit-identical scalars in all blocks, deterministic run to run, no broadcast step.
+// Partial buffers alternate between the two phases of an iteration, so a fast block never overwrites what a slow one still reads.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_u32(unsigned *p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+struct ReduceScratch {
+    float sh[2 * (PCG_THREADS / 32)];
+    double shd[PCG_THREADS / 32];
+};
+template <bool WITH_MAX>
+__device__ __forceinline__ void grid_reduce(unsigned *counter, unsigned &round, float *psum, float *pmax, float acc, float err, ReduceScratch &sc, double &tot,
+                                            float &gmax) {
+    constexpr int NW = PCG_THREADS / 32;
+    const int tid = linear_tid(), lane = tid & 31, w = tid >> 5;
+    acc = warp_sum(acc);
+    if (WITH_MAX) err = warp_max(err);
+    if (lane == 0) {
+        sc.sh[w] = acc;
+        if (WITH_MAX) sc.sh[NW + w] = err;
+    }
+    __syncthreads();
+    round += 1u;
+    if (tid == 0) {
+        float bs = 0.0f, bm = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            bs += sc.sh[k];
+            if (WITH_MAX) bm = fmaxf(bm, sc.sh[NW + k]);
+        }
+        psum[blockIdx.x] = bs;
+        if (WITH_MAX) pmax[blockIdx.x] = bm;
+        red_release_u32(counter, 1u);
+        const unsigned target = round * gridDim.x;
+        while (ld_acquire_u32(counter) < target) {}
+    }
+    __syncthreads();
+    double a = 0.0;
+    float m = 0.0f;
+    for (int k = tid; k < (int)gridDim.x; k += PCG_THREADS) {
+        a += (double)__ldcg(psum + k);
+        if (WITH_MAX) m = fmaxf(m, __ldcg(pmax + k));
+    }
+    a = warp_sum(a);
+    if (WITH_MAX) m = warp_max(m);
+    if (lane == 0) {
+        sc.shd[w] = a;
+        if (WITH_MAX) sc.sh[w] = m;
+    }
+    __syncthreads();
+    double t = 0.0;
+    float mm = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { // every thread adds the warp totals in the same order
+        t += sc.shd[k];
+        if (WITH_MAX) mm = fmaxf(mm, sc.sh[k]);
+    }
+    __syncthreads(); // the scratch is reused by the next reduction
+    tot = t;
+    gmax = mm;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Column solver (default on one GPU): the persistent solver with a work list that follows the fluid.
 //
 // What the in-step profile of the tile kernel showed (profiles/r02_s2_pcg_step110.md, step 110 of the 256^3 dam break, 12.6 % of the
@@ -1031,11 +1102,7 @@ __device__ __forceinline__ TileCtx column_ctx(int i, int sz) {
 }
 
 __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSolveArgs a) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    __shared__ float sh[PCG_THREADS / 32];
-    __shared__ double shd;
-    __shared__ float shf;
+    __shared__ ReduceScratch sc;
     __shared__ double sh_csum[SLAB_MAX_WORLD];
     __shared__ float sh_cmax[SLAB_MAX_WORLD];
     __shared__ int sh_dead;
@@ -1079,8 +1146,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
         load_column_codes(e, c, w);
         init_tile<true>(e, c, w, a.p, a.r, acc);
     }
-    double tot = grid_sum(grid, psumB, acc, sh, &shd);
+    unsigned round = 0;
+    double tot = 0.0;
     float gmax = 0.0f;
+    grid_reduce<false>(a.barrier, round, psumB, pmax, acc, 0.0f, sc, tot, gmax);
     if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
     float sigma = (float)tot;
     float alpha = 0.0f, beta = 0.0f, max_error = 0.0f;
@@ -1101,7 +1170,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
             load_column_codes(e, c, w);
             search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
         }
-        tot = grid_sum(grid, psumA, acc, sh, &shd);
+        grid_reduce<false>(a.barrier, round, psumA, pmax, acc, 0.0f, sc, tot, gmax);
         if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
         alpha = guarded_div(sigma, (float)tot); // RESULTMODE_ALPHA, pressure_reduce.comp:73-75
 
@@ -1119,18 +1188,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
             load_column_codes(e, c, w);
             update_tile<true>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
         }
-        {
-            const float bm = block_max(err, sh);
-            if (linear_tid() == 0) pmax[blockIdx.x] = bm;
-        }
-        tot = grid_sum(grid, psumB, acc, sh, &shd); // the barrier inside also publishes pmax
-        {
-            const float em = final_max(pmax, gridDim.x, sh);
-            if (linear_tid() == 0) shf = em;
-            __syncthreads();
-            gmax = shf;
-            __syncthreads();
-        }
+        grid_reduce<true>(a.barrier, round, psumB, pmax, acc, err, sc, tot, gmax);
         if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
         const float zr = (float)tot;
         if (with_err) {
@@ -1165,9 +1223,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
                 st4(peer_p_hi + i - e.push, ld4(a.p + i));
             }
         }
-        grid.sync();
         double dummy = 0.0;
         float dmax = 0.0f;
+        grid_reduce<false>(a.barrier, round, psumA, pmax, 0.0f, 0.0f, sc, dummy, dmax); // grid barrier: all pushes of this rank are issued
+        dummy = 0.0;
         comm_allreduce(cm_, ++seq, dummy, dmax, sh_csum, sh_cmax, &sh_dead);
         if (blockIdx.x == 0 && linear_tid() == 0) *cm_.seq = seq;
     }
@@ -1473,7 +1532,8 @@ __global__ void __launch_bounds__(PCG_THREADS, 3) pcg_solve_tma_kernel(const __g
     }
 }
 
-__global__ void pcg_reset_scalars_kernel(PcgScalars *scal) {
+__global__ void pcg_reset_scalars_kernel(PcgScalars *scal, unsigned *barrier) {
+    if (barrier) *barrier = 0u;
     scal->alpha = 0.0f; scal->beta = 0.0f; scal->sigma = 0.0f;
     scal->max_error = 0.0f; scal->num_iterations = 0; scal->done = 0; scal->ticket = 0u;
 }
@@ -1616,6 +1676,8 @@ PressureSolver::PressureSolver(const GridDim &grid, void *external_residual) : g
         BLUB_CUDA_CHECK(cudaMalloc(&tile_cols_, sizeof(int) * (2 * (size_t)t.ntiles + 2))); // counts | offsets | total
         BLUB_CUDA_CHECK(cudaMemset(tile_cols_, 0, sizeof(int) * (2 * (size_t)t.ntiles + 2)));
         BLUB_CUDA_CHECK(cudaMalloc(&col_list_, sizeof(int) * max_cols));
+        BLUB_CUDA_CHECK(cudaMalloc(&barrier_, 256));
+        BLUB_CUDA_CHECK(cudaMemset(barrier_, 0, 256));
         int per = 0;
         BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_columns_kernel, PCG_THREADS, 0));
         column_blocks_ = sms * per;
@@ -1631,6 +1693,7 @@ PressureSolver::~PressureSolver() {
     if (tile_list_) cudaFree(tile_list_);
     if (tile_cols_) cudaFree(tile_cols_);
     if (col_list_) cudaFree(col_list_);
+    if (barrier_) cudaFree(barrier_);
     delete static_cast<PcgTmaMaps *>(tma_maps_);
 }
 
@@ -1661,7 +1724,7 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
 
     field.touched = true; // the volume is zero-initialised at allocation (pressure_solver.rs:601-603)
 
-    BLUB_LAUNCH(pcg_reset_scalars_kernel, 1, 1, 0, stream, scal);
+    BLUB_LAUNCH(pcg_reset_scalars_kernel, 1, 1, 0, stream, scal, barrier_);
     int *const scratch_cols = tile_cols_ ? tile_cols_ : num_active_; // (no cooperative launch: the counts are not used)
     BLUB_LAUNCH(pcg_prepare_kernel, grid, block, 0, stream, g, t, marker, codes_.ptr, tile_active_, scratch_cols, p, r, s);
     if (mode != 0) { // the stored preconditioner vectors must obey the zero invariant as well
@@ -1683,7 +1746,7 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
         args.p = p; args.r = r; args.s0 = s; args.s1 = aux_.ptr; args.scal = scal; args.partials = partials_;
         args.params = dparams; args.which = which; args.max_iterations = max_it; args.check_frequency = freq;
         args.comm = comm;
-        args.col_list = col_list_; args.num_cols = num_cols;
+        args.col_list = col_list_; args.num_cols = num_cols; args.barrier = barrier_;
         if (columns) { // dense tiles by the tile body, everything else column by column
             BLUB_LAUNCH(pcg_column_fill_kernel, grid, block, 0, stream, g, t, st, ta, col_offset, ghost_tiles, t.ntiles - ghost_tiles, col_list_);
             int nblocks = column_blocks_;

@@ -587,7 +587,9 @@ __global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepPa
                                                          const float4 *__restrict__ rowz, float2 *__restrict__ nwx, float2 *__restrict__ nwy,
                                                          float2 *__restrict__ nwz, int8_t *__restrict__ marker) {
     const uint32_t i = blockIdx.x * PT + threadIdx.x;
-    const bool valid = i < params->num_particles; // no early return: every lane takes part in the shuffles
+    const uint32_t np = params->num_particles;
+    if ((i & ~31u) >= np) return;  // whole warp beyond the last particle (z-slab ranks launch over their capacity)
+    const bool valid = i < np;     // no per-lane early return: every lane of a live warp takes part in the shuffles
     const float3 p = transfer_position(g, valid ? pos[i] : make_float4(1.5f, 1.5f, 1.5f, 0.0f), 1.0f);
     if (MARK && valid) marker[cell_of_position(g, p)] = (int8_t)CELL_FLUID; // transfer_build_linkedlist.comp:17-19
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -690,7 +692,9 @@ __global__ void __launch_bounds__(PT) p2g_normalize_kernel(GridDim g, int wpr, c
 __global__ void __launch_bounds__(PT) density_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
                                                              float *__restrict__ density) {
     const uint32_t i = blockIdx.x * PT + threadIdx.x;
-    const bool valid = i < params->num_particles;
+    const uint32_t np = params->num_particles;
+    if ((i & ~31u) >= np) return; // whole warp beyond the last particle
+    const bool valid = i < np;
     const float3 p = transfer_position(g, valid ? pos[i] : make_float4(1.5f, 1.5f, 1.5f, 0.0f), 0.5f);
     const int dx = (int)(p.x - 0.5f), dy = (int)(p.y - 0.5f), dz = (int)(p.z - 0.5f);
     const float qx = (float)dx + 0.5f, qy = (float)dy + 0.5f, qz = (float)dz + 0.5f;

@@ -130,6 +130,64 @@ __global__ void __launch_bounds__(THREADS) k_two(float *partials, float *group_p
     if (blockIdx.x == 0 && threadIdx.x == 0) *out = carry;
 }
 
+// thread-block clusters of CS blocks: the cluster's partials meet in block 0's shared memory (DSMEM store + hardware cluster barrier), one
+// arrival per cluster on the global counter, gridDim / CS partials to re-read
+template <int THREADS, int CS>
+__global__ void __launch_bounds__(THREADS) k_cluster(float *cpartials, unsigned *counter, int iters, double *out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float sh[THREADS / 32];
+    __shared__ double shd[THREADS / 32];
+    __shared__ float cl_part[2][CS];
+    const unsigned rank = cluster.block_rank();
+    const int ncl = gridDim.x / CS, cid = blockIdx.x / CS;
+    double carry = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        const float bs = block_sum<THREADS>((float)(threadIdx.x & 3) + (float)carry * 1e-30f, sh);
+        if (threadIdx.x == 0) {
+            float *dst = cluster.map_shared_rank(&cl_part[it & 1][0], 0);
+            dst[rank] = bs;
+        }
+        cluster.sync();
+        if (threadIdx.x == 0) {
+            if (rank == 0) {
+                float g = 0.f;
+#pragma unroll
+                for (int k = 0; k < CS; ++k) g += cl_part[it & 1][k];
+                cpartials[(it & 1) * ncl + cid] = g;
+                red_release(counter, 1u);
+            }
+            const unsigned target = (unsigned)(it + 1) * ncl;
+            while (ld_acquire(counter) < target) {}
+        }
+        __syncthreads();
+        carry = all_sum<THREADS>(cpartials + (it & 1) * ncl, ncl, shd);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out = carry;
+}
+
+template <int CS>
+static bool launch_cluster(int blocks, float *partials, unsigned *counter, int n, double *out) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(256);
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_cluster<256, CS>, partials, counter, n, out);
+    if (e != cudaSuccess) {
+        std::printf("cluster%d: launch failed: %s\n", CS, cudaGetErrorString(e));
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+
 template <class Launch>
 static void time_it(const char *name, int blocks, int threads, int iters, Launch launch) {
     cudaEvent_t e0, e1;
@@ -177,6 +235,39 @@ int main() {
             void *args[] = {&partials, &gpart, &gc, &c, &n, &out};
             CHECK(cudaLaunchCooperativeKernel((const void *)k_two<256, 4>, dim3(blocks), dim3(256), args, 0, 0));
         });
+    }
+    {
+        const int blocks = sms * 4;
+        int ncl = 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks);
+        cfg.blockDim = dim3(256);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 4;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&ncl, k_cluster<256, 4>, &cfg) == cudaSuccess) std::printf("max co-resident clusters of 4 x 256 threads: %d (need %d)\n", ncl, blocks / 4);
+        cudaGetLastError();
+        if (ncl >= blocks / 4) {
+            bool ok = true;
+            time_it("cluster4", blocks, 256, iters, [&](int n) {
+                reset();
+                if (ok) ok = launch_cluster<4>(blocks, partials, counters, n, out);
+            });
+        }
+        attr[0].val.clusterDim.x = 2;
+        if (cudaOccupancyMaxActiveClusters(&ncl, k_cluster<256, 2>, &cfg) == cudaSuccess) std::printf("max co-resident clusters of 2 x 256 threads: %d (need %d)\n", ncl, blocks / 2);
+        cudaGetLastError();
+        if (ncl >= blocks / 2) {
+            bool ok = true;
+            time_it("cluster2", blocks, 256, iters, [&](int n) {
+                reset();
+                if (ok) ok = launch_cluster<2>(blocks, partials, counters, n, out);
+            });
+        }
     }
     {
         const int blocks = sms;
