@@ -59,11 +59,11 @@ fi
 if want sanitize; then
     bash tools/sanitize.sh pcg step 2>&1 | tee $OUT/session_sanitize.txt | tail -40
 fi
-if want ncustep; then       # full captures INSIDE the dam break (eager launches): the sparse PCG solve at step 110, one P2G gather
-    BLUB_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pcg_solve_persistent --launch-skip 220 -c 1 -o $OUT/session_pcg_step110 \
+if want ncustep; then       # full captures INSIDE the dam break (eager launches): the column solver at step 110, the P2G scatter + finish at step 5
+    BLUB_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pcg_solve_columns --launch-skip 220 -c 1 -o $OUT/session_pcg_step110 \
         python tools/profile_targets.py step dam_256 111 > $OUT/session_ncu_pcg_step110.log 2>&1
-    BLUB_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:p2g_gather --launch-skip 15 -c 3 -o $OUT/session_p2g_gather \
-        python tools/profile_targets.py step dam_256 7 > $OUT/session_ncu_p2g.log 2>&1
+    BLUB_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"p2g_scatter|p2g_normalize|marker_finalize|density_scatter|advect_kernel|correct_particles" --launch-skip 30 -c 6 -o $OUT/session_particle_kernels \
+        python tools/profile_targets.py step dam_256 7 > $OUT/session_ncu_particles.log 2>&1
     ls -la $OUT/*.ncu-rep
 fi
 if want bench; then
@@ -76,7 +76,7 @@ if want launches; then      # the launch list of the bench command itself (share
     python tools/summarize_ncu.py launches $OUT/session_launches.csv > $OUT/session_launches.md 2>&1; head -30 $OUT/session_launches.md
 fi
 if want ncu; then           # one full capture of the PCG kernel on the roofline microbench
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:pcg_solve_persistent -c 1 -o $OUT/session_pcg \
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:pcg_solve_columns -c 1 -o $OUT/session_pcg \
         python tools/profile_targets.py pcg 256 1 > $OUT/session_ncu.log 2>&1
     ls -la $OUT/session_pcg.ncu-rep
 fi
