@@ -1090,11 +1090,6 @@ __global__ void __launch_bounds__(1024) pcg_compact_kernel(const uint8_t *__rest
     for (int cb_ = warp_first, ci_ = cb_ + lane < ncols ? a.col_list[cb_ + lane] : -1, cn_ = -1; cb_ < ncols; cb_ += col_stride, ci_ = cn_) \
         if ((cn_ = cb_ + col_stride + lane < ncols ? a.col_list[cb_ + col_stride + lane] : -1), true)                                      \
             if (const TileCtx c = column_ctx(ci_, sz); true)
-// the batches after a warp's first one (which lives in registers, see pcg_solve_columns_kernel)
-#define PCG_FOR_EACH_LATER_COLUMN(c)                                                                                                                              \
-    for (int cb_ = warp_first + col_stride, ci_ = cb_ + lane < ncols ? a.col_list[cb_ + lane] : -1, cn_ = -1; cb_ < ncols; cb_ += col_stride, ci_ = cn_)         \
-        if ((cn_ = cb_ + col_stride + lane < ncols ? a.col_list[cb_ + col_stride + lane] : -1), true)                                                            \
-            if (const TileCtx c = column_ctx(ci_, sz); true)
 __device__ __forceinline__ TileCtx column_ctx(int i, int sz) {
     TileCtx c;
     c.tile = 0;
@@ -1138,12 +1133,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
     __syncthreads();
     if (sharded) slab_start_handshake(cm_, seq, sh_csum, sh_cmax, &sh_dead);
 
-    // The first batch of columns of this warp -- for most warps the only one -- is the same in every phase of the solve, and so are its
-    // code words: both stay in registers, which takes two dependent loads (list entry -> code words) out of every phase.
-    const int col0 = warp_first + lane < ncols ? a.col_list[warp_first + lane] : -1;
-    unsigned w0[PCG_TZ + 2];
-    load_column_codes(e, column_ctx(col0, sz), w0);
-
     // ---- init: r <- b - A p, sigma <- z.r (pressure_init.comp:45-83, pressure_solver.rs:625-649); s stays 0
     float acc = 0.0f;
     PCG_FOR_EACH_TILE(tile) {
@@ -1152,8 +1141,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
         load_column_codes(e, c, w);
         init_tile<false>(e, c, w, a.p, a.r, acc);
     }
-    if (warp_first < ncols) init_tile<true>(e, column_ctx(col0, sz), w0, a.p, a.r, acc);
-    PCG_FOR_EACH_LATER_COLUMN(c) {
+    PCG_FOR_EACH_COLUMN(c) {
         unsigned w[PCG_TZ + 2];
         load_column_codes(e, c, w);
         init_tile<true>(e, c, w, a.p, a.r, acc);
@@ -1177,8 +1165,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
             load_column_codes(e, c, w);
             search_tile<false>(e, c, w, a.r, s_in, s_out, beta, acc);
         }
-        if (warp_first < ncols) search_tile<true>(e, column_ctx(col0, sz), w0, a.r, s_in, s_out, beta, acc);
-        PCG_FOR_EACH_LATER_COLUMN(c) {
+        PCG_FOR_EACH_COLUMN(c) {
             unsigned w[PCG_TZ + 2];
             load_column_codes(e, c, w);
             search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
@@ -1196,8 +1183,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
             load_column_codes(e, c, w);
             update_tile<false>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
         }
-        if (warp_first < ncols) update_tile<true>(e, column_ctx(col0, sz), w0, s_out, a.p, a.r, alpha, acc, err);
-        PCG_FOR_EACH_LATER_COLUMN(c) {
+        PCG_FOR_EACH_COLUMN(c) {
             unsigned w[PCG_TZ + 2];
             load_column_codes(e, c, w);
             update_tile<true>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
@@ -1254,7 +1240,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
     }
 }
 #undef PCG_FOR_EACH_COLUMN
-#undef PCG_FOR_EACH_LATER_COLUMN
 #undef PCG_FOR_EACH_TILE
 
 // ---------------------------------------------------------------------------------------------------------------
