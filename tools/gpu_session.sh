@@ -72,7 +72,7 @@ if want bench; then
 fi
 if want launches; then      # the launch list of the bench command itself (shares only: ncu serialises and runs cold)
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/session_launches.csv \
-        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-roofline --no-scaling-reference > $OUT/session_launches.log 2>&1
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-roofline --no-scaling-reference --no-phases > $OUT/session_launches.log 2>&1
     python tools/summarize_ncu.py launches $OUT/session_launches.csv > $OUT/session_launches.md 2>&1; head -30 $OUT/session_launches.md
 fi
 if want ncu; then           # one full capture of the PCG kernel on the roofline microbench
