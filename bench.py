@@ -374,8 +374,9 @@ def main():
     ap.add_argument("--no-scaling-reference", action="store_true")
     ap.add_argument("--no-phases", action="store_true", help="skip the late-window timing and the in-step stage / roofline analysis (N = 1)")
     ap.add_argument("--late-start", type=int, default=100, help="first step of the late timing window (N = 1)")
-    ap.add_argument("--multi", default="sharded", choices=["sharded", "stacked", "replicas"],
-                    help="N > 1: one z-slab sharded simulation of a z-uniform dam (default, balanced), of N stacked dam_256 cubes, or N independent replicas")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "stacked", "split", "replicas"],
+                    help="N > 1: one z-slab sharded simulation of a z-uniform dam (default: weak scaling, balanced), of N stacked dam_256 cubes, of the workload's "
+                         "OWN grid cut into N slabs (split: strong scaling, e.g. --workload basin_512 = config C4), or N independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 2
@@ -409,7 +410,7 @@ def main():
     has_solid = args.workload in SOLID_WORKLOADS
     if has_solid and world > 1:
         args.multi = "replicas"  # the moving-solid workload is not sharded: N independent replicas
-    sharded_step = world > 1 and args.multi in ("sharded", "stacked")
+    sharded_step = world > 1 and args.multi in ("sharded", "stacked", "split")
     if not sharded_step:
         fluid = blub_b200.HybridFluid.from_scene(scene_path(workload_scene(args.workload)), device=local)
         npart = fluid.num_particles
@@ -421,8 +422,14 @@ def main():
 
         d = sc["fluid"]["grid_dimension"]
         scale = sc["fluid"]["grid_to_world_scale"]
-        cap = int(sc["fluid"]["max_num_particles"] * 2)  # head room: fluid flows between slabs
-        fluid = blub_b200.HybridFluid.create_slab(d["x"], d["y"], d["z"], cap, rank=rank, world=world, device=local)
+        split = args.multi == "split"  # STRONG scaling: the workload's own grid cut into `world` z-slabs (C4 = basin_512 on 8 GPUs; dam_256 literally)
+        if split and (d["z"] % world or (d["z"] // world) % 4):
+            raise SystemExit(f"--multi split: {d['z']} planes cannot be cut into {world} slabs of whole 4-plane tiles")
+        nz_owned = d["z"] // world if split else d["z"]
+        cap = int(sc["fluid"]["max_num_particles"] * 2) // (world if split else 1)  # head room: fluid flows between slabs
+        if split and args.workload == "dam_256":
+            cap = int(sc["fluid"]["max_num_particles"])  # the dam starts inside the first half of the slabs
+        fluid = blub_b200.HybridFluid.create_slab(d["x"], d["y"], nz_owned, cap, rank=rank, world=world, device=local)
         handles = slab.exchange_handles(fluid.ipc_export_window(), dist)
         own = fluid.slab_window()[0]
         fluid.attach_slab_peers([own if k == rank else F.ipc_open(handles[k], local) for k in range(world)])
@@ -432,6 +439,9 @@ def main():
             # dam_256).  `--multi stacked` stacks N copies of the dam_256 cube instead; they drain towards z = 0 and unbalance.
             zmax = float(d["z"] * world)
             fluid.add_fluid_cube([0.0, 0.0, 0.0], [d["x"] / 2.0, d["y"] / 4.0, zmax])
+        elif split:
+            for cube in sc["fluid"]["fluid_cubes"]:  # global coordinates: every rank keeps the particles of its planes
+                fluid.add_fluid_cube([cube["min"][c] / scale for c in "xyz"], [cube["max"][c] / scale for c in "xyz"])
         else:
             for k in range(world):
                 for cube in sc["fluid"]["fluid_cubes"]:
@@ -444,7 +454,9 @@ def main():
         counts = [None] * world
         dist.all_gather_object(counts, fluid.num_particles)
         npart = sum(counts)
-        if args.multi == "sharded":
+        if split:
+            desc = f"{desc}, cut into {world} z-slabs of {nz_owned} planes (strong scaling)"
+        elif args.multi == "sharded":
             desc = f"{world} z-slabs of {d['x']}x{d['y']}x{d['z']} cells = {d['x']}x{d['y']}x{d['z'] * world} grid, z-uniform dam (x < {d['x'] // 2}, y < {d['y'] // 4})"
         else:
             desc = f"{world} x ({desc}) stacked along z = {d['x']}x{d['y']}x{d['z'] * world} grid"
@@ -521,18 +533,24 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample(args.workload, 1)
     if rank == 0:
-        steps_per_s = world * args.steps / (ms_max * 1e-3)
+        split_mode = sharded_step and args.multi == "split"
+        steps_per_s = (1 if split_mode else world) * args.steps / (ms_max * 1e-3)
         line = {
             "metric": METRIC, "value": round(steps_per_s, 3), "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "strong" if split_mode else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": config_block(desc, npart, dt, parallelism, f"steps {max(args.warmup, 3)}..{max(args.warmup, 3) + args.steps - 1} of the scene (see scene_phases for a later window)"),
             "last_solver_stats": {"velocity": stats[0], "density": stats[1]},
             "clocks": clocks,
-            "e2e": {"value": round(world * args.steps / e2e_s, 3), "unit": "steps/s", "h2d_bytes_per_step": 36, "d2h_bytes_per_step": 16,
+            "e2e": {"value": round((1 if split_mode else world) * args.steps / e2e_s, 3), "unit": "steps/s", "h2d_bytes_per_step": 36, "d2h_bytes_per_step": 16,
                     "note": "blub_fluid_step + blub_fluid_synchronize + blub_fluid_update_statistics per step (host-timed); the state stays on the device as in the "
                             "reference (hybrid_fluid.rs:770): per step the host sends the 36-byte parameter block and reads the two 8-byte solver statistics; see result_handoff"},
             "gpu_launches": int(launches),
+            "simulation_steps_per_s": round(args.steps / (ms_max * 1e-3), 3),
+            "value_definition": ("steps/s of the one simulation" if world == 1 or split_mode or not sharded_step else
+                                 f"slab-steps/s = {world} x simulation_steps_per_s: ONE simulation on {world} z-slabs, each slab a 256^3-cell, 16.3 M-particle share "
+                                 "(weak scaling: the whole-job aggregate in units of the N = 1 workload)") if sharded_step or world == 1 else
+                                f"{world} independent replicas x steps/s",
             "slab_error": slab_err,
             "slab_particles": slab_counts,
             "roofline": roof,

@@ -586,8 +586,9 @@ __device__ __forceinline__ void comm_allreduce(const SlabComm &c, unsigned seq, 
         if (!ok) *sh_dead = 1;
         sh_sum[tid] = (double)__uint_as_float((unsigned)v0);
         sh_max[tid] = __uint_as_float((unsigned)v1);
+        __threadfence_system(); // acquire, by the threads that saw the flags (the block follows through the barrier below): orders the
+                                // block's later loads of the ghost planes after the peers' pushes and drops stale L1 lines of this SM
     }
-    __threadfence_system(); // acquire: drop stale L1 lines of the ghost planes the peers just wrote
     __syncthreads();
     double t = 0.0;
     float m = 0.0f;

@@ -557,28 +557,35 @@ __global__ void __launch_bounds__(PT) p2g_crowded_kernel(GridDim g, const uint32
 // One thread per particle.  For component c the particle lies in dual cell d = trunc(pos - off_c), off_c = 0.5 except 1.0 on
 // axis c (transfer_build_linkedlist.comp:21-23), and contributes to the eight faces d + {0,1}^3.  (sum w*value, sum w) of a
 // face are interleaved as one float2.  Runs of adjacent lanes with the same dual cell (cell-sorted particles hit the SAME eight
-// faces) first add their contributions up with shuffles (segmented reduction, log2 steps); only the first lane of a run issues
-// reductions: one 8-byte RED.ADD.F32x2 per (run, face).  Measured against one reduction per (particle, face): P2G 1.92 -> 1.71 ms,
+// faces) first add their contributions up with shuffles (segmented reduction in groups of four lanes); only the first lane of a group issues
+// reductions: one 8-byte RED.ADD.F32x2 per (group, face).  Measured against one reduction per (particle, face): P2G 1.92 -> 1.71 ms,
 // density 0.64 -> 0.57 ms at step 110 of the 256^3 dam break (profiles/r02_s1_tests_and_variant_timelines.md).
+// Runs are cut into groups of at most four lanes: two shuffle steps instead of five.  The full log2(32) reduction was what bound the kernel
+// (ncu: mio_throttle the top stall, 240 shuffles per particle, profiles/r02_s10_particle_kernels.md), while runs are short -- a dual cell
+// holds 8 particles on average and a cell-sorted warp holds them in 2-4 separate runs; a longer run simply issues one reduction per
+// group of four.  Warps in which every lane is its own run (the usual case once the particle order has decayed) skip the shuffles.
 template <int NV>
 __device__ __forceinline__ bool segmented_run_sum(int key, float (&v)[NV]) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int prev = __shfl_up_sync(full, key, 1);
-    const bool head = lane == 0 || prev != key;
-    const unsigned heads = __ballot_sync(full, head);
-    const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u)); // run heads in the lanes above this one
-    const int end = above ? __ffs(above) - 1 : 32;                            // first lane that is not part of this lane's run
+    const bool start = lane == 0 || prev != key;
+    const unsigned starts = __ballot_sync(full, start);
+    if (starts == full) return true;                                            // warp-uniform: nothing to add up
+    const unsigned upto = starts & (lane == 31 ? full : ((2u << lane) - 1u));   // run starts in the lanes up to this one
+    const int pos = lane - (31 - __clz(upto));                                  // position inside the run
+    const unsigned above = lane == 31 ? 0u : (starts & ~((2u << lane) - 1u));   // run starts in the lanes above this one
+    const int end = above ? __ffs(above) - 1 : 32;                              // first lane that is not part of this lane's run
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const bool take = lane + o < end;
+    for (int o = 1; o <= 2; o <<= 1) {
+        const bool take = (pos & 3) + o < 4 && lane + o < end;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const float t = __shfl_down_sync(full, v[k], o);
             if (take) v[k] += t;
         }
     }
-    return head;
+    return (pos & 3) == 0; // the first lane of every group of four issues the reductions
 }
 
 template <bool MARK>

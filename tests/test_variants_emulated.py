@@ -177,25 +177,27 @@ def test_gather_p2g_index_logic_equals_a_direct_scatter():
 
 
 def emulate_segmented_run_sum(keys, v):
-    """segmented_run_sum<NV> of fluid_kernels.cu for one 32-lane warp (NV = 1)."""
+    """segmented_run_sum<NV> of transfer_kernels.cu for one 32-lane warp (NV = 1): runs of equal keys cut into groups of four lanes."""
     lane = np.arange(32)
     v = v.astype(np.float64).copy()
     prev = np.r_[keys[0], keys[:-1]]                      # __shfl_up_sync(key, 1); lane 0 keeps its own
-    head = (lane == 0) | (prev != keys)
-    heads = sum(1 << i for i in range(32) if head[i])     # __ballot_sync
-    end = np.empty(32, int)
+    start = (lane == 0) | (prev != keys)
+    starts = sum(1 << i for i in range(32) if start[i])   # __ballot_sync
+    if starts == 0xFFFFFFFF:
+        return np.ones(32, bool), v
+    pos, end = np.empty(32, int), np.empty(32, int)
     for l in range(32):
-        above = 0 if l == 31 else heads & ~(((2 << l) - 1) & 0xFFFFFFFF) & 0xFFFFFFFF
+        upto = starts & (0xFFFFFFFF if l == 31 else ((2 << l) - 1))
+        pos[l] = l - (upto.bit_length() - 1)              # 31 - __clz(upto)
+        above = 0 if l == 31 else starts & ~(((2 << l) - 1) & 0xFFFFFFFF) & 0xFFFFFFFF
         end[l] = ((above & -above).bit_length() - 1) if above else 32   # __ffs(above) - 1
-    o = 1
-    while o < 32:
+    for o in (1, 2):
         t = np.array([v[l + o] if l + o < 32 else v[l] for l in range(32)])  # __shfl_down_sync: out-of-range lanes read themselves
-        v = np.where(lane + o < end, v + t, v)
-        o <<= 1
-    return head, v
+        v = np.where(((pos & 3) + o < 4) & (lane + o < end), v + t, v)
+    return (pos & 3) == 0, v
 
 
-def test_segmented_run_reduction_sums_every_run_into_its_first_lane():
+def test_segmented_run_reduction_sums_every_group_of_four_into_its_first_lane():
     rng = np.random.default_rng(0)
     for trial in range(500):
         n_runs = int(rng.integers(1, 33))
@@ -211,6 +213,9 @@ def test_segmented_run_reduction_sums_every_run_into_its_first_lane():
             r = l
             while r + 1 < 32 and keys[r + 1] == keys[l]:
                 r += 1
-            assert head[l] and not head[l + 1:r + 1].any()
-            assert abs(out[l] - v[l:r + 1].sum()) < 1e-12
+            for g in range(l, r + 1, 4):  # groups of four inside the run [l, r]
+                ge = min(g + 3, r)
+                assert head[g] and not head[g + 1:ge + 1].any()
+                assert abs(out[g] - v[g:ge + 1].sum()) < 1e-12
             l = r + 1
+        assert abs(out[head].sum() - v.sum()) < 1e-9  # every contribution is issued exactly once

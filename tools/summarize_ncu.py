@@ -12,10 +12,10 @@ import sys
 
 METRICS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-    "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
-    "smsp__inst_executed.sum", "smsp__cycles_active.avg", "sm__inst_executed_pipe_lsu.sum", "launch__occupancy_limit_registers",
-    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+    "launch__grid_size", "launch__block_size", "inst_executed", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__occupancy_limit_registers", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
 ]
 
 
@@ -57,6 +57,12 @@ def report(path):
         for m in METRICS:
             if m in idx:
                 print(f"| {m} | {r[idx[m]]} | {units[idx[m]]} |")
+        stalls = []
+        for h, i in idx.items():
+            if "issue_stalled" in h and "per_issue_active" in h and r[i] not in ("0", "n/a", ""):
+                stalls.append((h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), float(r[i].replace(",", ""))))
+        stalls.sort(key=lambda kv: -kv[1])
+        print("\nwarp stall reasons (warps per issue-active cycle): " + ", ".join(f"{a} {b:.2f}" for a, b in stalls[:7]))
         print()
 
 
