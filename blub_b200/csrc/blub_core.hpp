@@ -210,6 +210,8 @@ class HybridFluid {
     void upload_step_params(float dt);
     void run_stage(int stage, float dt);
     void refresh_fluid_bits();
+    bool binning_step() const;
+    uint32_t internal_resort_every_ = 8; // see binning_step(); single GPU and z-slab ranks alike
     void destroy_graphs();
 
     // ---- z-slab sharding of the whole step (slab.cu) ----

@@ -131,6 +131,7 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
     BLUB_CUDA_CHECK(cudaMallocHost(&params_host_, sizeof(StepParams) * 64));
     for (int k = 0; k < 64; ++k) BLUB_CUDA_CHECK(cudaEventCreateWithFlags(&param_events_[k], cudaEventDisableTiming));
     BLUB_CUDA_CHECK(cudaDeviceSynchronize());
+    if (const char *rs = std::getenv("BLUB_RESORT_EVERY")) internal_resort_every_ = (uint32_t)std::atoi(rs);
     const char *ng = std::getenv("BLUB_NO_GRAPH");
     if (ng && ng[0] == '1') use_graph = false;
 }
@@ -387,6 +388,17 @@ void HybridFluid::upload_step_params(float dt) {
     BLUB_CUDA_CHECK(cudaEventRecord(param_events_[slot], stream_));
 }
 
+// Particle binning (hybrid_fluid.rs:854-894): every `particle_rebinning_step_frequency`-th step including step 0, 0 = never -- and, because
+// a re-sort costs 0.5 ms here (positions only, deterministic) while a decayed particle order costs the scatters and the G2P kernels 0.5 ms
+// EVERY step (profiles/r02_s11_rebin_cadence.md), additionally every `internal_resort_every_`-th step (8; BLUB_RESORT_EVERY=0 turns that off).
+// Binning only permutes the particle arrays: with it or without it a step computes the same sums in a different order.
+bool HybridFluid::binning_step() const {
+    const uint32_t rebin = dynamic_settings_.particle_rebinning_step_frequency;
+    if (rebin == 0) return false;
+    if (step_counter_ % rebin == 0) return true;
+    return internal_resort_every_ != 0 && internal_resort_every_ < rebin && step_counter_ % internal_resort_every_ == 0;
+}
+
 // The extrapolation works on the FLUID bit mask, which every marker-finishing pass of a step rebuilds.  A marker volume written
 // from outside (test taps) makes it stale: rebuild it from the marker volume as it is.
 void HybridFluid::refresh_fluid_bits() {
@@ -442,7 +454,7 @@ void HybridFluid::run_stage(int stage, float dt) {
         if (!capturing_) field_velocity_->enqueue_error_buffer_read(stream_, dt); // the scalars live until this field's next solve
         break;
     case 3: // particle binning every n-th step, including step 0 (:854-894)
-        if (dynamic_settings_.particle_rebinning_step_frequency != 0 && step_counter_ % dynamic_settings_.particle_rebinning_step_frequency == 0) {
+        if (binning_step()) {
             launch_binning(stream_, grid_, params_dev_, np, pos_[cur_], pos_[1 - cur_], lists_);
             if (np > 0) cur_ = 1 - cur_; // ping-pong instead of the reference's full-buffer copy-back (:884-892)
         }
@@ -535,8 +547,7 @@ void HybridFluid::step(double simulation_delta_seconds) {
         destroy_graphs();
         graph_signature_ = sig;
     }
-    const uint32_t rebin = dynamic_settings_.particle_rebinning_step_frequency;
-    const bool binning = rebin != 0 && step_counter_ % rebin == 0 && num_particles_ > 0;
+    const bool binning = binning_step() && num_particles_ > 0;
     // Host-side buffer roles that a captured step bakes in (and changes): the graph is keyed by them.
     struct Roles {
         int cur, row_parity;

@@ -94,6 +94,8 @@ elif mode == "stages":
     scene = sys.argv[2] if len(sys.argv) > 2 else "dam_256"
     checkpoints = [int(a) for a in sys.argv[3:]] or [3]
     f = blub_b200.HybridFluid.from_scene(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".json"))
+    if os.environ.get("BLUB_REBIN"):  # experiment: the reference's particle_rebinning_step_frequency (default 60)
+        f.set_rebin_frequency(int(os.environ["BLUB_REBIN"]))
     STAGES = F.STAGES
     done, cols, reps = 0, [], 3
     for cp in checkpoints:
