@@ -232,7 +232,8 @@ class HybridFluid {
     uint32_t seeded_global_ = 0;
     float4 *row_alt_[3] = {nullptr, nullptr, nullptr}; // spare velocity rows: migration compacts out of place
     unsigned int *mig_counters_ = nullptr;
-    int *slab_error_ = nullptr;
+    int *slab_error_ = nullptr;      // device alias of slab_error_host_
+    int *slab_error_host_ = nullptr; // mapped pinned flag: 0 fine, 1 peer timed out, 2 particle capacity exceeded, 3 migration buffer overflow
     void *slab_peer_window_[2] = {nullptr, nullptr};
     uint32_t slab_exchange_index_ = 0;
 

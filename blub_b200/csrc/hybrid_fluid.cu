@@ -120,8 +120,11 @@ HybridFluid::HybridFluid(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t max_num
         }
         BLUB_CUDA_CHECK(cudaMalloc(&mig_counters_, 4 * sizeof(unsigned int)));
         BLUB_CUDA_CHECK(cudaMemset(mig_counters_, 0, 4 * sizeof(unsigned int)));
-        BLUB_CUDA_CHECK(cudaMalloc(&slab_error_, sizeof(int)));
-        BLUB_CUDA_CHECK(cudaMemset(slab_error_, 0, sizeof(int)));
+        // the error flag lives in mapped pinned host memory: the kernels store to it through the device alias, blub_fluid_step polls the host
+        // side without blocking (a dead peer must not let the caller go on stepping on halos that never arrived)
+        BLUB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&slab_error_host_), sizeof(int), cudaHostAllocMapped));
+        *slab_error_host_ = 0;
+        BLUB_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&slab_error_), slab_error_host_, 0));
     } else {
         solver_.reset(new PressureSolver(grid_));
         field_velocity_.reset(new PressureField(grid_, cfg));
@@ -174,7 +177,7 @@ HybridFluid::~HybridFluid() {
     if (window_) cudaFree(window_);
     for (int k = 0; k < 3; ++k) cudaFree(row_alt_[k]);
     cudaFree(mig_counters_);
-    cudaFree(slab_error_);
+    if (slab_error_host_) cudaFreeHost(slab_error_host_);
     cudaFree(params_dev_);
     cudaFreeHost(params_host_);
     for (int k = 0; k < 64; ++k) cudaEventDestroy(param_events_[k]);
@@ -309,12 +312,10 @@ uint32_t HybridFluid::num_particles() const {
 }
 
 int HybridFluid::slab_error() {
-    if (!slab_error_) return 0;
-    int e = 0;
+    if (!slab_error_host_) return 0;
     BLUB_CUDA_CHECK(cudaSetDevice(device_));
-    BLUB_CUDA_CHECK(cudaMemcpyAsync(&e, slab_error_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
     BLUB_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    return e;
+    return *static_cast<volatile int *>(slab_error_host_);
 }
 
 void HybridFluid::set_particles(uint32_t count, const float *pos4, const float *vx4, const float *vy4, const float *vz4) {
@@ -528,6 +529,9 @@ void HybridFluid::run_stage(int stage, float dt) {
 void HybridFluid::step(double simulation_delta_seconds) {
     BLUB_CUDA_CHECK(cudaSetDevice(device_));
     const NvtxScope scope("HybridFluid step");
+    if (slab_error_host_ && *static_cast<volatile int *>(slab_error_host_) != 0) // non-blocking: whatever the finished steps have reported so far
+        throw CudaError("z-slab exchange failed in an earlier step (1 = a peer timed out, 2 = particle capacity exceeded, 3 = migration buffer overflow): code " +
+                        std::to_string(*static_cast<volatile int *>(slab_error_host_)));
     const float dt = (float)simulation_delta_seconds; // Duration::as_secs_f32
     if (!(dt > 0.0f)) throw std::invalid_argument("simulation delta must be positive");
     field_velocity_->retrieve_new_error_samples(); // pressure_solver.rs:614

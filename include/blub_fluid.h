@@ -229,7 +229,9 @@ int blub_fluid_attach_slab_peers(BlubFluid *fluid, void *const *windows, int wor
  * marker and velocity halos, and particle migration across the slab faces travel as stream-ordered peer copies and P2P
  * stores (blub_b200/csrc/slab.cu).  blub_fluid_add_cube then takes GLOBAL grid coordinates and every rank keeps its part
  * of the same particle stream; particle taps are in local coordinates (global z = local z - 4 + rank * nz_owned).
- * Returns 0, or 1 = a peer timed out, 2 = particle capacity exceeded, 3 = migration buffer overflow (synchronises). */
+ * Returns 0, or 1 = a peer timed out, 2 = particle capacity exceeded, 3 = migration buffer overflow (synchronises).
+ * The flag is also polled WITHOUT blocking at the start of every blub_fluid_step: once a finished step has reported a failure, the next
+ * blub_fluid_step returns BLUB_ERR_CUDA instead of stepping on halos that never arrived. */
 int blub_fluid_slab_error(BlubFluid *fluid);
 int blub_ipc_export(const void *device_ptr, unsigned char handle[64]);
 int blub_ipc_open(const unsigned char handle[64], int device, void **out);

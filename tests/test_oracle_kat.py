@@ -199,3 +199,42 @@ def test_oracle_pcg_iterates_match_float64_cg(shape, iters):
         g.grid(O.ARR_RESIDUAL)[:] = b
         g.solve(0, DT)
         assert np.abs(g.grid(O.ARR_P_VEL) - want).max() > 5e-2 * np.abs(want).max()  # the quirk is real and large
+
+
+def test_list_caps_only_matter_in_crowded_cells():
+    """the reference reads at most 12 (P2G) / 32 (density) entries of a dual cell's particle list
+    (transfer_gather_velocity.comp:61, density_projection_gather_error.comp:69).  The CUDA path and the oracle's default sum EVERYTHING; this
+    records what the caps do: nothing at all at rest density (8 particles per cell: a P2G dual cell holds 8, a density dual cell 8), and a
+    visible deviation as soon as cells are crowded (here 27 per cell) -- which happens for dozens of steps in the 256^3 dam break
+    (DESIGN.md B18).  Parity of this repository is stated against the uncapped sums."""
+    n = 32
+    rng = np.random.default_rng(3)
+
+    def fields(per_axis, cap_p2g, cap_density):
+        f = O.OracleFluid(n, n, n, 40000)
+        c = np.arange(8, 18)
+        off = (np.arange(per_axis) + 0.5) / per_axis
+        ax = (c[:, None] + off[None, :]).ravel()
+        z, y, x = np.meshgrid(ax, ax, ax, indexing="ij")
+        pos = np.stack([x.ravel(), y.ravel(), z.ravel(), np.zeros(x.size)], axis=1).astype(np.float32)
+        rows = [np.random.default_rng(7 + k).normal(0, 2.0, pos.shape).astype(np.float32) for k in range(3)]
+        f.set_particles(pos, *rows)
+        f.set_quirks(precond_mode=0, cap_p2g=cap_p2g, cap_density=cap_density)
+        f.set_gravity_grid([0.0, -981.0, 0.0])
+        f.step_stages(DT, 0, 1)
+        u = [f.grid(a).copy() for a in (O.ARR_UX, O.ARR_UY, O.ARR_UZ)]
+        f.step_stages(DT, 8, 10)
+        return u, f.grid(O.ARR_RESIDUAL).copy(), f.grid(O.ARR_MARKER).copy()
+
+    u_free, rhs_free, m = fields(2, 0, 0)   # 8 particles per cell
+    u_cap, rhs_cap, _ = fields(2, 12, 32)
+    for c in range(3):
+        assert np.array_equal(u_free[c], u_cap[c])
+    assert np.array_equal(rhs_free, rhs_cap)
+    u_free, rhs_free, m = fields(3, 0, 0)   # 27 particles per cell
+    u_cap, rhs_cap, _ = fields(3, 12, 32)
+    dev_u = max(np.abs(u_free[c] - u_cap[c]).max() for c in range(3))
+    assert dev_u > 0.1, dev_u               # the first 12 of 27 list entries give a different weighted mean
+    fl = m == O.FLUID
+    assert np.abs(rhs_free[fl] - rhs_cap[fl]).max() > 1e-3 or np.abs(rhs_free[fl]).max() == np.abs(rhs_cap[fl]).max()  # (both clamp at +-0.5 / dt)
+    del rng
