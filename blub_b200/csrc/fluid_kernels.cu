@@ -295,12 +295,11 @@ __device__ __forceinline__ void trilerp3(const Corners &c, const float ix[3], co
 // into the spare arrays, particles that left the slab go straight to the neighbour (see MigrateOut) -- so that migration
 // costs one warp-aggregated atomic per warp instead of an extra pass over all particles.
 template <bool MIGRATE>
-__global__ void __launch_bounds__(PT) advect_kernel(GridDim g, const StepParams *__restrict__ params, float4 *__restrict__ pos,
+__device__ __forceinline__ void advect_kernel_one(uint32_t i, GridDim g, const StepParams *__restrict__ params, float4 *__restrict__ pos,
                                                     float4 *__restrict__ rowx, float4 *__restrict__ rowy, float4 *__restrict__ rowz,
                                                     const float *__restrict__ ux, const float *__restrict__ uy,
                                                     const float *__restrict__ uz, const uint2 *__restrict__ vox,
                                                     int8_t *__restrict__ marker, MigrateOut mig) {
-    const uint32_t i = blockIdx.x * PT + threadIdx.x;
     if (i >= params->num_particles) return;
     const float dt = params->dt;
     const float4 p4 = pos[i];
@@ -447,14 +446,23 @@ __global__ void __launch_bounds__(PT) advect_kernel(GridDim g, const StepParams 
         mig.counters[3] = 1u; // cannot happen with a CFL-limited flow; never overrun the neighbour's buffer
     }
 }
+template <bool MIGRATE>
+__global__ void __launch_bounds__(PT) advect_kernel(GridDim g, const StepParams *__restrict__ params, float4 *__restrict__ pos,
+                                                    float4 *__restrict__ rowx, float4 *__restrict__ rowy, float4 *__restrict__ rowz,
+                                                    const float *__restrict__ ux, const float *__restrict__ uy,
+                                                    const float *__restrict__ uz, const uint2 *__restrict__ vox,
+                                                    int8_t *__restrict__ marker, MigrateOut mig) {
+    // a bounded grid strides over the particles: launch cost does not grow with the CAPACITY a z-slab rank sizes its launches by
+    const uint32_t np_ = params->num_particles;
+    for (uint32_t i = blockIdx.x * PT + threadIdx.x; (i & ~31u) < np_; i += gridDim.x * PT) advect_kernel_one<MIGRATE>(i, g, params, pos, rowx, rowy, rowz, ux, uy, uz, vox, marker, mig);
+}
 
 // ------------------------------------------------------------------------------------------------ density projection
 // density_projection_correct_particles.comp:25-73 (fp32 software trilinear instead of the 8-bit hardware filter)
-__global__ void __launch_bounds__(PT) correct_particles_kernel(GridDim g, const StepParams *__restrict__ params,
+__device__ __forceinline__ void correct_particles_kernel_one(uint32_t i, GridDim g, const StepParams *__restrict__ params,
                                                                float4 *__restrict__ pos, const int8_t *__restrict__ marker,
                                                                const float *__restrict__ ux, const float *__restrict__ uy,
                                                                const float *__restrict__ uz) {
-    const uint32_t i = blockIdx.x * PT + threadIdx.x;
     if (i >= params->num_particles) return;
     const float4 p4 = pos[i];
     const float x0[3] = {p4.x, p4.y, p4.z};
@@ -487,8 +495,18 @@ __global__ void __launch_bounds__(PT) correct_particles_kernel(GridDim g, const 
     x1[2] = fminf(fmaxf(x1[2], g.z_keep_lo), g.z_keep_hi); // slab ranks only (no-op on one GPU)
     pos[i] = make_float4(x1[0], x1[1], x1[2], p4.w);
 }
+__global__ void __launch_bounds__(PT) correct_particles_kernel(GridDim g, const StepParams *__restrict__ params,
+                                                               float4 *__restrict__ pos, const int8_t *__restrict__ marker,
+                                                               const float *__restrict__ ux, const float *__restrict__ uy,
+                                                               const float *__restrict__ uz) {
+    // a bounded grid strides over the particles: launch cost does not grow with the CAPACITY a z-slab rank sizes its launches by
+    const uint32_t np_ = params->num_particles;
+    for (uint32_t i = blockIdx.x * PT + threadIdx.x; (i & ~31u) < np_; i += gridDim.x * PT) correct_particles_kernel_one(i, g, params, pos, marker, ux, uy, uz);
+}
 
 inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 1) / per_block); }
+// particle kernels: one thread per particle up to 16 blocks per SM, a grid-stride loop beyond (see the kernels)
+inline int particle_blocks(uint32_t np_upper) { return min(blocks_for(np_upper, PT), 148 * 16); }
 
 } // namespace
 
@@ -514,13 +532,13 @@ void launch_clear_marker(cudaStream_t st, const GridDim &g, int8_t *marker) {
 void launch_advect(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos, float4 *const row[3],
                    float *const u[3], const uint2 *vox, int8_t *marker) {
     if (np_upper == 0) return;
-    BLUB_LAUNCH(advect_kernel<false>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2], vox, marker, MigrateOut{});
+    BLUB_LAUNCH(advect_kernel<false>, particle_blocks(np_upper), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2], vox, marker, MigrateOut{});
 }
 
 void launch_advect_migrate(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos, float4 *const row[3],
                            float *const u[3], const uint2 *vox, int8_t *marker, const MigrateOut &mig) {
     if (np_upper == 0) return;
-    BLUB_LAUNCH(advect_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2], vox, marker, mig);
+    BLUB_LAUNCH(advect_kernel<true>, particle_blocks(np_upper), PT, 0, st, g, params, pos, row[0], row[1], row[2], u[0], u[1], u[2], vox, marker, mig);
 }
 
 void launch_position_change(cudaStream_t st, const GridDim &g, const FluidBits &bits, const StepParams *params, const int8_t *marker, const float *p, float *const u[3]) {
@@ -530,7 +548,7 @@ void launch_position_change(cudaStream_t st, const GridDim &g, const FluidBits &
 void launch_correct_particles(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, float4 *pos,
                               const int8_t *marker, float *const u[3]) {
     if (np_upper == 0) return;
-    BLUB_LAUNCH(correct_particles_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, marker, u[0], u[1], u[2]);
+    BLUB_LAUNCH(correct_particles_kernel, particle_blocks(np_upper), PT, 0, st, g, params, pos, marker, u[0], u[1], u[2]);
 }
 
 } // namespace blub

@@ -33,6 +33,8 @@ constexpr int PT = 256; // threads per block for particle and cell kernels
 
 __device__ __forceinline__ int lin(const GridDim &g, int x, int y, int z) { return (z * g.ny + y) * g.nx + x; }
 inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 1) / per_block); }
+// particle kernels: one thread per particle up to 16 blocks per SM, a grid-stride loop beyond (see the kernels)
+inline int particle_blocks(uint32_t np_upper) { return min(blocks_for(np_upper, PT), 148 * 16); }
 
 // The position a transfer sees: clamped so that every face / cell a particle touches exists (a simulated particle is always
 // inside [1.001, dim - 1.001], so this only ever changes particles handed in from outside the domain).  lo = 1.0 for the
@@ -46,12 +48,17 @@ __device__ __forceinline__ int cell_of_position(const GridDim &g, const float3 &
 
 // ------------------------------------------------------------------------------------------------ cell lists
 // count: cell_count[cell] += 1; the returned value is the particle's (arbitrary) slot inside the cell
-__global__ void __launch_bounds__(PT) cell_count_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos, float lo,
+__device__ __forceinline__ void cell_count_kernel_one(uint32_t i, GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos, float lo,
                                                         uint32_t *__restrict__ cell_count, uint2 *__restrict__ cell_slot) {
-    const uint32_t i = blockIdx.x * PT + threadIdx.x;
     if (i >= params->num_particles) return;
     const int cell = cell_of_position(g, transfer_position(g, pos[i], lo));
     cell_slot[i] = make_uint2((uint32_t)cell, atomicAdd(cell_count + cell, 1u));
+}
+__global__ void __launch_bounds__(PT) cell_count_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos, float lo,
+                                                        uint32_t *__restrict__ cell_count, uint2 *__restrict__ cell_slot) {
+    // a bounded grid strides over the particles: launch cost does not grow with the CAPACITY a z-slab rank sizes its launches by
+    const uint32_t np_ = params->num_particles;
+    for (uint32_t i = blockIdx.x * PT + threadIdx.x; (i & ~31u) < np_; i += gridDim.x * PT) cell_count_kernel_one(i, g, params, pos, lo, cell_count, cell_slot);
 }
 
 constexpr int SCAN_THREADS = 256;
@@ -155,12 +162,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t *__re
 }
 
 // fill: arrival[cell_start[cell] + slot] = particle index (the slot is whatever the count atomic returned: arbitrary inside a cell)
-__global__ void __launch_bounds__(PT) cell_fill_kernel(const StepParams *__restrict__ params, const uint2 *__restrict__ cell_slot,
+__device__ __forceinline__ void cell_fill_kernel_one(uint32_t i, const StepParams *__restrict__ params, const uint2 *__restrict__ cell_slot,
                                                        const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ arrival) {
-    const uint32_t i = blockIdx.x * PT + threadIdx.x;
     if (i >= params->num_particles) return;
     const uint2 cs = cell_slot[i];
     arrival[cell_start[cs.x] + cs.y] = i;
+}
+__global__ void __launch_bounds__(PT) cell_fill_kernel(const StepParams *__restrict__ params, const uint2 *__restrict__ cell_slot,
+                                                       const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ arrival) {
+    // a bounded grid strides over the particles: launch cost does not grow with the CAPACITY a z-slab rank sizes its launches by
+    const uint32_t np_ = params->num_particles;
+    for (uint32_t i = blockIdx.x * PT + threadIdx.x; (i & ~31u) < np_; i += gridDim.x * PT) cell_fill_kernel_one(i, params, cell_slot, cell_start, arrival);
 }
 
 // canonicalise: ascending particle index inside every cell, by rank counting -- entry j of cell c goes to position
@@ -172,10 +184,9 @@ __global__ void __launch_bounds__(PT) cell_fill_kernel(const StepParams *__restr
 // integer arithmetic (p2g_crowded_kernel), which is order independent, so the result stays deterministic without an O(k^2) rank count
 // and without one thread walking thousands of particles.
 constexpr uint32_t CROWD_T = 32;
-__global__ void __launch_bounds__(PT) cell_canonicalize_kernel(const StepParams *__restrict__ params, const uint2 *__restrict__ cell_slot,
+__device__ __forceinline__ void cell_canonicalize_kernel_one(uint32_t j, const StepParams *__restrict__ params, const uint2 *__restrict__ cell_slot,
                                                                const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ arrival,
                                                                uint32_t *__restrict__ order, CrowdedCells crowd) {
-    const uint32_t j = blockIdx.x * PT + threadIdx.x;
     if (j >= params->num_particles) return;
     const uint32_t v = arrival[j];
     const uint32_t cell = cell_slot[v].x;
@@ -190,6 +201,13 @@ __global__ void __launch_bounds__(PT) cell_canonicalize_kernel(const StepParams 
         crowd.slot_of_cell[cell] = slot;
     }
     order[s + rank] = v;
+}
+__global__ void __launch_bounds__(PT) cell_canonicalize_kernel(const StepParams *__restrict__ params, const uint2 *__restrict__ cell_slot,
+                                                               const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ arrival,
+                                                               uint32_t *__restrict__ order, CrowdedCells crowd) {
+    // a bounded grid strides over the particles: launch cost does not grow with the CAPACITY a z-slab rank sizes its launches by
+    const uint32_t np_ = params->num_particles;
+    for (uint32_t j = blockIdx.x * PT + threadIdx.x; (j & ~31u) < np_; j += gridDim.x * PT) cell_canonicalize_kernel_one(j, params, cell_slot, cell_start, arrival, order, crowd);
 }
 
 // Which cells of a 32-cell word the boundary rule makes SOLID: border cells and solid voxels (transfer_set_boundary_marker.comp:11-20)
@@ -589,11 +607,10 @@ __device__ __forceinline__ bool segmented_run_sum(int key, float (&v)[NV]) {
 }
 
 template <bool MARK>
-__global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
+__device__ __forceinline__ void p2g_scatter_kernel_one(uint32_t i, GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
                                                          const float4 *__restrict__ rowx, const float4 *__restrict__ rowy,
                                                          const float4 *__restrict__ rowz, float2 *__restrict__ nwx, float2 *__restrict__ nwy,
                                                          float2 *__restrict__ nwz, int8_t *__restrict__ marker) {
-    const uint32_t i = blockIdx.x * PT + threadIdx.x;
     const uint32_t np = params->num_particles;
     if ((i & ~31u) >= np) return;  // whole warp beyond the last particle (z-slab ranks launch over their capacity)
     const bool valid = i < np;     // no per-lane early return: every lane of a live warp takes part in the shuffles
@@ -629,6 +646,15 @@ __global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepPa
                 if (acc[2 * k + 1] > 0.0f) atomicAdd(nw[c] + base + (k & 1) + ((k >> 1) & 1) * g.sy + (k >> 2) * g.sz, make_float2(acc[2 * k], acc[2 * k + 1]));
         }
     }
+}
+template <bool MARK>
+__global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
+                                                         const float4 *__restrict__ rowx, const float4 *__restrict__ rowy,
+                                                         const float4 *__restrict__ rowz, float2 *__restrict__ nwx, float2 *__restrict__ nwy,
+                                                         float2 *__restrict__ nwz, int8_t *__restrict__ marker) {
+    // a bounded grid strides over the particles: launch cost does not grow with the CAPACITY a z-slab rank sizes its launches by
+    const uint32_t np_ = params->num_particles;
+    for (uint32_t i = blockIdx.x * PT + threadIdx.x; (i & ~31u) < np_; i += gridDim.x * PT) p2g_scatter_kernel_one<MARK>(i, g, params, pos, rowx, rowy, rowz, nwx, nwy, nwz, marker);
 }
 
 // Normalisation + global forces + "don't flow into solid" for the scatter form: transfer_gather_velocity.comp:116-127 -- and the
@@ -696,9 +722,8 @@ __global__ void __launch_bounds__(PT) p2g_normalize_kernel(GridDim g, int wpr, c
 // ------------------------------------------------------------------------------------------------ density projection
 // Scatter counterpart of density_projection_gather_error.comp:41-97: dual cell d = trunc(pos - 0.5), cell centres d + {0,1}^3;
 // warp-aggregated like the P2G scatter.
-__global__ void __launch_bounds__(PT) density_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
+__device__ __forceinline__ void density_scatter_kernel_one(uint32_t i, GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
                                                              float *__restrict__ density) {
-    const uint32_t i = blockIdx.x * PT + threadIdx.x;
     const uint32_t np = params->num_particles;
     if ((i & ~31u) >= np) return; // whole warp beyond the last particle
     const bool valid = i < np;
@@ -718,6 +743,12 @@ __global__ void __launch_bounds__(PT) density_scatter_kernel(GridDim g, const St
         for (int k = 0; k < 8; ++k)
             if (acc[k] > 0.0f) atomicAdd(density + base + (k & 1) + ((k >> 1) & 1) * g.sy + (k >> 2) * g.sz, acc[k]);
     }
+}
+__global__ void __launch_bounds__(PT) density_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
+                                                             float *__restrict__ density) {
+    // a bounded grid strides over the particles: launch cost does not grow with the CAPACITY a z-slab rank sizes its launches by
+    const uint32_t np_ = params->num_particles;
+    for (uint32_t i = blockIdx.x * PT + threadIdx.x; (i & ~31u) < np_; i += gridDim.x * PT) density_scatter_kernel_one(i, g, params, pos, density);
 }
 
 // density_projection_gather_error.comp:99-199
@@ -746,12 +777,17 @@ __global__ void __launch_bounds__(PT) density_rhs_kernel(GridDim g, const StepPa
 // particle_binning_rewrite_particles.comp: the cell lists ARE the sorted order -- dst[j] = src[order[j]] (x-fastest cell order,
 // ascending previous index inside a cell: deterministic; the reference's atomic ranks are not, and its inclusive - index
 // addressing loses a particle).
-__global__ void __launch_bounds__(PT) binning_permute_kernel(const StepParams *__restrict__ params, const uint32_t *__restrict__ order,
+__device__ __forceinline__ void binning_permute_kernel_one(uint32_t j, const StepParams *__restrict__ params, const uint32_t *__restrict__ order,
                                                              const float4 *__restrict__ src, float4 *__restrict__ dst) {
-    const uint32_t j = blockIdx.x * PT + threadIdx.x;
     if (j >= params->num_particles) return;
     const float4 p = src[order[j]];
     dst[j] = make_float4(p.x, p.y, p.z, 0.0f);
+}
+__global__ void __launch_bounds__(PT) binning_permute_kernel(const StepParams *__restrict__ params, const uint32_t *__restrict__ order,
+                                                             const float4 *__restrict__ src, float4 *__restrict__ dst) {
+    // a bounded grid strides over the particles: launch cost does not grow with the CAPACITY a z-slab rank sizes its launches by
+    const uint32_t np_ = params->num_particles;
+    for (uint32_t j = blockIdx.x * PT + threadIdx.x; (j & ~31u) < np_; j += gridDim.x * PT) binning_permute_kernel_one(j, params, order, src, dst);
 }
 
 } // namespace
@@ -763,14 +799,14 @@ void launch_cell_lists(cudaStream_t st, const GridDim &g, const StepParams *para
     const int64_t n1 = g.n + 1; // cell_start[n] = number of particles
     const int nb = binning_scan_blocks(g);
     BLUB_CUDA_CHECK(cudaMemsetAsync(l.cell_start, 0, (size_t)n1 * sizeof(uint32_t), st));
-    if (np_upper > 0) BLUB_LAUNCH(cell_count_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, clamp_lo, l.cell_start, l.cell_slot);
+    if (np_upper > 0) BLUB_LAUNCH(cell_count_kernel, particle_blocks(np_upper), PT, 0, st, g, params, pos, clamp_lo, l.cell_start, l.cell_slot);
     BLUB_LAUNCH(scan_block_sums_kernel, nb, SCAN_THREADS, 0, st, l.cell_start, n1, l.block_sums);
     BLUB_LAUNCH(scan_sums_kernel, 1, 1024, 0, st, l.block_sums, nb);
     BLUB_LAUNCH(scan_apply_kernel, nb, SCAN_THREADS, 0, st, l.cell_start, n1, l.block_sums);
     if (np_upper == 0) return;
-    BLUB_LAUNCH(cell_fill_kernel, blocks_for(np_upper, PT), PT, 0, st, params, l.cell_slot, l.cell_start, l.arrival);
+    BLUB_LAUNCH(cell_fill_kernel, particle_blocks(np_upper), PT, 0, st, params, l.cell_slot, l.cell_start, l.arrival);
     BLUB_CUDA_CHECK(cudaMemsetAsync(l.crowd.count, 0, sizeof(uint32_t), st));
-    BLUB_LAUNCH(cell_canonicalize_kernel, blocks_for(np_upper, PT), PT, 0, st, params, l.cell_slot, l.cell_start, l.arrival, l.order, l.crowd);
+    BLUB_LAUNCH(cell_canonicalize_kernel, particle_blocks(np_upper), PT, 0, st, params, l.cell_slot, l.cell_start, l.arrival, l.order, l.crowd);
 }
 
 void launch_marker_from_lists(cudaStream_t st, const GridDim &g, const CellLists &l, int8_t *marker, const uint2 *vox, const FluidBits &bits) {
@@ -817,7 +853,7 @@ void launch_p2g_scatter(cudaStream_t st, const GridDim &g, const StepParams *par
     if (clear_accumulators)
         for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(nw[c], 0, (size_t)g.n * sizeof(float2), st));
     if (np_upper == 0) return;
-    BLUB_LAUNCH(p2g_scatter_kernel<true>, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
+    BLUB_LAUNCH(p2g_scatter_kernel<true>, particle_blocks(np_upper), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
 }
 
 void launch_p2g_finish(cudaStream_t st, const GridDim &g, const StepParams *params, float *const u[3], float2 *const nw[3], int8_t *marker,
@@ -830,7 +866,7 @@ void launch_p2g_finish(cudaStream_t st, const GridDim &g, const StepParams *para
 void launch_density_scatter(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float *density) {
     BLUB_CUDA_CHECK(cudaMemsetAsync(density, 0, (size_t)g.n * sizeof(float), st));
     if (np_upper == 0) return;
-    BLUB_LAUNCH(density_scatter_kernel, blocks_for(np_upper, PT), PT, 0, st, g, params, pos, density);
+    BLUB_LAUNCH(density_scatter_kernel, particle_blocks(np_upper), PT, 0, st, g, params, pos, density);
 }
 
 void launch_density_finish(cudaStream_t st, const GridDim &g, const StepParams *params, const int8_t *marker, const float *density, float *rhs) {
@@ -846,7 +882,7 @@ void launch_density_rhs(cudaStream_t st, const GridDim &g, const StepParams *par
 void launch_binning(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *src, float4 *dst, const CellLists &l) {
     if (np_upper == 0) return;
     launch_cell_lists(st, g, params, np_upper, src, 0.0f, l);
-    BLUB_LAUNCH(binning_permute_kernel, blocks_for(np_upper, PT), PT, 0, st, params, l.order, src, dst);
+    BLUB_LAUNCH(binning_permute_kernel, particle_blocks(np_upper), PT, 0, st, params, l.order, src, dst);
 }
 
 } // namespace blub
