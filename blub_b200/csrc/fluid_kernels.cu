@@ -505,8 +505,8 @@ __global__ void __launch_bounds__(PT) correct_particles_kernel(GridDim g, const 
 }
 
 inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 1) / per_block); }
-// particle kernels: one thread per particle up to 16 blocks per SM, a grid-stride loop beyond (see the kernels)
-inline int particle_blocks(uint32_t np_upper) { return min(blocks_for(np_upper, PT), 148 * 16); }
+// particle kernels: at most 128 blocks per SM (small enough for a negligible tail, few enough to launch quickly), a grid-stride loop over the rest
+inline int particle_blocks(uint32_t np_upper) { return min(blocks_for(np_upper, PT), 148 * 128); }
 
 } // namespace
 

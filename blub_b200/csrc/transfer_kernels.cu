@@ -33,8 +33,8 @@ constexpr int PT = 256; // threads per block for particle and cell kernels
 
 __device__ __forceinline__ int lin(const GridDim &g, int x, int y, int z) { return (z * g.ny + y) * g.nx + x; }
 inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 1) / per_block); }
-// particle kernels: one thread per particle up to 16 blocks per SM, a grid-stride loop beyond (see the kernels)
-inline int particle_blocks(uint32_t np_upper) { return min(blocks_for(np_upper, PT), 148 * 16); }
+// particle kernels: at most 128 blocks per SM (small enough for a negligible tail, few enough to launch quickly), a grid-stride loop over the rest
+inline int particle_blocks(uint32_t np_upper) { return min(blocks_for(np_upper, PT), 148 * 128); }
 
 // The position a transfer sees: clamped so that every face / cell a particle touches exists (a simulated particle is always
 // inside [1.001, dim - 1.001], so this only ever changes particles handed in from outside the domain).  lo = 1.0 for the
