@@ -1012,6 +1012,97 @@ __device__ __forceinline__ void grid_reduce(unsigned *counter, unsigned &round, 
     gmax = mm;
 }
 
+// The same reduction on a z-slab rank, fused with the cross-GPU all-reduce: the block that arrives LAST on the local counter (atomicAdd returns
+// the ticket) adds this GPU's partials and publishes the total straight into every rank's mailbox -- its own included -- and ALL blocks of all
+// ranks wait on their own mailbox only.  The local "everybody waits for the counter, everybody re-reads the partials" step is off the critical
+// path: a round is one local arrival + one NVLink store + one poll (round 1: grid barrier, then block 0 publishes, then everybody polls).
+// Ordering of the ghost planes pushed during the phase: their writers release on the counter (gpu scope), the last block acquires, fences at
+// system scope and only then stores the flags; a reader polls the flag, fences at system scope and passes the block barrier.
+template <bool WITH_MAX>
+__device__ __forceinline__ void grid_allreduce(const SlabComm &c, unsigned seq, unsigned *counter, unsigned &round, float *psum, float *pmax, float acc, float err,
+                                               ReduceScratch &sc, double *sh_sum, float *sh_max, int *sh_dead, int *sh_last, double &tot, float &gmax) {
+    constexpr int NW = PCG_THREADS / 32;
+    const int tid = linear_tid(), lane = tid & 31, w = tid >> 5;
+    acc = warp_sum(acc);
+    if (WITH_MAX) err = warp_max(err);
+    if (lane == 0) {
+        sc.sh[w] = acc;
+        if (WITH_MAX) sc.sh[NW + w] = err;
+    }
+    __syncthreads();
+    round += 1u;
+    if (tid == 0) {
+        float bs = 0.0f, bm = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            bs += sc.sh[k];
+            if (WITH_MAX) bm = fmaxf(bm, sc.sh[NW + k]);
+        }
+        psum[blockIdx.x] = bs;
+        if (WITH_MAX) pmax[blockIdx.x] = bm;
+        __threadfence(); // release: the partials (and this block's pushes into the neighbours' ghost planes) before the ticket
+        const unsigned ticket = atomicAdd(counter, 1u);
+        *sh_last = ticket == round * gridDim.x - 1u ? 1 : 0;
+        __threadfence(); // acquire (matters in the last block): everybody else's partials are visible from here on
+    }
+    __syncthreads();
+    const int slot = (int)(seq & 1u) * 2 * SLAB_MAX_WORLD;
+    if (*sh_last) { // block-uniform: this block adds the GPU's partials in fixed order and publishes the total
+        double a = 0.0;
+        float m = 0.0f;
+        for (int k = tid; k < (int)gridDim.x; k += PCG_THREADS) {
+            a += (double)__ldcg(psum + k);
+            if (WITH_MAX) m = fmaxf(m, __ldcg(pmax + k));
+        }
+        a = warp_sum(a);
+        if (WITH_MAX) m = warp_max(m);
+        if (lane == 0) {
+            sc.shd[w] = a;
+            if (WITH_MAX) sc.sh[w] = m;
+        }
+        __syncthreads();
+        if (tid < c.world) {
+            double t = 0.0;
+            float mm = 0.0f;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                t += sc.shd[k];
+                if (WITH_MAX) mm = fmaxf(mm, sc.sh[k]);
+            }
+            __threadfence_system(); // everything this GPU wrote before, cumulatively through the ticket
+            volatile unsigned long long *dst = c.mailbox[tid] + slot + 2 * c.rank;
+            dst[0] = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint((float)t);
+            dst[1] = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(mm);
+        }
+    }
+    if (tid < c.world) {
+        volatile unsigned long long *src = c.mailbox[c.rank] + slot + 2 * tid;
+        unsigned long long v0 = 0, v1 = 0;
+        long long spins = 0;
+        bool ok = false;
+        while (!*sh_dead || spins == 0) {
+            v0 = src[0];
+            v1 = src[1];
+            if ((unsigned)(v0 >> 32) == seq && (unsigned)(v1 >> 32) == seq) { ok = true; break; }
+            if (++spins > COMM_SPIN_LIMIT) break;
+        }
+        if (!ok) *sh_dead = 1;
+        sh_sum[tid] = (double)__uint_as_float((unsigned)v0);
+        sh_max[tid] = __uint_as_float((unsigned)v1);
+        __threadfence_system(); // acquire: later loads of the ghost planes come after the peers' pushes; drops stale L1 lines of this SM
+    }
+    __syncthreads();
+    double t = 0.0;
+    float m = 0.0f;
+    for (int k = 0; k < c.world; ++k) {
+        t += sh_sum[k];
+        m = fmaxf(m, sh_max[k]);
+    }
+    __syncthreads(); // the scratch and the mailbox copies are reused by the next round
+    tot = t;
+    gmax = m;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Column solver (default on one GPU): the persistent solver with a work list that follows the fluid.
 //
@@ -1106,7 +1197,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
     __shared__ ReduceScratch sc;
     __shared__ double sh_csum[SLAB_MAX_WORLD];
     __shared__ float sh_cmax[SLAB_MAX_WORLD];
-    __shared__ int sh_dead;
+    __shared__ int sh_dead, sh_last;
     const TileMap t = a.t;
     const SlabComm &cm_ = a.comm;
     const bool sharded = cm_.world > 1;
@@ -1132,7 +1223,11 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
     if (linear_tid() == 0) sh_dead = 0;
     if (sharded) seq = *cm_.seq;
     __syncthreads();
-    if (sharded) slab_start_handshake(cm_, seq, sh_csum, sh_cmax, &sh_dead);
+    unsigned round = 0;
+    double tot = 0.0;
+    float gmax = 0.0f;
+    // start handshake: one empty round (a rank inside its solver has finished its prepare kernel; see the tile kernel)
+    if (sharded) grid_allreduce<false>(cm_, ++seq, a.barrier, round, psumA, pmax, 0.0f, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
 
     // ---- init: r <- b - A p, sigma <- z.r (pressure_init.comp:45-83, pressure_solver.rs:625-649); s stays 0
     float acc = 0.0f;
@@ -1147,11 +1242,8 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
         load_column_codes(e, c, w);
         init_tile<true>(e, c, w, a.p, a.r, acc);
     }
-    unsigned round = 0;
-    double tot = 0.0;
-    float gmax = 0.0f;
-    grid_reduce<false>(a.barrier, round, psumB, pmax, acc, 0.0f, sc, tot, gmax);
-    if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+    if (sharded) grid_allreduce<false>(cm_, ++seq, a.barrier, round, psumB, pmax, acc, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
+    else grid_reduce<false>(a.barrier, round, psumB, pmax, acc, 0.0f, sc, tot, gmax);
     float sigma = (float)tot;
     float alpha = 0.0f, beta = 0.0f, max_error = 0.0f;
     int num_iterations = 0;
@@ -1171,8 +1263,8 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
             load_column_codes(e, c, w);
             search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
         }
-        grid_reduce<false>(a.barrier, round, psumA, pmax, acc, 0.0f, sc, tot, gmax);
-        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+        if (sharded) grid_allreduce<false>(cm_, ++seq, a.barrier, round, psumA, pmax, acc, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
+        else grid_reduce<false>(a.barrier, round, psumA, pmax, acc, 0.0f, sc, tot, gmax);
         alpha = guarded_div(sigma, (float)tot); // RESULTMODE_ALPHA, pressure_reduce.comp:73-75
 
         const bool with_err = (a.max_iterations == it) || (it > 0 && it % a.check_frequency == 0); // pressure_solver.rs:676-677
@@ -1189,8 +1281,8 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
             load_column_codes(e, c, w);
             update_tile<true>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
         }
-        grid_reduce<true>(a.barrier, round, psumB, pmax, acc, err, sc, tot, gmax);
-        if (sharded) comm_allreduce(cm_, ++seq, tot, gmax, sh_csum, sh_cmax, &sh_dead);
+        if (sharded) grid_allreduce<true>(cm_, ++seq, a.barrier, round, psumB, pmax, acc, err, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
+        else grid_reduce<true>(a.barrier, round, psumB, pmax, acc, err, sc, tot, gmax);
         const float zr = (float)tot;
         if (with_err) {
             const float tol = a.params->tolerance[a.which];
@@ -1226,9 +1318,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSo
         }
         double dummy = 0.0;
         float dmax = 0.0f;
-        grid_reduce<false>(a.barrier, round, psumA, pmax, 0.0f, 0.0f, sc, dummy, dmax); // grid barrier: all pushes of this rank are issued
-        dummy = 0.0;
-        comm_allreduce(cm_, ++seq, dummy, dmax, sh_csum, sh_cmax, &sh_dead);
+        grid_allreduce<false>(cm_, ++seq, a.barrier, round, psumA, pmax, 0.0f, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, dummy, dmax);
         if (blockIdx.x == 0 && linear_tid() == 0) *cm_.seq = seq;
     }
     if (blockIdx.x == 0 && linear_tid() == 0) {
