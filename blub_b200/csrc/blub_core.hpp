@@ -140,7 +140,6 @@ class PressureSolver {
   private:
     void *tma_maps_ = nullptr;       // PcgTmaMaps (tensor maps of r, s0, s1, codes)
     int tma_blocks_ = 0, column_blocks_ = 0;
-    int column_sub_ = 4;              // virtual blocks of 256 threads per block of the column solver (4: one 1024-thread block per SM)
     int *tile_cols_ = nullptr;        // column solver: per-tile column counts | exclusive offsets | total
     int *col_list_ = nullptr;         // compacted quad columns (linear index of the quad in its tile's first plane)
     unsigned *barrier_ = nullptr;     // arrival counter of the column solver's grid-wide reductions

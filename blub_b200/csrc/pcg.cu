@@ -956,20 +956,15 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     return v;
 }
 __device__ __forceinline__ void red_release_u32(unsigned *p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-// A block of the column solver is SUB "virtual blocks" of PCG_THREADS threads stacked along threadIdx.z: SUB = 4 gives ONE block of 1024 threads
-// per SM, i.e. 148 instead of 592 participants in every grid-wide reduction (tools/barrier_bench.cu: 3.76 -> 2.46 us per reduction); the tile /
-// column bodies only see their virtual block.
-constexpr int PCG_MAX_SUB = 4;
 struct ReduceScratch {
-    float sh[2 * PCG_MAX_SUB * (PCG_THREADS / 32)];
-    double shd[PCG_MAX_SUB * (PCG_THREADS / 32)];
+    float sh[2 * (PCG_THREADS / 32)];
+    double shd[PCG_THREADS / 32];
 };
-__device__ __forceinline__ int block_tid() { return threadIdx.z * PCG_THREADS + linear_tid(); }
-template <bool WITH_MAX, int SUB>
+template <bool WITH_MAX>
 __device__ __forceinline__ void grid_reduce(unsigned *counter, unsigned &round, float *psum, float *pmax, float acc, float err, ReduceScratch &sc, double &tot,
                                             float &gmax) {
-    constexpr int BT = PCG_THREADS * SUB, NW = BT / 32;
-    const int tid = block_tid(), lane = tid & 31, w = tid >> 5;
+    constexpr int NW = PCG_THREADS / 32;
+    const int tid = linear_tid(), lane = tid & 31, w = tid >> 5;
     acc = warp_sum(acc);
     if (WITH_MAX) err = warp_max(err);
     if (lane == 0) {
@@ -994,7 +989,7 @@ __device__ __forceinline__ void grid_reduce(unsigned *counter, unsigned &round, 
     __syncthreads();
     double a = 0.0;
     float m = 0.0f;
-    for (int k = tid; k < (int)gridDim.x; k += BT) {
+    for (int k = tid; k < (int)gridDim.x; k += PCG_THREADS) {
         a += (double)__ldcg(psum + k);
         if (WITH_MAX) m = fmaxf(m, __ldcg(pmax + k));
     }
@@ -1023,11 +1018,11 @@ __device__ __forceinline__ void grid_reduce(unsigned *counter, unsigned &round, 
 // path: a round is one local arrival + one NVLink store + one poll (round 1: grid barrier, then block 0 publishes, then everybody polls).
 // Ordering of the ghost planes pushed during the phase: their writers release on the counter (gpu scope), the last block acquires, fences at
 // system scope and only then stores the flags; a reader polls the flag, fences at system scope and passes the block barrier.
-template <bool WITH_MAX, int SUB>
+template <bool WITH_MAX>
 __device__ __forceinline__ void grid_allreduce(const SlabComm &c, unsigned seq, unsigned *counter, unsigned &round, float *psum, float *pmax, float acc, float err,
                                                ReduceScratch &sc, double *sh_sum, float *sh_max, int *sh_dead, int *sh_last, double &tot, float &gmax) {
-    constexpr int BT = PCG_THREADS * SUB, NW = BT / 32;
-    const int tid = block_tid(), lane = tid & 31, w = tid >> 5;
+    constexpr int NW = PCG_THREADS / 32;
+    const int tid = linear_tid(), lane = tid & 31, w = tid >> 5;
     acc = warp_sum(acc);
     if (WITH_MAX) err = warp_max(err);
     if (lane == 0) {
@@ -1055,7 +1050,7 @@ __device__ __forceinline__ void grid_allreduce(const SlabComm &c, unsigned seq, 
     if (*sh_last) { // block-uniform: this block adds the GPU's partials in fixed order and publishes the total
         double a = 0.0;
         float m = 0.0f;
-        for (int k = tid; k < (int)gridDim.x; k += BT) {
+        for (int k = tid; k < (int)gridDim.x; k += PCG_THREADS) {
             a += (double)__ldcg(psum + k);
             if (WITH_MAX) m = fmaxf(m, __ldcg(pmax + k));
         }
@@ -1179,8 +1174,8 @@ __global__ void __launch_bounds__(1024) pcg_compact_kernel(const uint8_t *__rest
 }
 
 #define PCG_FOR_EACH_TILE(tile)                                                                                                      \
-    for (int li_ = vblock, tile = li_ < nact ? a.tile_list_flagged[li_] : 0, next_ = 0; li_ < nact; li_ += nvblocks, tile = next_) \
-        if ((next_ = li_ + nvblocks < nact ? a.tile_list_flagged[li_ + nvblocks] : 0), true)
+    for (int li_ = blockIdx.x, tile = li_ < nact ? a.tile_list_flagged[li_] : 0, next_ = 0; li_ < nact; li_ += gridDim.x, tile = next_) \
+        if ((next_ = li_ + (int)gridDim.x < nact ? a.tile_list_flagged[li_ + gridDim.x] : 0), true)
 // 32 consecutive list entries per warp and pass; the index of the next pass is fetched one pass ahead.  All 32 lanes stay in the loop
 // (the bodies shuffle): lanes beyond the end of the list carry valid = false.
 #define PCG_FOR_EACH_COLUMN(c)                                                                                                            \
@@ -1198,8 +1193,7 @@ __device__ __forceinline__ TileCtx column_ctx(int i, int sz) {
     return c;
 }
 
-template <int SUB>
-__global__ void __launch_bounds__(PCG_THREADS *SUB, SUB == 1 ? 4 : 1) pcg_solve_columns_kernel(PcgSolveArgs a) {
+__global__ void __launch_bounds__(PCG_THREADS, 4) pcg_solve_columns_kernel(PcgSolveArgs a) {
     __shared__ ReduceScratch sc;
     __shared__ double sh_csum[SLAB_MAX_WORLD];
     __shared__ float sh_cmax[SLAB_MAX_WORLD];
@@ -1209,11 +1203,10 @@ __global__ void __launch_bounds__(PCG_THREADS *SUB, SUB == 1 ? 4 : 1) pcg_solve_
     const bool sharded = cm_.world > 1;
     const int nact = *a.num_active, ncols = *a.num_cols;
     const int lane = linear_tid() & 31;
-    const int vblock = blockIdx.x * SUB + threadIdx.z, nvblocks = gridDim.x * SUB; // virtual blocks of PCG_THREADS threads
     // Tiles are dealt to the blocks from block 0 upwards, columns to the warps from the LAST warp of the last block downwards: when there are
     // fewer dense tiles than blocks (or a remainder), the blocks without a tile take the columns first and a phase is one pass, not two.
-    const int col_stride = nvblocks * PCG_THREADS;
-    const int warp_first = col_stride - 32 - (vblock * (PCG_THREADS / 32) + (linear_tid() >> 5)) * 32;
+    const int col_stride = gridDim.x * PCG_THREADS;
+    const int warp_first = col_stride - 32 - (blockIdx.x * (PCG_THREADS / 32) + (linear_tid() >> 5)) * 32;
     float *psumA = a.partials, *psumB = a.partials + gridDim.x, *pmax = a.partials + 2 * gridDim.x;
     TileEnv e;
     e.g = a.g;
@@ -1227,14 +1220,14 @@ __global__ void __launch_bounds__(PCG_THREADS *SUB, SUB == 1 ? 4 : 1) pcg_solve_
     e.peer_r_hi = cm_.peer_r[1];
     const int sz = a.g.sz;
     unsigned seq = 0;
-    if (block_tid() == 0) sh_dead = 0;
+    if (linear_tid() == 0) sh_dead = 0;
     if (sharded) seq = *cm_.seq;
     __syncthreads();
     unsigned round = 0;
     double tot = 0.0;
     float gmax = 0.0f;
     // start handshake: one empty round (a rank inside its solver has finished its prepare kernel; see the tile kernel)
-    if (sharded) grid_allreduce<false, SUB>(cm_, ++seq, a.barrier, round, psumA, pmax, 0.0f, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
+    if (sharded) grid_allreduce<false>(cm_, ++seq, a.barrier, round, psumA, pmax, 0.0f, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
 
     // ---- init: r <- b - A p, sigma <- z.r (pressure_init.comp:45-83, pressure_solver.rs:625-649); s stays 0
     float acc = 0.0f;
@@ -1249,8 +1242,8 @@ __global__ void __launch_bounds__(PCG_THREADS *SUB, SUB == 1 ? 4 : 1) pcg_solve_
         load_column_codes(e, c, w);
         init_tile<true>(e, c, w, a.p, a.r, acc);
     }
-    if (sharded) grid_allreduce<false, SUB>(cm_, ++seq, a.barrier, round, psumB, pmax, acc, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
-    else grid_reduce<false, SUB>(a.barrier, round, psumB, pmax, acc, 0.0f, sc, tot, gmax);
+    if (sharded) grid_allreduce<false>(cm_, ++seq, a.barrier, round, psumB, pmax, acc, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
+    else grid_reduce<false>(a.barrier, round, psumB, pmax, acc, 0.0f, sc, tot, gmax);
     float sigma = (float)tot;
     float alpha = 0.0f, beta = 0.0f, max_error = 0.0f;
     int num_iterations = 0;
@@ -1270,8 +1263,8 @@ __global__ void __launch_bounds__(PCG_THREADS *SUB, SUB == 1 ? 4 : 1) pcg_solve_
             load_column_codes(e, c, w);
             search_tile<true>(e, c, w, a.r, s_in, s_out, beta, acc);
         }
-        if (sharded) grid_allreduce<false, SUB>(cm_, ++seq, a.barrier, round, psumA, pmax, acc, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
-        else grid_reduce<false, SUB>(a.barrier, round, psumA, pmax, acc, 0.0f, sc, tot, gmax);
+        if (sharded) grid_allreduce<false>(cm_, ++seq, a.barrier, round, psumA, pmax, acc, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
+        else grid_reduce<false>(a.barrier, round, psumA, pmax, acc, 0.0f, sc, tot, gmax);
         alpha = guarded_div(sigma, (float)tot); // RESULTMODE_ALPHA, pressure_reduce.comp:73-75
 
         const bool with_err = (a.max_iterations == it) || (it > 0 && it % a.check_frequency == 0); // pressure_solver.rs:676-677
@@ -1288,8 +1281,8 @@ __global__ void __launch_bounds__(PCG_THREADS *SUB, SUB == 1 ? 4 : 1) pcg_solve_
             load_column_codes(e, c, w);
             update_tile<true>(e, c, w, s_out, a.p, a.r, alpha, acc, err);
         }
-        if (sharded) grid_allreduce<true, SUB>(cm_, ++seq, a.barrier, round, psumB, pmax, acc, err, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
-        else grid_reduce<true, SUB>(a.barrier, round, psumB, pmax, acc, err, sc, tot, gmax);
+        if (sharded) grid_allreduce<true>(cm_, ++seq, a.barrier, round, psumB, pmax, acc, err, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, tot, gmax);
+        else grid_reduce<true>(a.barrier, round, psumB, pmax, acc, err, sc, tot, gmax);
         const float zr = (float)tot;
         if (with_err) {
             const float tol = a.params->tolerance[a.which];
@@ -1325,10 +1318,10 @@ __global__ void __launch_bounds__(PCG_THREADS *SUB, SUB == 1 ? 4 : 1) pcg_solve_
         }
         double dummy = 0.0;
         float dmax = 0.0f;
-        grid_allreduce<false, SUB>(cm_, ++seq, a.barrier, round, psumA, pmax, 0.0f, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, dummy, dmax);
-        if (blockIdx.x == 0 && block_tid() == 0) *cm_.seq = seq;
+        grid_allreduce<false>(cm_, ++seq, a.barrier, round, psumA, pmax, 0.0f, 0.0f, sc, sh_csum, sh_cmax, &sh_dead, &sh_last, dummy, dmax);
+        if (blockIdx.x == 0 && linear_tid() == 0) *cm_.seq = seq;
     }
-    if (blockIdx.x == 0 && block_tid() == 0) {
+    if (blockIdx.x == 0 && linear_tid() == 0) {
         a.scal->alpha = alpha;
         a.scal->beta = beta;
         a.scal->sigma = sigma;
@@ -1777,13 +1770,7 @@ PressureSolver::PressureSolver(const GridDim &grid, void *external_residual) : g
         BLUB_CUDA_CHECK(cudaMalloc(&barrier_, 256));
         BLUB_CUDA_CHECK(cudaMemset(barrier_, 0, 256));
         int per = 0;
-        const char *sub = std::getenv("BLUB_PCG_SUB"); // A/B: 1 = 592 blocks of 256 threads, 4 (default) = 148 blocks of 1024 threads
-        column_sub_ = sub && std::string(sub) == "1" ? 1 : 4;
-        if (column_sub_ == 4) {
-            BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_columns_kernel<4>, PCG_THREADS * 4, 0));
-            if (per < 1) column_sub_ = 1;
-        }
-        if (column_sub_ == 1) BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_columns_kernel<1>, PCG_THREADS, 0));
+        BLUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, pcg_solve_columns_kernel, PCG_THREADS, 0));
         column_blocks_ = sms * per;
         if (column_blocks_ > 2048) column_blocks_ = 2048;
     }
@@ -1855,9 +1842,7 @@ void PressureSolver::solve(cudaStream_t stream, PressureField &field, int which,
             BLUB_LAUNCH(pcg_column_fill_kernel, grid, block, 0, stream, g, t, st, ta, col_offset, ghost_tiles, t.ntiles - ghost_tiles, col_list_);
             int nblocks = column_blocks_;
             void *kargs[] = {&args};
-            const dim3 cblock(t.bx, t.by, column_sub_);
-            BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel(column_sub_ == 4 ? (const void *)pcg_solve_columns_kernel<4> : (const void *)pcg_solve_columns_kernel<1>, dim3(nblocks),
-                                                        cblock, kargs, 0, stream));
+            BLUB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pcg_solve_columns_kernel, dim3(nblocks), t.block(), kargs, 0, stream));
             g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
             return;
         }

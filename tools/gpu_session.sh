@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call, many answers: every call costs 1.5-3 minutes of box time before the command even starts, so measurements are
 # batched.  Usage (from the repository root, on the GPU box):
-#     bash tools/gpu_session.sh [tests] [smoke] [timeline] [variants] [p2gparts] [pcgparts] [sub] [overhead] [multi2] [barrier] [sanitize] [ncustep] [bench] [launches] [ncu] [blubrun]
+#     bash tools/gpu_session.sh [tests] [smoke] [timeline] [variants] [p2gparts] [pcgparts] [overhead] [multi2] [barrier] [sanitize] [ncustep] [bench] [launches] [ncu] [blubrun]
 # Everything lands in gpurun_out/session_*.{txt,json,csv}; nothing here is a bench number unless it comes from bench.py outside ncu.
 set -u
 OUT=gpurun_out
@@ -26,14 +26,6 @@ if want variants; then      # comparison paths against the default timeline
     BLUB_PCG=tiles python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_tiles.txt 2>&1
     python tools/profile_targets.py pcg 256 6 > $OUT/session_pcg_dense_default.txt 2>&1; cat $OUT/session_pcg_dense_default.txt
     for f in p2g_gather pcg_tiles; do echo "== $f"; grep -E "after|p2g|solve_|extrapolate |density_gather|total|Error|error" $OUT/session_timeline_$f.txt; done
-fi
-if want sub; then           # A/B of the column solver's block shape: 592 x 256 threads (BLUB_PCG_SUB=1) against 148 x 1024 (default)
-    for v in 1 4; do
-        BLUB_PCG_SUB=$v python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_sub$v.txt 2>&1
-        BLUB_PCG_SUB=$v python tools/profile_targets.py pcg 256 6 > $OUT/session_pcg_dense_sub$v.txt 2>&1
-        BLUB_PCG_SUB=$v python tools/profile_targets.py pcg_overhead > $OUT/session_pcg_overhead_sub$v.txt 2>&1
-        echo "== sub $v"; grep -E "after|solve_|total|Error|error" $OUT/session_timeline_sub$v.txt; tail -3 $OUT/session_pcg_dense_sub$v.txt; tail -4 $OUT/session_pcg_overhead_sub$v.txt
-    done
 fi
 if want p2gparts; then      # which kernel of the P2G stage is slow late in the run: launch list of stage 0 at step 56 (eager launches) + cell statistics
     python tools/profile_targets.py cellstats dam_256 3 56 110 > $OUT/session_cellstats.txt 2>&1; cat $OUT/session_cellstats.txt
