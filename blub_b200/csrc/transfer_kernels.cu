@@ -606,7 +606,42 @@ __device__ __forceinline__ bool segmented_run_sum(int key, float (&v)[NV]) {
     return (pos & 3) == 0; // the first lane of every group of four issues the reductions
 }
 
-template <bool MARK>
+// The same reduction over ALL lanes of the warp that share a dual cell, adjacent or not (match.any).  A cell-sorted warp holds the particles
+// of about four primal cells; a dual cell of component c collects the particles of one half of a primal cell (c = x) or of the facing halves of
+// two x-adjacent primal cells (c = y, z), which sit in the warp but not next to each other: adjacent runs save 17-25 % of the reductions, the
+// peer groups 55 % (24 -> 10.7 per particle on the dam break, 8 -> 3.7-4.4 for the density; tools/red_stats.py, oracle positions), and they
+// keep doing so while the particle order decays between two re-sorts.  Peer groups are cut into groups of four by rank, the tree is the one
+// above: (v0 + v1) + (v2 + v3) in ascending lane order, the group's lowest lane issues the reductions.
+template <int NV>
+__device__ __forceinline__ bool matched_group_sum(int key, float (&v)[NV]) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(full, key);
+    if (__all_sync(full, peers == (1u << lane))) return true;                    // warp-uniform: every lane is alone
+    const int rank = __popc(peers & ((1u << lane) - 1u));                        // position among the lanes with this key
+    const unsigned above = lane == 31 ? 0u : (peers & ~((2u << lane) - 1u));
+    const int n1 = above ? __ffs(above) - 1 : -1;                                // the peer of rank + 1, if any
+    const int n2 = __shfl_sync(full, n1, n1 >= 0 ? n1 : lane);                   // the peer of rank + 2 (a lane without a next peer reads its own -1)
+    const bool take1 = (rank & 1) == 0 && n1 >= 0, take2 = (rank & 3) == 0 && n2 >= 0;
+    const int s1 = n1 >= 0 ? n1 : lane, s2 = n2 >= 0 ? n2 : lane;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const float t = __shfl_sync(full, v[k], s1);
+        if (take1) v[k] += t;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const float t = __shfl_sync(full, v[k], s2);
+        if (take2) v[k] += t;
+    }
+    return (rank & 3) == 0; // the lowest lane of every group of four issues the reductions
+}
+template <bool MATCH, int NV>
+__device__ __forceinline__ bool warp_group_sum(int key, float (&v)[NV]) {
+    return MATCH ? matched_group_sum<NV>(key, v) : segmented_run_sum<NV>(key, v);
+}
+
+template <bool MARK, bool MATCH>
 __device__ __forceinline__ void p2g_scatter_kernel_one(uint32_t i, GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
                                                          const float4 *__restrict__ rowx, const float4 *__restrict__ rowy,
                                                          const float4 *__restrict__ rowz, float2 *__restrict__ nwx, float2 *__restrict__ nwy,
@@ -639,7 +674,7 @@ __device__ __forceinline__ void p2g_scatter_kernel_one(uint32_t i, GridDim g, co
             acc[2 * k] = w > 0.0f ? w * v : 0.0f;
             acc[2 * k + 1] = w > 0.0f ? w : 0.0f;
         }
-        const bool head = segmented_run_sum<16>(valid ? base : -1 - (int)(threadIdx.x & 31), acc);
+        const bool head = warp_group_sum<MATCH, 16>(valid ? base : -1 - (int)(threadIdx.x & 31), acc);
         if (head && valid) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
@@ -647,14 +682,14 @@ __device__ __forceinline__ void p2g_scatter_kernel_one(uint32_t i, GridDim g, co
         }
     }
 }
-template <bool MARK>
+template <bool MARK, bool MATCH>
 __global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
                                                          const float4 *__restrict__ rowx, const float4 *__restrict__ rowy,
                                                          const float4 *__restrict__ rowz, float2 *__restrict__ nwx, float2 *__restrict__ nwy,
                                                          float2 *__restrict__ nwz, int8_t *__restrict__ marker) {
     // a bounded grid strides over the particles: launch cost does not grow with the CAPACITY a z-slab rank sizes its launches by
     const uint32_t np_ = params->num_particles;
-    for (uint32_t i = blockIdx.x * PT + threadIdx.x; (i & ~31u) < np_; i += gridDim.x * PT) p2g_scatter_kernel_one<MARK>(i, g, params, pos, rowx, rowy, rowz, nwx, nwy, nwz, marker);
+    for (uint32_t i = blockIdx.x * PT + threadIdx.x; (i & ~31u) < np_; i += gridDim.x * PT) p2g_scatter_kernel_one<MARK, MATCH>(i, g, params, pos, rowx, rowy, rowz, nwx, nwy, nwz, marker);
 }
 
 // Normalisation + global forces + "don't flow into solid" for the scatter form: transfer_gather_velocity.comp:116-127 -- and the
@@ -722,6 +757,7 @@ __global__ void __launch_bounds__(PT) p2g_normalize_kernel(GridDim g, int wpr, c
 // ------------------------------------------------------------------------------------------------ density projection
 // Scatter counterpart of density_projection_gather_error.comp:41-97: dual cell d = trunc(pos - 0.5), cell centres d + {0,1}^3;
 // warp-aggregated like the P2G scatter.
+template <bool MATCH>
 __device__ __forceinline__ void density_scatter_kernel_one(uint32_t i, GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
                                                              float *__restrict__ density) {
     const uint32_t np = params->num_particles;
@@ -737,18 +773,19 @@ __device__ __forceinline__ void density_scatter_kernel_one(uint32_t i, GridDim g
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = valid ? wx[k & 1] * wy[(k >> 1) & 1] * wz[k >> 2] : 0.0f;
-    const bool head = segmented_run_sum<8>(valid ? base : -1 - (int)(threadIdx.x & 31), acc);
+    const bool head = warp_group_sum<MATCH, 8>(valid ? base : -1 - (int)(threadIdx.x & 31), acc);
     if (head && valid) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             if (acc[k] > 0.0f) atomicAdd(density + base + (k & 1) + ((k >> 1) & 1) * g.sy + (k >> 2) * g.sz, acc[k]);
     }
 }
+template <bool MATCH>
 __global__ void __launch_bounds__(PT) density_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
                                                              float *__restrict__ density) {
     // a bounded grid strides over the particles: launch cost does not grow with the CAPACITY a z-slab rank sizes its launches by
     const uint32_t np_ = params->num_particles;
-    for (uint32_t i = blockIdx.x * PT + threadIdx.x; (i & ~31u) < np_; i += gridDim.x * PT) density_scatter_kernel_one(i, g, params, pos, density);
+    for (uint32_t i = blockIdx.x * PT + threadIdx.x; (i & ~31u) < np_; i += gridDim.x * PT) density_scatter_kernel_one<MATCH>(i, g, params, pos, density);
 }
 
 // density_projection_gather_error.comp:99-199
@@ -844,6 +881,16 @@ void launch_p2g_gather(cudaStream_t st, const GridDim &g, const StepParams *para
     BLUB_LAUNCH(p2g_gather_kernel<2>, grid, GATHER_THREADS, GATHER_SMEM_BYTES, st, g, params, l.cell_start, l.order, pos, row[2], marker, u[2], l.crowd);
 }
 
+// Which warp aggregation the scatter kernels use: peer groups found with match.any (default) or runs of adjacent lanes (the comparison
+// path: BLUB_SCATTER_AGG=adjacent, read once).
+static bool scatter_groups_by_match() {
+    static const bool by_match = [] {
+        const char *e = std::getenv("BLUB_SCATTER_AGG");
+        return !(e && std::strcmp(e, "adjacent") == 0);
+    }();
+    return by_match;
+}
+
 void launch_p2g_scatter(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float4 *const row[3],
                         float2 *const nw[3], int8_t *marker, bool clear_accumulators) {
     // transfer_clear.comp: marker <- AIR.  The (num, weight) volumes (they replace the linked-list head volume) are all zero here on one GPU:
@@ -853,7 +900,8 @@ void launch_p2g_scatter(cudaStream_t st, const GridDim &g, const StepParams *par
     if (clear_accumulators)
         for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(nw[c], 0, (size_t)g.n * sizeof(float2), st));
     if (np_upper == 0) return;
-    BLUB_LAUNCH(p2g_scatter_kernel<true>, particle_blocks(np_upper), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
+    const auto kernel = scatter_groups_by_match() ? p2g_scatter_kernel<true, true> : p2g_scatter_kernel<true, false>;
+    BLUB_LAUNCH(kernel, particle_blocks(np_upper), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
 }
 
 void launch_p2g_finish(cudaStream_t st, const GridDim &g, const StepParams *params, float *const u[3], float2 *const nw[3], int8_t *marker,
@@ -866,7 +914,8 @@ void launch_p2g_finish(cudaStream_t st, const GridDim &g, const StepParams *para
 void launch_density_scatter(cudaStream_t st, const GridDim &g, const StepParams *params, uint32_t np_upper, const float4 *pos, float *density) {
     BLUB_CUDA_CHECK(cudaMemsetAsync(density, 0, (size_t)g.n * sizeof(float), st));
     if (np_upper == 0) return;
-    BLUB_LAUNCH(density_scatter_kernel, particle_blocks(np_upper), PT, 0, st, g, params, pos, density);
+    const auto kernel = scatter_groups_by_match() ? density_scatter_kernel<true> : density_scatter_kernel<false>;
+    BLUB_LAUNCH(kernel, particle_blocks(np_upper), PT, 0, st, g, params, pos, density);
 }
 
 void launch_density_finish(cudaStream_t st, const GridDim &g, const StepParams *params, const int8_t *marker, const float *density, float *rhs) {

@@ -84,3 +84,29 @@ if want blubrun; then
     ./blub_b200/blub_run tests/golden/scenes/dam_halfhalf.json --steps 320 --stats $OUT/session_run_stats.json --trace $OUT/session_run_trace.json > $OUT/session_run.txt 2>&1
     tail -2 $OUT/session_run.txt
 fi
+if want matchab; then       # warp aggregation of the scatter kernels: peer groups (match.any, default) against adjacent runs; cost of MATCH.ANY itself
+    [ -x tools/match_bench ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/match_bench tools/match_bench.cu
+    ./tools/match_bench > $OUT/session_match_bench.txt 2>&1; cat $OUT/session_match_bench.txt
+    BLUB_SCATTER_AGG=adjacent python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_agg_adjacent.txt 2>&1
+    echo "== adjacent runs"; grep -E "after|p2g|density_gather|advect|correct|binning|total|Error|error" $OUT/session_timeline_agg_adjacent.txt
+    B="--steps 100 --warmup 10 --no-cpu-baseline --no-roofline --no-scaling-reference --no-phases"
+    for v in "match 8" "adjacent 8" "match 12" "match 16" "match 4"; do
+        set -- $v
+        BLUB_SCATTER_AGG=$1 BLUB_RESORT_EVERY=$2 timeout 300 python bench.py $B > $OUT/session_bench_agg_$1_$2.json 2>> $OUT/session_bench.err
+        python -c "import json,sys; d=json.load(open('$OUT/session_bench_agg_$1_$2.json')); print('agg $1 resort every $2:', d['value'], 'steps/s', d['ms_per_step'], 'ms, e2e', d['e2e']['value'])"
+    done
+fi
+if want configs; then       # the other BASELINE configurations on one GPU (C2, C3, C5, C4), 100 steps after 10
+    B="--steps 100 --warmup 10 --no-cpu-baseline --no-roofline --no-scaling-reference --no-phases"
+    for w in dam_halfhalf dam_halfhalf_highres double_dam_box basin_512; do
+        timeout 400 python bench.py --workload $w $B > $OUT/session_bench_$w.json 2>> $OUT/session_bench.err
+        python -c "import json,sys; d=json.load(open('$OUT/session_bench_$w.json')); print('$w:', d['value'], 'steps/s', d['ms_per_step'], 'ms, e2e', d['e2e']['value'], d['config']['workload'], d['config']['particles'])"
+    done
+fi
+if want ncuscatter; then    # full captures of the two scatter kernels at step 5, both aggregation forms (eager launches)
+    for a in match adjacent; do
+        BLUB_SCATTER_AGG=$a BLUB_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"p2g_scatter|density_scatter" --launch-skip 10 -c 2 -o $OUT/session_scatter_$a \
+            python tools/profile_targets.py step dam_256 7 > $OUT/session_ncu_scatter_$a.log 2>&1
+    done
+    ls -la $OUT/session_scatter_*.ncu-rep
+fi
