@@ -629,10 +629,12 @@ __device__ __forceinline__ bool matched_group_sum(int key, float (&v)[NV]) {
         const float t = __shfl_sync(full, v[k], s1);
         if (take1) v[k] += t;
     }
+    if (__any_sync(full, take2)) { // warp-uniform: no group of this warp has a third member (the usual case for the x component)
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const float t = __shfl_sync(full, v[k], s2);
-        if (take2) v[k] += t;
+        for (int k = 0; k < NV; ++k) {
+            const float t = __shfl_sync(full, v[k], s2);
+            if (take2) v[k] += t;
+        }
     }
     return (rank & 3) == 0; // the lowest lane of every group of four issues the reductions
 }
@@ -682,8 +684,8 @@ __device__ __forceinline__ void p2g_scatter_kernel_one(uint32_t i, GridDim g, co
         }
     }
 }
-template <bool MARK, bool MATCH>
-__global__ void __launch_bounds__(PT) p2g_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
+template <bool MARK, bool MATCH, int MIN_BLOCKS>
+__global__ void __launch_bounds__(PT, MIN_BLOCKS) p2g_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
                                                          const float4 *__restrict__ rowx, const float4 *__restrict__ rowy,
                                                          const float4 *__restrict__ rowz, float2 *__restrict__ nwx, float2 *__restrict__ nwy,
                                                          float2 *__restrict__ nwz, int8_t *__restrict__ marker) {
@@ -900,7 +902,10 @@ void launch_p2g_scatter(cudaStream_t st, const GridDim &g, const StepParams *par
     if (clear_accumulators)
         for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(nw[c], 0, (size_t)g.n * sizeof(float2), st));
     if (np_upper == 0) return;
-    const auto kernel = scatter_groups_by_match() ? p2g_scatter_kernel<true, true> : p2g_scatter_kernel<true, false>;
+    // resident blocks per SM the kernel is compiled for: 4 (62 registers), 5 (48 registers, 16 bytes of spills) or 6 (40 registers); BLUB_SCATTER_OCC, read once
+    static const int occ = [] { const char *e = std::getenv("BLUB_SCATTER_OCC"); return e ? std::atoi(e) : 4; }();
+    auto kernel = p2g_scatter_kernel<true, false, 4>;
+    if (scatter_groups_by_match()) kernel = occ == 5 ? p2g_scatter_kernel<true, true, 5> : occ == 6 ? p2g_scatter_kernel<true, true, 6> : p2g_scatter_kernel<true, true, 4>;
     BLUB_LAUNCH(kernel, particle_blocks(np_upper), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
 }
 
