@@ -7,20 +7,22 @@
 // and gathers them with 729-thread groups in lock-step rounds, capped at 12 / 32 entries ("by far the biggest bottleneck",
 // README.md:76).  Here:
 //
-//   * CELL LISTS (every step): a counting sort of particle INDICES by primal cell -- count (one integer atomic per particle),
+//   * P2G SCATTER (default; the form z-slab ranks always use): one thread per particle; the lanes of a warp that share a dual cell -- found
+//     with match.any, adjacent or not -- add their contributions up in groups of four with two shuffle steps, and the lowest lane of a
+//     group issues one 8-byte vector reduction (RED.ADD.F32x2) per face: 10.7 reductions per particle instead of 24 (17.8 with runs of
+//     adjacent lanes only).  A sparse finish pass normalises and puts the accumulators back to zero (no memsets, no dense pass).
+//   * CELL LISTS (gather form and binning): a counting sort of particle INDICES by primal cell -- count (one integer atomic per particle),
 //     exclusive scan, fill, and a canonicalisation (rank counting) that puts every cell's slice into ascending particle index.  The
 //     lists are therefore a pure function of the particle array: the same input gives the same lists, run after run, whatever
 //     order the atomics arrived in.
-//   * P2G GATHER (default): one thread per primal cell walks its own list and keeps the (sum w*value, sum w) of the 18 faces
-//     a cell's particles can reach in REGISTERS; blocks march along y so that the y-combination of those partial sums happens
-//     in registers too, x-neighbours are combined with warp shuffles, z-neighbours through shared memory -- all in a fixed
-//     order.  No atomics, no accumulator volumes, no memsets, normalisation / gravity / solid rule fused into the epilogue, and
-//     the result is bit-identical run to run.  A warp stages the particles of its 32 cells through shared memory with
-//     coalesced loads (the lists of x-consecutive cells are one contiguous range).
-//   * P2G SCATTER (z-slab sharded fluids, and the comparison path): one thread per particle, segmented warp reduction over
-//     runs of equal dual cell, then one 8-byte vector reduction (RED.ADD.F32x2) per (run, face).
-//   * the marker volume and a 1-bit-per-cell FLUID mask are derived from the cell counts (a cell is FLUID iff a particle lies
-//     in it, transfer_build_linkedlist.comp:17-19, unless it is a border / solid cell, transfer_set_boundary_marker.comp).
+//   * P2G GATHER (deterministic, selectable: BLUB_P2G=gather): one thread per primal cell walks its own list and keeps the
+//     (sum w*value, sum w) of the 18 faces a cell's particles can reach in REGISTERS; blocks march along y so that the y-combination of
+//     those partial sums happens in registers too, x-neighbours are combined with warp shuffles, z-neighbours through shared memory --
+//     all in a fixed order.  No atomics, normalisation / gravity / solid rule fused into the epilogue, bit-identical run to run; slower
+//     than the scatter at every phase of a dam break (instruction bound), hence not the default.
+//   * the marker volume and a 1-bit-per-cell FLUID mask: from the particles' cells (scatter form) or the cell counts (gather form); a cell
+//     is FLUID iff a particle lies in it (transfer_build_linkedlist.comp:17-19) unless it is a border / solid cell
+//     (transfer_set_boundary_marker.comp).
 #include <cstdlib>
 #include <cstring>
 
@@ -582,6 +584,7 @@ __global__ void __launch_bounds__(PT) p2g_crowded_kernel(GridDim g, const uint32
 // (ncu: mio_throttle the top stall, 240 shuffles per particle, profiles/r02_s10_particle_kernels.md), while runs are short -- a dual cell
 // holds 8 particles on average and a cell-sorted warp holds them in 2-4 separate runs; a longer run simply issues one reduction per
 // group of four.  Warps in which every lane is its own run (the usual case once the particle order has decayed) skip the shuffles.
+// Since r2 session 18 this is the comparison path (BLUB_SCATTER_AGG=adjacent); the default is matched_group_sum below.
 template <int NV>
 __device__ __forceinline__ bool segmented_run_sum(int key, float (&v)[NV]) {
     const unsigned full = 0xffffffffu;
@@ -684,8 +687,10 @@ __device__ __forceinline__ void p2g_scatter_kernel_one(uint32_t i, GridDim g, co
         }
     }
 }
-template <bool MARK, bool MATCH, int MIN_BLOCKS>
-__global__ void __launch_bounds__(PT, MIN_BLOCKS) p2g_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
+// 4 resident blocks per SM (64 registers): compiled for 5 / 6 blocks (48 / 40 registers, 16 / 64 bytes of spills) the stage is slower
+// (0.697 / 0.713 / 0.768 ms at step 3 of the 256^3 dam break, profiles/r02_s19_multi_gpu_check_and_occupancy.md)
+template <bool MARK, bool MATCH>
+__global__ void __launch_bounds__(PT, 4) p2g_scatter_kernel(GridDim g, const StepParams *__restrict__ params, const float4 *__restrict__ pos,
                                                          const float4 *__restrict__ rowx, const float4 *__restrict__ rowy,
                                                          const float4 *__restrict__ rowz, float2 *__restrict__ nwx, float2 *__restrict__ nwy,
                                                          float2 *__restrict__ nwz, int8_t *__restrict__ marker) {
@@ -902,10 +907,7 @@ void launch_p2g_scatter(cudaStream_t st, const GridDim &g, const StepParams *par
     if (clear_accumulators)
         for (int c = 0; c < 3; ++c) BLUB_CUDA_CHECK(cudaMemsetAsync(nw[c], 0, (size_t)g.n * sizeof(float2), st));
     if (np_upper == 0) return;
-    // resident blocks per SM the kernel is compiled for: 4 (62 registers), 5 (48 registers, 16 bytes of spills) or 6 (40 registers); BLUB_SCATTER_OCC, read once
-    static const int occ = [] { const char *e = std::getenv("BLUB_SCATTER_OCC"); return e ? std::atoi(e) : 4; }();
-    auto kernel = p2g_scatter_kernel<true, false, 4>;
-    if (scatter_groups_by_match()) kernel = occ == 5 ? p2g_scatter_kernel<true, true, 5> : occ == 6 ? p2g_scatter_kernel<true, true, 6> : p2g_scatter_kernel<true, true, 4>;
+    const auto kernel = scatter_groups_by_match() ? p2g_scatter_kernel<true, true> : p2g_scatter_kernel<true, false>;
     BLUB_LAUNCH(kernel, particle_blocks(np_upper), PT, 0, st, g, params, pos, row[0], row[1], row[2], nw[0], nw[1], nw[2], marker);
 }
 

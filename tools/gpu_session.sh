@@ -110,17 +110,6 @@ if want ncuscatter; then    # full captures of the two scatter kernels at step 5
     done
     ls -la $OUT/session_scatter_*.ncu-rep
 fi
-if want occ; then           # P2G scatter compiled for 4 / 5 / 6 resident blocks per SM (64 / 48 / 40 registers)
-    B="--steps 100 --warmup 10 --no-cpu-baseline --no-roofline --no-scaling-reference --no-phases"
-    for o in 4 5 6 4 5; do
-        BLUB_SCATTER_OCC=$o timeout 300 python bench.py $B > $OUT/session_bench_occ_$o.json 2>> $OUT/session_bench.err
-        python -c "import json,sys; d=json.load(open('$OUT/session_bench_occ_$o.json')); print('scatter blocks/SM $o:', d['value'], 'steps/s', d['ms_per_step'], 'ms, e2e', d['e2e']['value'])"
-    done
-    for o in 4 5 6; do
-        BLUB_SCATTER_OCC=$o python tools/profile_targets.py stages dam_256 3 56 > $OUT/session_timeline_occ_$o.txt 2>&1
-        echo "== scatter blocks/SM $o"; grep -E "after|p2g|total|Error|error" $OUT/session_timeline_occ_$o.txt
-    done
-fi
 if want multicheck; then    # needs gpurun --gpus 2: the multi-GPU tests and the N = 2 bench line (z-slab ranks run the same scatter kernels over their capacity)
     timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q --tb=short -p no:cacheprovider 2>&1 | grep -v "^$" | tail -30 > $OUT/session_multi_tests.txt; tail -6 $OUT/session_multi_tests.txt
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 5 > $OUT/session_bench_n2.json 2> $OUT/session_bench_n2.err
