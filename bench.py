@@ -271,10 +271,11 @@ def late_window_and_in_step(fluid, step, stepper, dt, steps_done, args, early_ms
         step(dt)
         steps_done += 1
     fluid.synchronize()
+    late_first = steps_done  # == late_start unless the timed regions already ran past it (large --steps): the label follows the scene, not the flag
     ms_late = stepper.time_steps(dt, late_steps) if stepper else fluid.time_steps(dt, late_steps)
     steps_done += late_steps
     phases = {"early": {"first_step": max(args.warmup, 3), "steps": args.steps, "ms_per_step": round(early_ms_per_step, 4), "steps_per_s": round(1e3 / early_ms_per_step, 3)},
-              "late": {"first_step": late_start, "steps": late_steps, "ms_per_step": round(ms_late / late_steps, 4), "steps_per_s": round(late_steps / (ms_late * 1e-3), 3)}}
+              "late": {"first_step": late_first, "steps": late_steps, "ms_per_step": round(ms_late / late_steps, 4), "steps_per_s": round(late_steps / (ms_late * 1e-3), 3)}}
     if stepper:
         return phases, None, None, steps_done
     stage_ms = fluid.step_timed(dt)
