@@ -115,3 +115,9 @@ if want multicheck; then    # needs gpurun --gpus 2: the multi-GPU tests and the
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 5 > $OUT/session_bench_n2.json 2> $OUT/session_bench_n2.err
     head -c 400 $OUT/session_bench_n2.json; echo; tail -3 $OUT/session_bench_n2.err
 fi
+if want pcgvariants; then   # in-step solve times of the comparison solvers (TMA-staged tiles, register-marching tiles) against the default column solver
+    for v in tma tiles; do
+        BLUB_PCG=$v python tools/profile_targets.py stages dam_256 3 56 110 > $OUT/session_timeline_pcg_$v.txt 2>&1
+        echo "== BLUB_PCG=$v"; grep -E "after|solve_|total|Error|error" $OUT/session_timeline_pcg_$v.txt
+    done
+fi
